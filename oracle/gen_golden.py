@@ -1,0 +1,238 @@
+"""Generate the committed golden vectors under tests/golden/ by running the REFERENCE'S OWN CODE.
+
+TEST INFRASTRUCTURE ONLY.  Runs in the build container (needs /root/reference, read-only); the GPU
+box never runs this.  The reference's files are imported verbatim from where they lie:
+
+  * ``pipelines/context.py``               (stand-alone, numpy only)          -> context_windows.json
+  * ``modules/{unet_3d,unet_3d_blocks,transformer_3d,attention,motion_module,resnet,
+     mutual_self_attention}.py``           (over oracle/diffusers_shim)        -> unet_small.pt
+  * ``pipelines/v_express_pipeline.py``    (over the shim; DDIM + VAE decoder restated) -> pipeline_small.pt
+
+Inputs/weights are NOT stored: they are regenerated from seeds by ``oracle.vx_oracle.synth_*``.
+Usage:  python oracle/gen_golden.py
+"""
+import importlib
+import importlib.util
+import json
+import os
+import sys
+import types
+
+import torch
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+REF = os.environ.get("VX_REFERENCE", "/root/reference")
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle", "diffusers_shim"))
+from oracle import vx_oracle as O  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def import_reference():
+    """Register empty ``modules`` / ``pipelines`` packages whose __path__ points into the read-only
+    reference tree so their files import verbatim without running the package __init__ (which pulls
+    the UNet2D's wide diffusers import surface)."""
+    for name in ("modules", "pipelines"):
+        m = types.ModuleType(name)
+        m.__path__ = [os.path.join(REF, name)]
+        sys.modules[name] = m
+    msa = importlib.import_module("modules.mutual_self_attention")
+    sys.modules["modules"].ReferenceAttentionControl = msa.ReferenceAttentionControl
+    unet3d = importlib.import_module("modules.unet_3d")
+    ctx = importlib.import_module("pipelines.context")
+    pipe = importlib.import_module("pipelines.v_express_pipeline")
+    return msa, unet3d, ctx, pipe
+
+
+UNET_EXTRA = dict(  # inference_v2.yaml:1-21
+    use_inflated_groupnorm=True, unet_use_cross_frame_attention=False, unet_use_temporal_attention=False,
+    use_motion_module=True, motion_module_resolutions=[1, 2, 4, 8], motion_module_mid_block=True,
+    motion_module_decoder_only=False, motion_module_type="Vanilla",
+    motion_module_kwargs=dict(num_attention_heads=8, num_transformer_block=1,
+                              attention_block_types=["Temporal_Self", "Temporal_Self"],
+                              temporal_position_encoding=True, temporal_position_encoding_max_len=32,
+                              temporal_attention_dim_div=1))
+
+
+def build_reference_unet(unet3d, cfg, sd):
+    model = unet3d.UNet3DConditionModel(
+        sample_size=64, in_channels=4, out_channels=4,
+        down_block_types=("CrossAttnDownBlock3D", "CrossAttnDownBlock3D", "CrossAttnDownBlock3D", "DownBlock3D"),
+        mid_block_type="UNetMidBlock3DCrossAttn",
+        up_block_types=("UpBlock3D", "CrossAttnUpBlock3D", "CrossAttnUpBlock3D", "CrossAttnUpBlock3D"),
+        block_out_channels=cfg["block_out_channels"], layers_per_block=2, cross_attention_dim=cfg["cross_attention_dim"],
+        attention_head_dim=8, norm_num_groups=32, norm_eps=1e-5, **UNET_EXTRA)
+    ref_sd = model.state_dict()
+    assert set(ref_sd) == set(sd), (sorted(set(ref_sd) ^ set(sd))[:10])
+    for k in ref_sd:
+        assert tuple(ref_sd[k].shape) == tuple(sd[k].shape), k
+    model.load_state_dict(sd, strict=True)
+    return model.eval()
+
+
+def install_reader(msa, model, banks, ref_w, audio_w, do_cfg=True):
+    reader = msa.ReferenceAttentionControl(model, do_classifier_free_guidance=do_cfg, mode="read", batch_size=1,
+                                           fusion_blocks="full", reference_attention_weight=ref_w,
+                                           audio_attention_weight=audio_w)
+    # same selection + stable sort as ReferenceAttentionControl.update (mutual_self_attention.py:339-351)
+    from modules.attention import TemporalBasicTransformerBlock
+    mods = [m for m in msa.torch_dfs(model) if isinstance(m, TemporalBasicTransformerBlock)]
+    mods = sorted(mods, key=lambda x: -x.norm1.normalized_shape[0])
+    names = {id(m): n for n, m in model.named_modules()}
+    order = [names[id(m)].replace(".transformer_blocks.0", "") for m in mods]
+    for m, bk in zip(mods, banks):
+        m.bank = [bk.clone()]
+    return reader, order
+
+
+def gen_context(ctx):
+    cases = [(4, 24, 4), (16, 16, 8), (96, 16, 8), (384, 16, 8), (924, 24, 4), (20, 16, 4), (100, 16, 8),
+             (40, 16, 8), (12, 8, 4), (33, 24, 4)]
+    out = []
+    for L, S, Ov in cases:
+        wins = list(ctx.uniform(step=0, num_frames=L, context_size=S, context_stride=1, context_overlap=Ov,
+                                closed_loop=False))
+        nfc = torch.zeros(L, dtype=torch.long)
+        for w in wins:
+            nfc[w] += 1  # the reference's own index-put (v_express_pipeline.py:498-500)
+        out.append(dict(L=L, S=S, O=Ov, windows=[[int(e) for e in w] for w in wins], num_frame_context=nfc.tolist()))
+    # other scheduler-call flavours (step != 0, stride > 1, closed loop) to pin `uniform` itself
+    extra = []
+    for (step, L, S, stride, Ov, closed) in [(1, 64, 16, 3, 4, True), (5, 48, 16, 2, 4, True), (3, 100, 24, 3, 4, False)]:
+        wins = list(ctx.uniform(step, L, S, stride, Ov, closed))
+        extra.append(dict(step=step, L=L, S=S, stride=stride, O=Ov, closed=closed,
+                          windows=[[int(e) for e in w] for w in wins]))
+    oh = {str(v): ctx.ordered_halving(v) for v in (0, 1, 2, 3, 5, 8, 1000, 2 ** 63)}
+    with open(os.path.join(GOLD, "context_windows.json"), "w") as f:
+        json.dump(dict(pipeline_calls=out, uniform_calls=extra, ordered_halving=oh), f)
+    print("context_windows.json:", len(out), "+", len(extra), "cases")
+
+
+def gen_unet(msa, unet3d):
+    torch.manual_seed(0)
+    cfg = O.small_cfg()
+    sd = O.synth_state_dict(O.unet_param_shapes(cfg), seed=1234)
+    model = build_reference_unet(unet3d, cfg, sd)
+    f, h = 4, 16
+    latents, kps, audio, banks = O.synth_inputs(cfg, L=f, h=h, w=h, do_cfg=True, seed=42)
+    reader, order = install_reader(msa, model, banks, 0.95, 3.0)
+    assert order == O.bank_order(cfg), (order, O.bank_order(cfg))
+    taps = {}
+    want = ["down_blocks.0.resnets.0", "down_blocks.0.attentions.0", "down_blocks.0.motion_modules.0",
+            "down_blocks.1.attentions.1", "down_blocks.3.motion_modules.1", "mid_block",
+            "up_blocks.1.attentions.2", "up_blocks.3.motion_modules.2"]
+    mods = dict(model.named_modules())
+    hooks = []
+    for n in want:
+        def mk(n):
+            def hook(_m, _i, out):
+                t = out.sample if hasattr(out, "sample") else out
+                taps[n] = t.detach().permute(0, 2, 1, 3, 4).reshape(-1, t.shape[1], *t.shape[3:]).clone()
+            return hook
+        hooks.append(mods[n].register_forward_hook(mk(n)))
+    x = latents.repeat(2, 1, 1, 1, 1)
+    enc = audio.reshape(-1, 5, cfg["cross_attention_dim"])
+    with torch.no_grad():
+        out = model(x, torch.tensor(499), encoder_hidden_states=enc, kps_features=kps, return_dict=False)[0]
+        for hk in hooks:   # taps belong to the t=499 call only
+            hk.remove()
+        out2 = model(x, 959, encoder_hidden_states=enc, kps_features=kps, return_dict=False)[0]
+    torch.save(dict(cfg=cfg, seed_weights=1234, seed_inputs=42, f=f, h=h, ref_w=0.95, audio_w=3.0,
+                    bank_order=order, out_t499=out, out_t959=out2,
+                    taps={k: v.half() for k, v in taps.items()}),
+               os.path.join(GOLD, "unet_small.pt"))
+    print("unet_small.pt: out", tuple(out.shape), "absmean", out.abs().mean().item())
+
+
+def gen_pipeline(msa, unet3d, pipe):
+    cfg = O.small_cfg()
+    vcfg = O.small_vae_cfg()
+    sd = O.synth_state_dict(O.unet_param_shapes(cfg), seed=1234)
+    vsd = O.synth_state_dict(O.vae_param_shapes(vcfg), seed=1235)
+    model = build_reference_unet(unet3d, cfg, sd)
+    L, h, S, Ov, steps, gs = 12, 16, 8, 4, 3, 3.5
+    latents, kps, audio, banks = O.synth_inputs(cfg, L=L, h=h, w=h, do_cfg=True, seed=42)
+    from diffusers import AutoencoderKL, DDIMScheduler
+    vae = AutoencoderKL(vsd, vcfg)
+
+    class StubRefNet(torch.nn.Module):
+        """Stands in for the ReferenceNet write pass (out of scope)."""
+        def __init__(self):
+            super().__init__()
+            self.p = torch.nn.Parameter(torch.zeros(1))
+
+        def forward(self, *a, **k):
+            return None
+
+    class Pipe(pipe.VExpressPipeline):
+        # only the three prologue methods are overridden (v_express_pipeline.py:343-407)
+        def prepare_reference_latent(self, *a, **k):
+            return torch.zeros(1, 4, h, h)
+
+        def prepare_kps_feature(self, *a, **k):
+            return kps
+
+        def prepare_audio_embeddings(self, *a, **k):
+            return audio
+
+        def prepare_latents(self, *a, **k):
+            return latents.clone() * self.scheduler.init_noise_sigma
+
+    # the pipeline constructs its own reader; make `update` a bank injection in pairing order
+    real_update = msa.ReferenceAttentionControl.update
+
+    def update(self, writer, do_classifier_free_guidance=True, do_unconditional_forward=False, dtype=torch.float16):
+        from modules.attention import TemporalBasicTransformerBlock
+        mods = [m for m in msa.torch_dfs(self.unet) if isinstance(m, TemporalBasicTransformerBlock)]
+        mods = sorted(mods, key=lambda x: -x.norm1.normalized_shape[0])
+        for m, bk in zip(mods, banks):
+            m.bank = [bk.clone().to(dtype)]
+    msa.ReferenceAttentionControl.update = update
+    try:
+        p = Pipe(vae=vae, reference_net=StubRefNet(), denoising_unet=model, v_kps_guider=None, audio_processor=None,
+                 audio_encoder=None, audio_projection=None, scheduler=DDIMScheduler())
+        captured = {}
+        orig_decode = Pipe.decode_latents
+
+        def decode(self, lat):
+            captured["latents"] = lat.clone()
+            return orig_decode(self, lat)
+        Pipe.decode_latents = decode
+        with torch.no_grad():
+            video = p(reference_image=None, kps_images=None, audio_waveform=None, width=h * 8, height=h * 8,
+                      video_length=L, num_inference_steps=steps, guidance_scale=gs, context_frames=S,
+                      context_overlap=Ov, reference_attention_weight=0.95, audio_attention_weight=3.0)
+    finally:
+        msa.ReferenceAttentionControl.update = real_update
+    torch.save(dict(cfg=cfg, vae_cfg=vcfg, L=L, h=h, S=S, O=Ov, steps=steps, guidance_scale=gs,
+                    final_latents=captured["latents"], video=video.half()),
+               os.path.join(GOLD, "pipeline_small.pt"))
+    print("pipeline_small.pt: video", tuple(video.shape), "latents absmean", captured["latents"].abs().mean().item())
+
+
+def gen_ddim():
+    """Known-answer values of the restated DDIM -- self-pins, cross-checked
+    against the constants quoted in the survey."""
+    s = O.DDIM()
+    kat = dict(abar={str(i): float(s.alphas_cumprod[i]) for i in (0, 1, 499, 959, 998, 999)})
+    for n in (2, 25, 50):
+        s.set_timesteps(n)
+        kat[f"timesteps_{n}"] = s.timesteps.tolist()
+    s.set_timesteps(25)
+    x = torch.tensor([1.5409961, -0.2934289, -2.1787894, 0.5684313])
+    v = torch.tensor([-1.0845224, -1.3985955, 0.4033468, 0.8380263])
+    kat["step_t999_n25"] = s.step(v, 999, x).prev_sample.tolist()
+    with open(os.path.join(GOLD, "ddim_kat.json"), "w") as f:
+        json.dump(kat, f)
+    print("ddim_kat.json", kat["step_t999_n25"])
+
+
+if __name__ == "__main__":
+    os.makedirs(GOLD, exist_ok=True)
+    torch.set_num_threads(os.cpu_count())
+    msa, unet3d, ctx, pipe = import_reference()
+    gen_context(ctx)
+    gen_ddim()
+    gen_unet(msa, unet3d)
+    gen_pipeline(msa, unet3d, pipe)

@@ -1,0 +1,93 @@
+"""The CPU oracle (oracle/vx_oracle.py) against golden vectors produced by the reference's own code
+(oracle/gen_golden.py).  No GPU."""
+import json
+import os
+
+import numpy as np
+import torch
+
+from oracle import vx_oracle as O
+
+
+def test_context_windows_bit_exact(golden_dir):
+    g = json.load(open(os.path.join(golden_dir, "context_windows.json")))
+    for c in g["pipeline_calls"]:
+        wins = O.context_windows(c["L"], c["S"], c["O"])
+        assert wins == c["windows"], c
+        assert O.num_frame_context(wins, c["L"]).tolist() == c["num_frame_context"], c
+    for c in g["uniform_calls"]:
+        wins = list(O.uniform(c["step"], c["L"], c["S"], c["stride"], c["O"], c["closed"]))
+        assert wins == c["windows"], c
+    for k, v in g["ordered_halving"].items():
+        assert O.ordered_halving(int(k)) == v
+
+
+def test_context_survey_table():
+    # SURVEY.md Appendix D
+    for (L, S, Ov, nwin, total) in [(4, 24, 4, 1, 4), (16, 16, 8, 1, 16), (96, 16, 8, 11, 176),
+                                    (384, 16, 8, 47, 752), (924, 24, 4, 46, 1104), (20, 16, 4, 2, 32),
+                                    (100, 16, 8, 12, 192)]:
+        w = O.context_windows(L, S, Ov)
+        assert len(w) == nwin and sum(len(x) for x in w) == total
+        c = O.num_frame_context(w, L)
+        assert c.min() == 1 and c.max() <= 2
+
+
+def test_ddim_known_answers(golden_dir):
+    g = json.load(open(os.path.join(golden_dir, "ddim_kat.json")))
+    s = O.DDIM()
+    # constants quoted in SURVEY.md Appendix B.5
+    assert abs(float(s.alphas_cumprod[0]) - 0.99914998) < 1e-7
+    assert abs(float(s.alphas_cumprod[499]) - 0.24235900) < 1e-7
+    assert float(s.alphas_cumprod[999]) == 0.0
+    for n, first, last in ((25, 999, 39), (50, 999, 19), (2, 999, 499)):
+        s.set_timesteps(n)
+        assert s.timesteps.tolist() == g[f"timesteps_{n}"]
+        assert s.timesteps[0] == first and s.timesteps[-1] == last
+    s.set_timesteps(25)
+    x = torch.tensor([1.5409961, -0.2934289, -2.1787894, 0.5684313])
+    v = torch.tensor([-1.0845224, -1.3985955, 0.4033468, 0.8380263])
+    out = s.step(v, 999, x).prev_sample
+    np.testing.assert_allclose(out.numpy(), [1.5617130, -0.2662846, -2.1861930, 0.5520930], atol=1e-6)
+
+
+def test_param_layout_full_width():
+    S = O.unet_param_shapes(O.DEFAULT_CFG)
+    assert len(S) == 1386
+    assert sum(int(np.prod(v)) for v in S.values()) == 1363537604
+    mm = sum(int(np.prod(v)) for k, v in S.items() if "motion_modules" in k)
+    assert abs(mm / 1e6 - 454.42) < 0.01
+    assert S["up_blocks.1.resnets.2.conv1.weight"] == (1280, 1920, 3, 3)
+    assert S["down_blocks.1.resnets.0.conv_shortcut.weight"] == (640, 320, 1, 1)
+
+
+def test_unet_forward_matches_reference(golden_dir):
+    g = torch.load(os.path.join(golden_dir, "unet_small.pt"), weights_only=False)
+    cfg = g["cfg"]
+    sd = O.synth_state_dict(O.unet_param_shapes(cfg), g["seed_weights"])
+    lat, kps, audio, banks = O.synth_inputs(cfg, g["f"], g["h"], g["h"], True, g["seed_inputs"])
+    assert g["bank_order"] == O.bank_order(cfg)
+    x = lat.repeat(2, 1, 1, 1, 1)
+    enc = audio.reshape(-1, 5, cfg["cross_attention_dim"])
+    taps = {}
+    with torch.no_grad():
+        out = O.unet_forward(sd, cfg, x, 499, enc, kps, banks, g["ref_w"], g["audio_w"], taps=taps)
+        out2 = O.unet_forward(sd, cfg, x, 959, enc, kps, banks, g["ref_w"], g["audio_w"])
+    torch.testing.assert_close(out, g["out_t499"], atol=2e-4, rtol=1e-4)
+    torch.testing.assert_close(out2, g["out_t959"], atol=2e-4, rtol=1e-4)
+    for k, v in g["taps"].items():
+        torch.testing.assert_close(taps[k], v.float(), atol=2e-2, rtol=2e-3)   # taps stored in fp16
+
+
+def test_pipeline_matches_reference(golden_dir):
+    g = torch.load(os.path.join(golden_dir, "pipeline_small.pt"), weights_only=False)
+    cfg, vcfg = g["cfg"], g["vae_cfg"]
+    sd = O.synth_state_dict(O.unet_param_shapes(cfg), 1234)
+    vsd = O.synth_state_dict(O.vae_param_shapes(vcfg), 1235)
+    lat, kps, audio, banks = O.synth_inputs(cfg, g["L"], g["h"], g["h"], True, 42)
+    with torch.no_grad():
+        final = O.denoise(sd, cfg, lat, kps, audio, banks, g["steps"], g["guidance_scale"], g["S"], g["O"], 0.95, 3.0)
+        torch.testing.assert_close(final, g["final_latents"], atol=5e-4, rtol=1e-4)
+        video = O.decode_latents(vsd, vcfg, final)
+    assert video.shape == g["video"].shape and video.dtype == torch.float32
+    torch.testing.assert_close(video, g["video"].float(), atol=2e-3, rtol=0)
