@@ -1,0 +1,63 @@
+"""tcgen05 GEMM / implicit-GEMM conv against torch fp32 on the same bf16-rounded inputs (GPU)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return ((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-12)).item()
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from vexpress_b200 import _ffi, ops
+    _ffi.require_sm100()
+    return ops
+
+
+@pytest.mark.parametrize("M,N,K,bn", [(128, 64, 64, 64), (256, 128, 128, 128), (512, 320, 320, 160),
+                                      (4096, 1280, 1280, 256), (160, 640, 768, 0), (2048, 2560, 320, 0),
+                                      (131072, 320, 320, 0), (300, 96, 200, 0)])
+def test_gemm_plain(ops, M, N, K, bn):
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).bfloat16()
+    out = ops.gemm(a, w, block_n=bn)
+    ref = a.float() @ w.float().t()
+    torch.cuda.synchronize()
+    err = _rel(out, ref)
+    print(f"gemm {M}x{N}x{K} bn={bn} rel={err:.3e}")
+    assert err < 5e-3, err          # bf16 output rounding ~ 2^-9 relative
+
+
+def test_gemm_epilogue_and_splitk(ops):
+    g = torch.Generator(device="cuda").manual_seed(7)
+    M, K1, K2, N = 1024, 640, 320, 640
+    a = torch.randn(M, K1, device="cuda", generator=g).bfloat16()
+    a2 = torch.randn(M, K2, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(N, K1 + K2, device="cuda", generator=g) / 30).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    bias2 = torch.randn(4, N, device="cuda", generator=g)
+    res = torch.randn(M, N, device="cuda", generator=g).bfloat16()
+    out = ops.gemm(a, w, bias, a2=a2, bias2=bias2, bias2_div=256, scale=0.95, residual=res)
+    ref = (torch.cat([a, a2], 1).float() @ w.float().t() + bias + bias2.repeat_interleave(256, 0)) * 0.95 + res.float()
+    err = _rel(out, ref)
+    print("gemm epilogue rel", err)
+    assert err < 5e-3
+
+
+@pytest.mark.parametrize("NB,H,W,C,Cout", [(2, 64, 64, 64, 64), (4, 32, 32, 128, 256), (4, 16, 16, 256, 320),
+                                           (6, 8, 8, 128, 128), (32, 64, 64, 320, 320), (1, 256, 256, 128, 128),
+                                           (2, 8, 8, 2560, 1280)])
+def test_conv3x3(ops, NB, H, W, C, Cout):
+    g = torch.Generator(device="cuda").manual_seed(NB * H + C)
+    x = torch.randn(NB, H, W, C, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(Cout, C, 3, 3, device="cuda", generator=g) / (9 * C) ** 0.5).bfloat16()
+    bias = torch.randn(Cout, device="cuda", generator=g)
+    out = ops.conv3x3(x, ops.pack_conv3x3_weight(w), bias)
+    ref = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2).float(), w.float(), bias, padding=1)
+    ref = ref.permute(0, 2, 3, 1).reshape(-1, Cout)
+    err = _rel(out, ref)
+    print(f"conv {NB}x{H}x{W}x{C}->{Cout} rel={err:.3e}")
+    assert err < 5e-3

@@ -1,0 +1,46 @@
+"""ctypes binding of the C-ABI library ``libvxb200.so`` (declared in include/vxb200.h).
+
+There is no fallback: if the library is missing or the device is not sm_100, loading raises."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libvxb200.so")
+
+_lib = None
+
+c_int, c_ll, c_float, c_void_p = ctypes.c_int, ctypes.c_longlong, ctypes.c_float, ctypes.c_void_p
+
+
+class VxError(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise VxError(f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(there is no CPU/PyTorch fallback)")
+        _lib = ctypes.CDLL(LIB_PATH)
+        _lib.vx_last_error.restype = ctypes.c_char_p
+    return _lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        raise VxError(f"{what}: {lib().vx_last_error().decode()}")
+
+
+def ptr(t):
+    """Raw device/host pointer of a torch tensor (or None)."""
+    return c_void_p(0 if t is None else t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_sm100():
+    check(lib().vx_require_sm100(), "vx_require_sm100")

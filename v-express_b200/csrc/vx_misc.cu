@@ -1,0 +1,371 @@
+// Small kernels around the GEMM/conv/attention core (all HBM- or latency-bound, CUDA cores):
+//   * conv_in  : 3x3 conv from Cin<=8 planar (n,c,h,w)/(b,c,f,h,w) input to NHWC bf16, + bias + kps_features
+//                (reference modules/unet_3d.py:485-487; also the VAE decoder conv_in).
+//   * conv_out : 3x3 conv from NHWC bf16 to Cout<=4 planar output (reference modules/unet_3d.py:573; VAE conv_out
+//                with the (x/2+0.5).clamp(0,1) of pipelines/v_express_pipeline.py:160 fused).
+//   * im2col for the stride-2 Downsample3D conv (modules/resnet.py:93-120), nearest-2x Upsample3D (:53-82).
+//   * skinny linear for the time embedding MLP and the 22 time_emb_proj (modules/unet_3d.py:464-470,
+//     modules/resnet.py:225-228): rows <= 8, one warp per output feature.
+//   * CFG + /count + overlap accumulation and the DDIM update (pipelines/v_express_pipeline.py:548-572).
+#include "vx_host.h"
+#include "vx_ptx.cuh"
+
+namespace vx {
+
+// ------------------------------------------------------------------ conv_in
+// in: planar, element (img n, ch c, y, x) at in[n*sn + c*sc + y*W + x]  (bf16)
+// w: fp32 [Cout][Cin*9] ; out NHWC [n*H*W + y*W + x][Cout]
+// addend (optional): NHWC bf16 rows indexed by add_row[n] (frame gather) or n when add_row == null
+struct ConvInArgs {
+  const __nv_bfloat16* in; long long sn, sc;
+  int NB, H, W, Cin, Cout;
+  const float* w; const float* bias;
+  const __nv_bfloat16* addend; const int* add_frame; long long add_ld;
+  __nv_bfloat16* out; long long ldo;
+};
+
+__global__ void conv_in_kernel(const ConvInArgs p) {
+  extern __shared__ float sw[];  // [Cin*9][Cout] transposed for conflict-free reads
+  const int K = p.Cin * 9;
+  for (int i = threadIdx.x; i < K * p.Cout; i += blockDim.x) {
+    const int co = i / K, kk = i % K;
+    sw[kk * p.Cout + co] = p.w[i];
+  }
+  __syncthreads();
+  const int vecs = p.Cout / 8;
+  const long long total = (long long)p.NB * p.H * p.W * vecs;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(idx % vecs);
+    const long long pix = idx / vecs;
+    const int x = (int)(pix % p.W);
+    const int y = (int)((pix / p.W) % p.H);
+    const int n = (int)(pix / ((long long)p.W * p.H));
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = p.bias ? p.bias[cv * 8 + i] : 0.f;
+    for (int c = 0; c < p.Cin; ++c) {
+      const __nv_bfloat16* plane = p.in + n * p.sn + c * p.sc;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
+        if (yy < 0 || yy >= p.H || xx < 0 || xx >= p.W) continue;
+        const float v = __bfloat162float(plane[yy * p.W + xx]);
+        const float* wr = sw + (c * 9 + t) * p.Cout + cv * 8;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += v * wr[i];
+      }
+    }
+    if (p.addend) {
+      const long long arow = (p.add_frame ? (long long)p.add_frame[n] : (long long)n) * p.H * p.W + (long long)y * p.W + x;
+      const uint4 u = *reinterpret_cast<const uint4*>(p.addend + arow * p.add_ld + cv * 8);
+      const uint32_t ww[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 t = unpack_bf16(ww[i]);
+        acc[2 * i] += t.x;
+        acc[2 * i + 1] += t.y;
+      }
+    }
+    *reinterpret_cast<uint4*>(p.out + pix * p.ldo + cv * 8) = make_uint4(
+        pack_bf16(acc[0], acc[1]), pack_bf16(acc[2], acc[3]), pack_bf16(acc[4], acc[5]), pack_bf16(acc[6], acc[7]));
+  }
+}
+
+// ------------------------------------------------------------------ conv_out
+// x NHWC bf16 [NB*H*W, C] (already normalised + SiLU) ; w fp32 [Cout][9][C] ; one warp per output pixel.
+// out planar: element (n, co, y, x) at out[n*sn + co*sc + y*W + x]; out_f32 selects fp32 vs bf16 storage;
+// post = 1 applies (v/2 + 0.5).clamp(0,1).
+struct ConvOutArgs {
+  const __nv_bfloat16* x; long long ldx;
+  int NB, H, W, C, Cout;
+  const float* w; const float* bias;
+  void* out; long long sn, sc; int out_f32, post;
+};
+
+__global__ void conv_out_kernel(const ConvOutArgs p) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long npix = (long long)p.NB * p.H * p.W;
+  if (warp >= npix) return;
+  const int x = (int)(warp % p.W);
+  const int y = (int)((warp / p.W) % p.H);
+  const long long n = warp / ((long long)p.W * p.H);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const int vecs = p.C / 8;
+  for (int t = 0; t < 9; ++t) {
+    const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
+    if (yy < 0 || yy >= p.H || xx < 0 || xx >= p.W) continue;
+    const __nv_bfloat16* row = p.x + ((n * p.H + yy) * p.W + xx) * p.ldx;
+    for (int v = lane; v < vecs; v += 32) {
+      const uint4 u = *reinterpret_cast<const uint4*>(row + v * 8);
+      const uint32_t ww[4] = {u.x, u.y, u.z, u.w};
+      float f[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 tt = unpack_bf16(ww[i]);
+        f[2 * i] = tt.x;
+        f[2 * i + 1] = tt.y;
+      }
+      for (int co = 0; co < p.Cout; ++co) {
+        const float* wr = p.w + ((long long)co * 9 + t) * p.C + v * 8;
+        const float4 w0 = *reinterpret_cast<const float4*>(wr);
+        const float4 w1 = *reinterpret_cast<const float4*>(wr + 4);
+        acc[co] += f[0] * w0.x + f[1] * w0.y + f[2] * w0.z + f[3] * w0.w + f[4] * w1.x + f[5] * w1.y + f[6] * w1.z +
+                   f[7] * w1.w;
+      }
+    }
+  }
+#pragma unroll
+  for (int co = 0; co < 4; ++co)
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc[co] += __shfl_xor_sync(0xffffffffu, acc[co], o);
+  if (lane < p.Cout) {
+    float v = acc[0];
+    if (lane == 1) v = acc[1];
+    if (lane == 2) v = acc[2];
+    if (lane == 3) v = acc[3];
+    v += p.bias ? p.bias[lane] : 0.f;
+    if (p.post) v = fminf(fmaxf(v * 0.5f + 0.5f, 0.f), 1.f);
+    const long long off = n * p.sn + lane * p.sc + (long long)y * p.W + x;
+    if (p.out_f32) reinterpret_cast<float*>(p.out)[off] = v;
+    else reinterpret_cast<__nv_bfloat16*>(p.out)[off] = __float2bfloat16(v);
+  }
+}
+
+// ------------------------------------------------------------------ im2col (3x3, stride 2, pad 1), NHWC
+__global__ void im2col_s2_kernel(const __nv_bfloat16* __restrict__ x, int NB, int H, int W, int C,
+                                 __nv_bfloat16* __restrict__ out) {
+  const int Ho = H / 2, Wo = W / 2, V = C / 8;
+  const long long total = (long long)NB * Ho * Wo * 9 * V;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(idx % V);
+    const int t = (int)((idx / V) % 9);
+    const long long opix = idx / ((long long)V * 9);
+    const int ox = (int)(opix % Wo), oy = (int)((opix / Wo) % Ho);
+    const long long n = opix / ((long long)Wo * Ho);
+    const int yy = oy * 2 + t / 3 - 1, xx = ox * 2 + t % 3 - 1;
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (yy >= 0 && yy < H && xx >= 0 && xx < W)
+      val = *reinterpret_cast<const uint4*>(x + ((n * H + yy) * W + xx) * C + v * 8);
+    *reinterpret_cast<uint4*>(out + opix * 9 * C + (long long)t * C + v * 8) = val;
+  }
+}
+
+// ------------------------------------------------------------------ nearest 2x upsample, NHWC
+__global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ x, int NB, int H, int W, int C,
+                                  __nv_bfloat16* __restrict__ out) {
+  const int V = C / 8;
+  const long long total = (long long)NB * 2 * H * 2 * W * V;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(idx % V);
+    const long long opix = idx / V;
+    const int ox = (int)(opix % (2 * W)), oy = (int)((opix / (2 * W)) % (2 * H));
+    const long long n = opix / ((long long)4 * W * H);
+    *reinterpret_cast<uint4*>(out + opix * C + v * 8) =
+        *reinterpret_cast<const uint4*>(x + ((n * H + oy / 2) * W + ox / 2) * C + v * 8);
+  }
+}
+
+// ------------------------------------------------------------------ skinny linear (rows <= 8)
+// y[r, n] = act_out( sum_k act_in(x[r,k]) * W[n,k] + b[n] );  act: 0 none, 1 SiLU.  x,y fp32; W bf16.
+__global__ void skinny_linear_kernel(const float* __restrict__ x, int rows, int K, const __nv_bfloat16* __restrict__ w,
+                                     const float* __restrict__ bias, int N, int act_in, int act_out,
+                                     float* __restrict__ y) {
+  const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (n >= N) return;
+  float acc[8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) acc[r] = 0.f;
+  for (int k = lane * 8; k < K; k += 256) {
+    float wv[8];
+    const uint4 u = *reinterpret_cast<const uint4*>(w + (long long)n * K + k);
+    const uint32_t ww[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 t = unpack_bf16(ww[i]);
+      wv[2 * i] = t.x;
+      wv[2 * i + 1] = t.y;
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      if (r < rows) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float xv = x[r * K + k + i];
+          if (act_in) xv = xv / (1.f + __expf(-xv));
+          acc[r] += xv * wv[i];
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 8; ++r)
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
+  if (lane == 0) {
+    for (int r = 0; r < rows; ++r) {
+      float v = acc[r] + (bias ? bias[n] : 0.f);
+      if (act_out) v = v / (1.f + __expf(-v));
+      y[(long long)r * N + n] = v;
+    }
+  }
+}
+
+// Timesteps(dim, flip_sin_to_cos=True, shift 0): out[r] = [cos(t*f_i) | sin(t*f_i)], rounded through bf16 like the
+// reference's cast to the model dtype (modules/unet_3d.py:469).
+__global__ void timestep_embed_kernel(const float* __restrict__ t, int rows, int dim, float* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int half = dim / 2;
+  if (idx >= rows * half) return;
+  const int r = idx / half, i = idx % half;
+  const float freq = expf(-logf(10000.f) * (float)i / (float)half);
+  const float a = t[r] * freq;
+  out[r * dim + i] = __bfloat162float(__float2bfloat16(cosf(a)));
+  out[r * dim + half + i] = __bfloat162float(__float2bfloat16(sinf(a)));
+}
+
+// ------------------------------------------------------------------ CFG + /count + overlap accumulate
+// noise: planar bf16 (b, 4, f, h, w) from the UNet; for local frame i -> global frame win[i]:
+//   acc[:, win[i]] += bf16( bf16(u + g*(c-u)) / count[win[i]] )     (same rounding points as the reference's
+//   model-dtype arithmetic, pipelines/v_express_pipeline.py:548-560)
+struct CfgArgs {
+  const __nv_bfloat16* noise; int f, hw, L, do_cfg;
+  const int* win; const int* count; float g;
+  float* acc;  // fp32 (4, L, hw) accumulator holding bf16-representable partial sums
+};
+
+__device__ __forceinline__ float rbf(float v) { return __bfloat162float(__float2bfloat16(v)); }
+
+__global__ void cfg_overlap_kernel(const CfgArgs p) {
+  const long long total = (long long)4 * p.f * p.hw;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int px = (int)(idx % p.hw);
+    const int i = (int)((idx / p.hw) % p.f);
+    const int c = (int)(idx / ((long long)p.hw * p.f));
+    const long long off = ((long long)c * p.f + i) * p.hw + px;
+    float v;
+    if (p.do_cfg) {
+      const float u = __bfloat162float(p.noise[off]);
+      const float cd = __bfloat162float(p.noise[(long long)4 * p.f * p.hw + off]);
+      v = rbf(u + rbf(p.g * rbf(cd - u)));
+    } else {
+      v = __bfloat162float(p.noise[off]);
+    }
+    const int fr = p.win[i];
+    v = rbf(v / (float)p.count[fr]);
+    float* a = p.acc + ((long long)c * p.L + fr) * p.hw + px;
+    *a = rbf(*a + v);
+  }
+}
+
+// DDIM v-prediction step on all frames (eta = 0), bf16 rounding after every tensor op like the reference
+// (diffusers DDIMScheduler.step with fp32 scalar coefficients on model-dtype tensors).
+__global__ void ddim_step_kernel(__nv_bfloat16* __restrict__ latents, const float* __restrict__ acc, long long n,
+                                 float sa, float sb, float sap, float sbp) {
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const float x = __bfloat162float(latents[idx]);
+    const float v = acc[idx];
+    const float x0 = rbf(rbf(sa * x) - rbf(sb * v));
+    const float eps = rbf(rbf(sa * v) + rbf(sb * x));
+    const float dir = rbf(sbp * eps);
+    latents[idx] = __float2bfloat16(rbf(sap * x0) + dir);
+  }
+}
+
+}  // namespace vx
+
+using namespace vx;
+
+extern "C" int vx_conv_in(const void* in, long long sn, long long sc, int NB, int H, int W, int Cin, int Cout,
+                          const float* w, const float* bias, const void* addend, const int* add_frame,
+                          long long add_ld, void* out, long long ldo, void* stream) {
+  VX_REQUIRE(Cout % 8 == 0 && Cin * 9 * Cout * 4 <= 200 * 1024, "vx_conv_in: Cin=%d Cout=%d unsupported", Cin, Cout);
+  ConvInArgs a{(const __nv_bfloat16*)in, sn, sc, NB, H, W, Cin, Cout, w, bias, (const __nv_bfloat16*)addend, add_frame,
+               add_ld, (__nv_bfloat16*)out, ldo};
+  const size_t smem = (size_t)Cin * 9 * Cout * 4;
+  static bool cfg = false;
+  if (!cfg) {
+    VX_CHECK_CUDA(cudaFuncSetAttribute(conv_in_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    cfg = true;
+  }
+  const long long total = (long long)NB * H * W * (Cout / 8);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  conv_in_kernel<<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(a);
+  VX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int vx_conv_out(const void* x, long long ldx, int NB, int H, int W, int C, int Cout, const float* w,
+                           const float* bias, void* out, long long sn, long long sc, int out_f32, int post,
+                           void* stream) {
+  VX_REQUIRE(C % 8 == 0 && Cout >= 1 && Cout <= 4, "vx_conv_out: C=%d Cout=%d unsupported", C, Cout);
+  ConvOutArgs a{(const __nv_bfloat16*)x, ldx, NB, H, W, C, Cout, w, bias, out, sn, sc, out_f32, post};
+  const long long npix = (long long)NB * H * W;
+  conv_out_kernel<<<(unsigned)((npix * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a);
+  VX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int vx_im2col_s2(const void* x, int NB, int H, int W, int C, void* out, void* stream) {
+  VX_REQUIRE(C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "vx_im2col_s2: bad shape");
+  const long long total = (long long)NB * (H / 2) * (W / 2) * 9 * (C / 8);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  im2col_s2_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, NB, H, W, C,
+                                                                      (__nv_bfloat16*)out);
+  VX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int vx_upsample2x(const void* x, int NB, int H, int W, int C, void* out, void* stream) {
+  VX_REQUIRE(C % 8 == 0, "vx_upsample2x: C=%d", C);
+  const long long total = (long long)NB * 4 * H * W * (C / 8);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  upsample2x_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, NB, H, W, C,
+                                                                       (__nv_bfloat16*)out);
+  VX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int vx_skinny_linear(const float* x, int rows, int K, const void* w, const float* bias, int N, int act_in,
+                                int act_out, float* y, void* stream) {
+  VX_REQUIRE(rows >= 1 && rows <= 8 && K % 8 == 0, "vx_skinny_linear: rows=%d K=%d", rows, K);
+  skinny_linear_kernel<<<(N * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(x, rows, K, (const __nv_bfloat16*)w, bias,
+                                                                              N, act_in, act_out, y);
+  VX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int vx_timestep_embed(const float* t, int rows, int dim, float* out, void* stream) {
+  const int n = rows * (dim / 2);
+  timestep_embed_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(t, rows, dim, out);
+  VX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int vx_cfg_overlap_accumulate(const void* noise, int f, int hw, int L, int do_cfg, const int* win,
+                                         const int* count, float guidance, float* acc, void* stream) {
+  CfgArgs a{(const __nv_bfloat16*)noise, f, hw, L, do_cfg, win, count, guidance, acc};
+  const long long total = (long long)4 * f * hw;
+  cfg_overlap_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a);
+  VX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int vx_ddim_step(void* latents, const float* acc, long long n, float sqrt_a, float sqrt_1ma,
+                            float sqrt_aprev, float sqrt_1maprev, void* stream) {
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  ddim_step_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)latents, acc, n, sqrt_a,
+                                                                      sqrt_1ma, sqrt_aprev, sqrt_1maprev);
+  VX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -1,0 +1,321 @@
+// HBM-bound normalisation / activation kernels on channels-last bf16 token matrices [rows, C]:
+//   * GroupNorm (per frame, 32 groups) as a deterministic two-kernel pair: partial statistics per
+//     (frame, pixel chunk, group), then finalise (Chan merge in fixed order) + apply (+ optional SiLU).
+//     Reads may come from TWO sources (x1 | x2 channel-concatenated): the `torch.cat([h, skip], 1)` of the
+//     up blocks (reference modules/unet_3d_blocks.py:694,831) is never materialised on its own.
+//     Reference: InflatedGroupNorm modules/resnet.py:20-28, ResnetBlock3D.forward :220-221,235-241,
+//     Transformer3DModel.forward modules/transformer_3d.py:124, TemporalTransformer3DModel modules/motion_module.py:156.
+//   * LayerNorm over C (eps 1e-5) with the optional sinusoidal positional-encoding add of the temporal
+//     attention (reference modules/motion_module.py:244,262-277,365-366; attention.py:329-333).
+//   * GEGLU gate: out = h * gelu_erf(gate) (diffusers FeedForward/GEGLU).
+// All loads/stores are 16-byte vectors, threads walk the contiguous channel dimension.
+#include "vx_host.h"
+#include "vx_ptx.cuh"
+
+namespace vx {
+
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&f)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = unpack_bf16(w[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&f)[8]) {
+  *reinterpret_cast<uint4*>(p) =
+      make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+}
+
+// ------------------------------------------------------------------ GroupNorm statistics
+// grid (S, NB); block = V*R threads (V = C/8 vectors per pixel, R pixel rows in flight).
+// partial[(n*S + s)*G + g] = {count, mean, M2}
+struct GnStatsArgs {
+  const __nv_bfloat16* x1; long long ld1; int C1;
+  const __nv_bfloat16* x2; long long ld2; int C2;
+  int HW, G, S, R;
+  float* partial;
+};
+
+__global__ void gn_stats_kernel(const GnStatsArgs p) {
+  extern __shared__ float sm[];  // [R][C] sums, [R][C] sumsq
+  const int C = p.C1 + p.C2;
+  const int V = C / 8;
+  const int n = blockIdx.y, s = blockIdx.x;
+  const int v = threadIdx.x % V, r = threadIdx.x / V;
+  const int chunk = (p.HW + p.S - 1) / p.S;
+  const int p0 = s * chunk;
+  const int p1 = min(p.HW, p0 + chunk);
+  float sum[8], sq[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sum[i] = sq[i] = 0.f;
+  const int c0 = v * 8;
+  const bool second = c0 >= p.C1;
+  const __nv_bfloat16* base = second ? p.x2 + (long long)n * p.HW * p.ld2 + (c0 - p.C1)
+                                     : p.x1 + (long long)n * p.HW * p.ld1 + c0;
+  const long long ld = second ? p.ld2 : p.ld1;
+  for (int px = p0 + r; px < p1; px += p.R) {
+    float f[8];
+    load8(base + px * ld, f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      sum[i] += f[i];
+      sq[i] += f[i] * f[i];
+    }
+  }
+  float* ssum = sm;
+  float* ssq = sm + p.R * C;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    ssum[r * C + c0 + i] = sum[i];
+    ssq[r * C + c0 + i] = sq[i];
+  }
+  __syncthreads();
+  const int cpg = C / p.G;
+  for (int g = threadIdx.x; g < p.G; g += blockDim.x) {
+    float a = 0.f, b = 0.f;
+    for (int rr = 0; rr < p.R; ++rr)
+      for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+        a += ssum[rr * C + c];
+        b += ssq[rr * C + c];
+      }
+    const float cnt = (float)(p1 - p0) * cpg;
+    const float mean = cnt > 0 ? a / cnt : 0.f;
+    const float m2 = cnt > 0 ? fmaxf(b - a * mean, 0.f) : 0.f;
+    float* o = p.partial + ((long long)(n * p.S + s) * p.G + g) * 3;
+    o[0] = cnt;
+    o[1] = mean;
+    o[2] = m2;
+  }
+}
+
+// ------------------------------------------------------------------ GroupNorm finalise + apply (+SiLU)
+struct GnApplyArgs {
+  const __nv_bfloat16* x1; long long ld1; int C1;
+  const __nv_bfloat16* x2; long long ld2; int C2;
+  int HW, G, S;
+  const float* partial;
+  const float* gamma; const float* beta;
+  float eps; int silu;
+  __nv_bfloat16* out; long long ldo;
+  int chunk;  // pixels per CTA
+};
+
+__global__ void gn_apply_kernel(const GnApplyArgs p) {
+  extern __shared__ float sm[];  // scale[C], shift[C], mean[G], rstd[G]
+  const int C = p.C1 + p.C2;
+  float* scale = sm;
+  float* shift = sm + C;
+  float* gmean = sm + 2 * C;
+  float* grstd = gmean + p.G;
+  const int n = blockIdx.y;
+  for (int g = threadIdx.x; g < p.G; g += blockDim.x) {
+    // Chan et al. parallel-variance merge of the S partials, always in the same order (deterministic)
+    float cnt = 0.f, mean = 0.f, m2 = 0.f;
+    for (int s = 0; s < p.S; ++s) {
+      const float* q = p.partial + ((long long)(n * p.S + s) * p.G + g) * 3;
+      const float cb = q[0];
+      if (cb <= 0.f) continue;
+      const float tot = cnt + cb;
+      const float delta = q[1] - mean;
+      mean += delta * (cb / tot);
+      m2 += q[2] + delta * delta * (cnt * cb / tot);
+      cnt = tot;
+    }
+    gmean[g] = mean;
+    grstd[g] = rsqrtf(m2 / cnt + p.eps);
+  }
+  __syncthreads();
+  const int cpg = C / p.G;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    const float sc = grstd[g] * p.gamma[c];
+    scale[c] = sc;
+    shift[c] = p.beta[c] - gmean[g] * sc;
+  }
+  __syncthreads();
+  const int V = C / 8;
+  const int p0 = blockIdx.x * p.chunk;
+  const int p1 = min(p.HW, p0 + p.chunk);
+  const long long total = (long long)(p1 - p0) * V;
+  for (long long idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    const int px = p0 + (int)(idx / V);
+    const int c0 = (int)(idx % V) * 8;
+    const long long row = (long long)n * p.HW + px;
+    const __nv_bfloat16* src = c0 >= p.C1 ? p.x2 + row * p.ld2 + (c0 - p.C1) : p.x1 + row * p.ld1 + c0;
+    float f[8];
+    load8(src, f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float y = f[i] * scale[c0 + i] + shift[c0 + i];
+      if (p.silu) y = y / (1.f + __expf(-y));
+      f[i] = y;
+    }
+    store8(p.out + row * p.ldo + c0, f);
+  }
+}
+
+// ------------------------------------------------------------------ LayerNorm (+PE)
+// One warp per row; the row lives in registers (C <= 2048), exact two-pass mean/variance like torch.
+template <int MAXV>
+__global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, int rows, int C,
+                                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                 const float* __restrict__ pe, int pe_rows_per_frame, int pe_frames,
+                                 __nv_bfloat16* __restrict__ out, long long ldo) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const int V = C / 8;
+  float f[MAXV][8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int v = lane + i * 32;
+    if (v < V) {
+      load8(x + (long long)warp * ldx + v * 8, f[i]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += f[i][j];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int v = lane + i * 32;
+    if (v < V) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = f[i][j] - mean;
+        q += d * d;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / C + eps);
+  const float* perow = nullptr;
+  if (pe) perow = pe + (long long)((warp / pe_rows_per_frame) % pe_frames) * C;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int v = lane + i * 32;
+    if (v < V) {
+      float y[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = v * 8 + j;
+        y[j] = (f[i][j] - mean) * rstd * gamma[c] + beta[c];
+        if (perow) y[j] += perow[c];
+      }
+      store8(out + (long long)warp * ldo + v * 8, y);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ GEGLU gate
+__global__ void geglu_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, long long rows, int inner,
+                             __nv_bfloat16* __restrict__ out, long long ldo) {
+  const int V = inner / 8;
+  const long long total = rows * V;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long r = idx / V;
+    const int c0 = (int)(idx % V) * 8;
+    float h[8], g[8];
+    load8(x + r * ldx + c0, h);
+    load8(x + r * ldx + inner + c0, g);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) h[i] *= 0.5f * g[i] * (1.f + erff(g[i] * 0.70710678118654752f));
+    store8(out + r * ldo + c0, h);
+  }
+}
+
+}  // namespace vx
+
+using namespace vx;
+
+static int gn_block(int C, int* R) {
+  const int V = C / 8;
+  int r = 256 / V;
+  if (r < 1) r = 1;
+  while (V * r > 1024) --r;
+  *R = r;
+  return V * r;
+}
+
+extern "C" int vx_groupnorm_stats_ws_floats(int NB, int G, int S) { return NB * S * G * 3; }
+
+// x = [x1 | x2] per row (x2 may be null, C2 = 0); rows = NB*HW; partial: float[NB*S*G*3] workspace.
+extern "C" int vx_groupnorm_stats(const void* x1, long long ld1, int C1, const void* x2, long long ld2, int C2,
+                                  int NB, int HW, int G, int S, float* partial, void* stream) {
+  const int C = C1 + C2;
+  VX_REQUIRE(C1 % 8 == 0 && C2 % 8 == 0 && C % G == 0 && S >= 1, "vx_groupnorm_stats: bad C1=%d C2=%d G=%d", C1, C2, G);
+  VX_REQUIRE(C / 8 <= 1024, "vx_groupnorm_stats: C=%d too wide", C);
+  GnStatsArgs a{(const __nv_bfloat16*)x1, ld1, C1, (const __nv_bfloat16*)x2, ld2, C2, HW, G, S, 0, partial};
+  const int threads = gn_block(C, &a.R);
+  const size_t smem = (size_t)2 * a.R * C * sizeof(float);
+  VX_REQUIRE(smem <= 200 * 1024, "vx_groupnorm_stats: smem %zu too large", smem);
+  if (smem > 48 * 1024)
+    VX_CHECK_CUDA(cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  gn_stats_kernel<<<dim3(S, NB), threads, smem, (cudaStream_t)stream>>>(a);
+  VX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int vx_groupnorm_apply(const void* x1, long long ld1, int C1, const void* x2, long long ld2, int C2,
+                                  int NB, int HW, int G, int S, const float* partial, const float* gamma,
+                                  const float* beta, float eps, int silu, void* out, long long ldo, void* stream) {
+  const int C = C1 + C2;
+  VX_REQUIRE(C1 % 8 == 0 && C2 % 8 == 0 && C % G == 0, "vx_groupnorm_apply: bad C1=%d C2=%d G=%d", C1, C2, G);
+  GnApplyArgs a{(const __nv_bfloat16*)x1, ld1, C1, (const __nv_bfloat16*)x2, ld2, C2, HW, G, S, partial, gamma, beta,
+                eps, silu, (__nv_bfloat16*)out, ldo, 0};
+  // ~64 KB of activations per CTA
+  int chunk = (32768 / C);
+  if (chunk < 1) chunk = 1;
+  if (chunk > HW) chunk = HW;
+  a.chunk = chunk;
+  const size_t smem = (size_t)(2 * C + 2 * G) * sizeof(float);
+  gn_apply_kernel<<<dim3((HW + chunk - 1) / chunk, NB), 256, smem, (cudaStream_t)stream>>>(a);
+  VX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// pe: optional float [pe_frames, C]; row r uses pe[(r / rows_per_frame) % pe_frames]
+extern "C" int vx_layernorm(const void* x, long long ldx, long long rows, int C, const float* gamma,
+                            const float* beta, float eps, const float* pe, int rows_per_frame, int pe_frames,
+                            void* out, long long ldo, void* stream) {
+  VX_REQUIRE(C % 8 == 0 && C <= 2048, "vx_layernorm: C=%d unsupported", C);
+  const int threads = 256;
+  const long long blocks = (rows * 32 + threads - 1) / threads;
+  const int V = C / 8;
+  auto st = (cudaStream_t)stream;
+  if (pe && (rows_per_frame <= 0 || pe_frames <= 0)) return fail("vx_layernorm: bad pe args");
+#define LN_LAUNCH(MV)                                                                                            \
+  layernorm_kernel<MV><<<(unsigned)blocks, threads, 0, st>>>((const __nv_bfloat16*)x, ldx, (int)rows, C, gamma, \
+                                                             beta, eps, pe, rows_per_frame, pe_frames,          \
+                                                             (__nv_bfloat16*)out, ldo)
+  if (V <= 32) LN_LAUNCH(1);
+  else if (V <= 64) LN_LAUNCH(2);
+  else if (V <= 96) LN_LAUNCH(3);
+  else if (V <= 160) LN_LAUNCH(5);
+  else LN_LAUNCH(8);
+#undef LN_LAUNCH
+  VX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// x: [rows, 2*inner] = (h | gate) -> out [rows, inner]
+extern "C" int vx_geglu(const void* x, long long ldx, long long rows, int inner, void* out, long long ldo,
+                        void* stream) {
+  VX_REQUIRE(inner % 8 == 0, "vx_geglu: inner=%d", inner);
+  const long long total = rows * (inner / 8);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  geglu_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, ldx, rows, inner,
+                                                                  (__nv_bfloat16*)out, ldo);
+  VX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
