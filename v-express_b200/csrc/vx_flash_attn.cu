@@ -1,0 +1,304 @@
+// tcgen05 flash attention for the spatial attentions of the denoising UNet (sm_100a).
+//
+//   O[b, q, h, :] = softmax_k( Q[b, q, h, :] . K[b / kv_div, k, h, :] * hd^-0.5 ) @ V[b / kv_div, k, h, :]
+//
+// covers attn1 (self-attention, kv_div = 1; reference modules/mutual_self_attention.py:176-186) and attn1_5
+// (reference attention: K/V projected from the ReferenceNet bank, one bank per CFG half shared by the f frames
+// of the window, kv_div = f; :202-219) -- both diffusers AttnProcessor2_0 / F.scaled_dot_product_attention
+// without mask.
+//
+// One CTA = 128 query rows of one (frame, head).  Per 128-key tile:
+//   TMA   : K_j, V_j tiles -> smem ring (3-D view (8, rows, C/8) of the [rows, C] token matrix, so a head slice
+//           lands as [hd/8][rows][8] = the no-swizzle core-matrix layout; hd = 40 is zero-padded to 48 in smem
+//           only, never in HBM)
+//   MMA   : S_j = Q K_j^T  (tcgen05.mma, M=128, N=kv_tile, K=hd)     -> TMEM (double buffered)
+//   softmax warps (1 thread = 1 query row): tcgen05.ld S, online max / exp2 / row sum, P_j (bf16) -> smem,
+//           lazy rescale of the O accumulator (only when the running max grew by > 2^8)
+//   MMA   : O += P_j V_j  (A = P from smem, B = V tile MN-major)       -> TMEM
+// Epilogue: O / l -> bf16 -> out[row, h*hd : (h+1)*hd].
+#include "vx_host.h"
+#include "vx_ptx.cuh"
+
+namespace vx {
+
+constexpr int kFaThreads = 192;
+constexpr int kFaStages = 3;
+
+struct FaArgs {
+  int Nq, Nk, hd, hdp, kv_tile, kv_div, heads;
+  float scale_log2;
+  __nv_bfloat16* out;
+  long long ldo;
+  int q_bytes, kv_bytes, p_bytes;  // smem tile sizes (padded)
+};
+
+__global__ void __launch_bounds__(kFaThreads, 1)
+flash_attn_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
+                  const __grid_constant__ CUtensorMap mapV, const FaArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + p.q_bytes;                     // kFaStages x kv_bytes
+  uint8_t* sV = sK + kFaStages * p.kv_bytes;        // kFaStages x kv_bytes
+  uint8_t* sP = sV + kFaStages * p.kv_bytes;        // 2 x p_bytes
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * p.p_bytes);
+  uint64_t* q_full = bars;                 // 1
+  uint64_t* kv_full = bars + 1;            // stages
+  uint64_t* kv_empty = kv_full + kFaStages;
+  uint64_t* s_full = kv_empty + kFaStages;  // 2
+  uint64_t* p_ready = s_full + 2;           // 2
+  uint64_t* pv_done = p_ready + 2;          // 2
+  uint64_t* o_full = pv_done + 2;           // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q_tile = blockIdx.x, head = blockIdx.y, bq = blockIdx.z;
+  const int T = p.Nk / p.kv_tile;
+
+  // zero the operand tiles once: the K-padding chunk (hd 40 -> 48) must read as exact zeros
+  {
+    const int total16 = (p.q_bytes + 2 * kFaStages * p.kv_bytes) / 16;
+    uint4* z = reinterpret_cast<uint4*>(sQ);
+    for (int i = threadIdx.x; i < total16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+  }
+  if (threadIdx.x == 0) {
+    mbar_init(q_full, 1);
+    for (int s = 0; s < kFaStages; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&s_full[s], 1);
+      mbar_init(&p_ready[s], 128);
+      mbar_init(&pv_done[s], 1);
+    }
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  fence_proxy_async_smem();  // generic-proxy zero fill visible to TMA / tensor core (async proxy)
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_o = tmem_base + 256;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      tma_prefetch_desc(&mapQ);
+      tma_prefetch_desc(&mapK);
+      tma_prefetch_desc(&mapV);
+      const int col_chunk = head * p.hd / 8;
+      mbar_expect_tx(q_full, 128 * p.hd * 2);
+      tma_load_3d(sQ, &mapQ, q_full, 0, bq * p.Nq + q_tile * 128, col_chunk);
+      const int kv_row0 = (bq / p.kv_div) * p.Nk;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < T; ++j) {
+        mbar_wait(&kv_empty[stage], phase ^ 1);
+        mbar_expect_tx(&kv_full[stage], 2 * p.kv_tile * p.hd * 2);
+        tma_load_3d(sK + stage * p.kv_bytes, &mapK, &kv_full[stage], 0, kv_row0 + j * p.kv_tile, col_chunk);
+        tma_load_3d(sV + stage * p.kv_bytes, &mapV, &kv_full[stage], 0, kv_row0 + j * p.kv_tile, col_chunk);
+        if (++stage == kFaStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc_bf16(128, (uint32_t)p.kv_tile, 0, 0);
+      const uint32_t idesc_o = make_idesc_bf16(128, (uint32_t)p.hdp, 0, 1);  // B = V is MN-major
+      const uint32_t q_addr = smem_u32(sQ);
+      const uint32_t lbo_k = (uint32_t)p.kv_tile * 16;
+      auto issue_s = [&](int j) {
+        const int stage = j % kFaStages;
+        mbar_wait(&kv_full[stage], (uint32_t)((j / kFaStages) & 1));
+        tc_fence_after();
+        const uint32_t k_addr = smem_u32(sK + stage * p.kv_bytes);
+        const uint32_t d = tmem_base + (uint32_t)((j & 1) * 128);
+        for (int k = 0; k < p.hdp / 16; ++k) {
+          const uint64_t da = make_smem_desc(q_addr + k * 2 * 2048, 2048, 128, SWZ_NONE);
+          const uint64_t db = make_smem_desc(k_addr + k * 2 * lbo_k, lbo_k, 128, SWZ_NONE);
+          umma_ss(d, da, db, idesc_s, k ? 1u : 0u);
+        }
+        umma_commit(&s_full[j & 1]);
+      };
+      mbar_wait(q_full, 0);
+      issue_s(0);
+      for (int j = 0; j < T; ++j) {
+        if (j + 1 < T) issue_s(j + 1);
+        mbar_wait(&p_ready[j & 1], (uint32_t)((j >> 1) & 1));
+        tc_fence_after();
+        const int stage = j % kFaStages;
+        const uint32_t p_addr = smem_u32(sP + (j & 1) * p.p_bytes);
+        const uint32_t v_addr = smem_u32(sV + stage * p.kv_bytes);
+        for (int k = 0; k < p.kv_tile / 16; ++k) {
+          const uint64_t da = make_smem_desc(p_addr + k * 2 * 2048, 2048, 128, SWZ_NONE);
+          const uint64_t db = make_smem_desc(v_addr + k * 256, 128, lbo_k, SWZ_NONE);
+          umma_ss(tmem_o, da, db, idesc_o, (j | k) ? 1u : 0u);
+        }
+        umma_commit(&kv_empty[stage]);
+        umma_commit(&pv_done[j & 1]);
+      }
+      umma_commit(o_full);
+    }
+  } else {
+    // ------------------------------------------------------------ softmax + correction + epilogue (warps 2..5)
+    const int qd = warp & 3;
+    const int row = qd * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
+    float m_used = -INFINITY;  // max (in raw score units) the accumulators are currently scaled by
+    float l = 0.f;
+    const float c = p.scale_log2;
+    for (int j = 0; j < T; ++j) {
+      mbar_wait(&s_full[j & 1], (uint32_t)((j >> 1) & 1));
+      tc_fence_after();
+      const uint32_t ts = tmem_base + lane_addr + (uint32_t)((j & 1) * 128);
+      float mx = -INFINITY;
+      for (int cb = 0; cb < p.kv_tile; cb += 16) {
+        uint32_t v[16];
+        tmem_ld16(ts + cb, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+      }
+      if (j > 0) {
+        mbar_wait(&pv_done[(j - 1) & 1], (uint32_t)(((j - 1) >> 1) & 1));
+        tc_fence_after();
+      }
+      const float m_new = fmaxf(m_used, mx);
+      const bool need = (m_new - m_used) * c > 8.0f;  // also true for the first tile (m_used = -inf)
+      if (__any_sync(0xffffffffu, need)) {
+        const float alpha = (m_used == -INFINITY) ? 0.f : exp2f((m_used - m_new) * c);
+        l *= alpha;
+        m_used = m_new;
+        if (j > 0) {
+          for (int cb = 0; cb < p.hdp; cb += 16) {
+            uint32_t v[16];
+            tmem_ld16(tmem_o + lane_addr + cb, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+            tmem_st16(tmem_o + lane_addr + cb, v);
+          }
+          tmem_st_wait();
+        }
+      }
+      const float mc = m_used * c;
+      uint8_t* pb = sP + (j & 1) * p.p_bytes + row * 16;
+      for (int cb = 0; cb < p.kv_tile; cb += 16) {
+        uint32_t v[16];
+        tmem_ld16(ts + cb, v);
+        tmem_ld_wait();
+        float e[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          e[i] = exp2f(__uint_as_float(v[i]) * c - mc);
+          l += e[i];
+        }
+        *reinterpret_cast<uint4*>(pb + (cb / 8) * 2048) =
+            make_uint4(pack_bf16(e[0], e[1]), pack_bf16(e[2], e[3]), pack_bf16(e[4], e[5]), pack_bf16(e[6], e[7]));
+        *reinterpret_cast<uint4*>(pb + (cb / 8 + 1) * 2048) = make_uint4(
+            pack_bf16(e[8], e[9]), pack_bf16(e[10], e[11]), pack_bf16(e[12], e[13]), pack_bf16(e[14], e[15]));
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(&p_ready[j & 1]);
+    }
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    const int qrow = q_tile * 128 + row;
+    const float inv = 1.f / l;
+    __nv_bfloat16* op = p.out + ((long long)bq * p.Nq + qrow) * p.ldo + head * p.hd;
+    for (int cb = 0; cb < p.hdp; cb += 16) {
+      uint32_t v[16];
+      tmem_ld16(tmem_o + lane_addr + cb, v);
+      tmem_ld_wait();
+      if (qrow < p.Nq) {
+#pragma unroll
+        for (int h8 = 0; h8 < 2; ++h8) {
+          if (cb + h8 * 8 < p.hd) {
+            const int o = h8 * 8;
+            *reinterpret_cast<uint4*>(op + cb + o) = make_uint4(
+                pack_bf16(__uint_as_float(v[o]) * inv, __uint_as_float(v[o + 1]) * inv),
+                pack_bf16(__uint_as_float(v[o + 2]) * inv, __uint_as_float(v[o + 3]) * inv),
+                pack_bf16(__uint_as_float(v[o + 4]) * inv, __uint_as_float(v[o + 5]) * inv),
+                pack_bf16(__uint_as_float(v[o + 6]) * inv, __uint_as_float(v[o + 7]) * inv));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace vx
+
+using namespace vx;
+
+// q: [Bq*Nq, ldq], k/v: [Bkv*Nk, ldk] / [.., ldv] (bf16, heads*hd columns used), out: [Bq*Nq, ldo].
+// kv batch of query batch b is b / kv_div.
+extern "C" int vx_flash_attention(const void* q, long long ldq, const void* k, long long ldk, const void* v,
+                                  long long ldv, void* out, long long ldo, int Bq, int Nq, int Bkv, int Nk, int heads,
+                                  int hd, int kv_div, void* stream) {
+  VX_REQUIRE(hd % 8 == 0 && hd <= 256, "vx_flash_attention: hd=%d unsupported", hd);
+  VX_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0, "vx_flash_attention: ld must be %%8");
+  VX_REQUIRE(kv_div >= 1 && (Bq + kv_div - 1) / kv_div <= Bkv, "vx_flash_attention: kv_div=%d Bq=%d Bkv=%d", kv_div, Bq, Bkv);
+  const int hdp = (hd + 15) / 16 * 16;
+  int kv_tile = 0;
+  const int kv_max = hdp > 96 ? 64 : 128;
+  for (int t = kv_max; t >= 16; t -= 16)
+    if (Nk % t == 0) {
+      kv_tile = t;
+      break;
+    }
+  VX_REQUIRE(kv_tile > 0, "vx_flash_attention: Nk=%d must be a multiple of 16", Nk);
+  FaArgs a{};
+  a.Nq = Nq; a.Nk = Nk; a.hd = hd; a.hdp = hdp; a.kv_tile = kv_tile; a.kv_div = kv_div; a.heads = heads;
+  a.scale_log2 = 1.4426950408889634f / sqrtf((float)hd);
+  a.out = (__nv_bfloat16*)out; a.ldo = ldo;
+  a.q_bytes = 128 * hdp * 2;
+  a.kv_bytes = kv_tile * hdp * 2;
+  a.p_bytes = 128 * kv_tile * 2;
+  const size_t smem = (size_t)a.q_bytes + 2 * kFaStages * a.kv_bytes + 2 * a.p_bytes + 256 + 128;
+  VX_REQUIRE(smem <= 227 * 1024, "vx_flash_attention: smem %zu too large (hd=%d)", smem, hd);
+  CUtensorMap mQ, mK, mV;
+  {
+    uint64_t dims[3] = {8, (uint64_t)Bq * Nq, (uint64_t)ldq / 8};
+    uint64_t str[2] = {(uint64_t)ldq * 2, 16};
+    uint32_t box[3] = {8, 128, (uint32_t)hd / 8};
+    if (make_tmap_bf16(&mQ, q, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
+  }
+  {
+    uint64_t dims[3] = {8, (uint64_t)Bkv * Nk, (uint64_t)ldk / 8};
+    uint64_t str[2] = {(uint64_t)ldk * 2, 16};
+    uint32_t box[3] = {8, (uint32_t)kv_tile, (uint32_t)hd / 8};
+    if (make_tmap_bf16(&mK, k, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
+  }
+  {
+    uint64_t dims[3] = {8, (uint64_t)Bkv * Nk, (uint64_t)ldv / 8};
+    uint64_t str[2] = {(uint64_t)ldv * 2, 16};
+    uint32_t box[3] = {8, (uint32_t)kv_tile, (uint32_t)hd / 8};
+    if (make_tmap_bf16(&mV, v, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
+  }
+  static bool cfg = false;
+  if (!cfg) {
+    VX_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    cfg = true;
+  }
+  dim3 grid((Nq + 127) / 128, heads, Bq);
+  flash_attn_kernel<<<grid, kFaThreads, smem, (cudaStream_t)stream>>>(mQ, mK, mV, a);
+  VX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

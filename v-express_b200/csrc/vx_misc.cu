@@ -229,7 +229,7 @@ __global__ void timestep_embed_kernel(const float* __restrict__ t, int rows, int
 }
 
 // ------------------------------------------------------------------ CFG + /count + overlap accumulate
-// noise: planar bf16 (b, 4, f, h, w) from the UNet; for local frame i -> global frame win[i]:
+// noise: frame-major planar bf16 ((b f), 4, h, w) from the UNet's conv_out; local frame i -> global frame win[i]:
 //   acc[:, win[i]] += bf16( bf16(u + g*(c-u)) / count[win[i]] )     (same rounding points as the reference's
 //   model-dtype arithmetic, pipelines/v_express_pipeline.py:548-560)
 struct CfgArgs {
@@ -247,7 +247,7 @@ __global__ void cfg_overlap_kernel(const CfgArgs p) {
     const int px = (int)(idx % p.hw);
     const int i = (int)((idx / p.hw) % p.f);
     const int c = (int)(idx / ((long long)p.hw * p.f));
-    const long long off = ((long long)c * p.f + i) * p.hw + px;
+    const long long off = ((long long)i * 4 + c) * p.hw + px;
     float v;
     if (p.do_cfg) {
       const float u = __bfloat162float(p.noise[off]);

@@ -1,0 +1,2 @@
+from .unet_3d import UNet3DConditionModel  # noqa: F401
+from .mutual_self_attention import ReferenceAttentionControl  # noqa: F401

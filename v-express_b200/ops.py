@@ -80,3 +80,167 @@ def probe_tma(base, dims, strides_bytes, box, swizzle, coords, nbytes):
                                   U32(*pad(box, 5)), c_int(swizzle), I32(*pad(coords, 5)), c_int(nbytes), ptr(out),
                                   stream_ptr()), "vx_probe_tma")
     return out
+
+
+# ----------------------------------------------------------------------------- attention
+def flash_attention(q, k, v, heads, Nq, Nk, kv_div=1, out=None):
+    """q: [Bq*Nq, >=heads*hd] (row stride arbitrary), k/v: [Bkv*Nk, ...]; returns [Bq*Nq, heads*hd]."""
+    _chk_bf16(q, k, v, out)
+    C = q.shape[1]
+    hd = C // heads
+    Bq = q.shape[0] // Nq
+    Bkv = k.shape[0] // Nk
+    if out is None:
+        out = torch.empty((q.shape[0], C), device=q.device, dtype=BF16)
+    check(_ffi.lib().vx_flash_attention(ptr(q), c_ll(q.stride(0)), ptr(k), c_ll(k.stride(0)), ptr(v),
+                                        c_ll(v.stride(0)), ptr(out), c_ll(out.stride(0)), c_int(Bq), c_int(Nq),
+                                        c_int(Bkv), c_int(Nk), c_int(heads), c_int(hd), c_int(kv_div), stream_ptr()),
+          "vx_flash_attention")
+    return out
+
+
+def temporal_attention(q, k, v, b, f, HW, heads, out=None):
+    """q/k/v: [(b f HW), C] column slices sharing one row stride; attention over f per (b, pixel, head)."""
+    _chk_bf16(q, k, v, out)
+    assert q.stride(0) == k.stride(0) == v.stride(0)
+    C = q.shape[1]
+    if out is None:
+        out = torch.empty((q.shape[0], C), device=q.device, dtype=BF16)
+    check(_ffi.lib().vx_temporal_attention(ptr(q), ptr(k), ptr(v), c_ll(q.stride(0)), ptr(out), c_ll(out.stride(0)),
+                                           c_int(b), c_int(f), c_int(HW), c_int(heads), c_int(C // heads),
+                                           stream_ptr()), "vx_temporal_attention")
+    return out
+
+
+def smallkv_attention(q, k, v, rows_per_frame, heads, Lk, out=None):
+    """q: [rows, C]; k/v: [frames*Lk, C] (shared row stride)."""
+    _chk_bf16(q, k, v, out)
+    assert k.stride(0) == v.stride(0)
+    C = q.shape[1]
+    if out is None:
+        out = torch.empty((q.shape[0], C), device=q.device, dtype=BF16)
+    check(_ffi.lib().vx_smallkv_attention(ptr(q), c_ll(q.stride(0)), ptr(k), ptr(v), c_ll(k.stride(0)), ptr(out),
+                                          c_ll(out.stride(0)), c_ll(q.shape[0]), c_int(rows_per_frame), c_int(heads),
+                                          c_int(C // heads), c_int(Lk), stream_ptr()), "vx_smallkv_attention")
+    return out
+
+
+# ----------------------------------------------------------------------------- norms / activations
+def _gn_S(NB, HW):
+    s = max(1, min(HW // 32, (148 * 6) // max(NB, 1)))
+    return max(1, min(s, 64))
+
+
+def groupnorm(x1, NB, HW, gamma, beta, eps, silu, x2=None, groups=32, out=None, ws=None):
+    """Per-frame GroupNorm (+SiLU) of the channel-concatenation [x1 | x2]; x*: [NB*HW, C*] bf16."""
+    _chk_bf16(x1, x2, out)
+    C1 = x1.shape[1]
+    C2 = 0 if x2 is None else x2.shape[1]
+    S = _gn_S(NB, HW)
+    if ws is None:
+        ws = torch.empty(NB * S * groups * 3, device=x1.device, dtype=torch.float32)
+    if out is None:
+        out = torch.empty((NB * HW, C1 + C2), device=x1.device, dtype=BF16)
+    L = _ffi.lib()
+    ld2 = c_ll(0 if x2 is None else x2.stride(0))
+    check(L.vx_groupnorm_stats(ptr(x1), c_ll(x1.stride(0)), c_int(C1), ptr(x2), ld2, c_int(C2), c_int(NB), c_int(HW),
+                               c_int(groups), c_int(S), ptr(ws), stream_ptr()), "vx_groupnorm_stats")
+    check(L.vx_groupnorm_apply(ptr(x1), c_ll(x1.stride(0)), c_int(C1), ptr(x2), ld2, c_int(C2), c_int(NB), c_int(HW),
+                               c_int(groups), c_int(S), ptr(ws), ptr(gamma), ptr(beta), c_float(eps), c_int(int(silu)),
+                               ptr(out), c_ll(out.stride(0)), stream_ptr()), "vx_groupnorm_apply")
+    return out
+
+
+def layernorm(x, gamma, beta, eps=1e-5, pe=None, rows_per_frame=0, out=None):
+    _chk_bf16(x, out)
+    rows, C = x.shape
+    if out is None:
+        out = torch.empty((rows, C), device=x.device, dtype=BF16)
+    check(_ffi.lib().vx_layernorm(ptr(x), c_ll(x.stride(0)), c_ll(rows), c_int(C), ptr(gamma), ptr(beta),
+                                  c_float(eps), ptr(pe), c_int(rows_per_frame), c_int(0 if pe is None else pe.shape[0]),
+                                  ptr(out), c_ll(out.stride(0)), stream_ptr()), "vx_layernorm")
+    return out
+
+
+def geglu(x, out=None):
+    _chk_bf16(x, out)
+    rows, two = x.shape
+    inner = two // 2
+    if out is None:
+        out = torch.empty((rows, inner), device=x.device, dtype=BF16)
+    check(_ffi.lib().vx_geglu(ptr(x), c_ll(x.stride(0)), c_ll(rows), c_int(inner), ptr(out), c_ll(out.stride(0)),
+                              stream_ptr()), "vx_geglu")
+    return out
+
+
+# ----------------------------------------------------------------------------- misc
+def conv_in(x, w, bias, Cout, addend=None, add_frame=None, out=None):
+    """x: planar bf16 (n, c, h, w) given as a 4-D tensor whose (h, w) plane is contiguous."""
+    assert x.dtype == BF16 and x.stride(3) == 1 and x.stride(2) == x.shape[3]
+    NB, Cin, H, W = x.shape
+    if out is None:
+        out = torch.empty((NB * H * W, Cout), device=x.device, dtype=BF16)
+    check(_ffi.lib().vx_conv_in(ptr(x), c_ll(x.stride(0)), c_ll(x.stride(1)), c_int(NB), c_int(H), c_int(W), c_int(Cin),
+                                c_int(Cout), ptr(w), ptr(bias), ptr(addend), ptr(add_frame),
+                                c_ll(0 if addend is None else addend.stride(0)), ptr(out), c_ll(out.stride(0)),
+                                stream_ptr()), "vx_conv_in")
+    return out
+
+
+def conv_out(x, NB, H, W, w, bias, out, post=False):
+    """x: NHWC [NB*H*W, C] bf16; w fp32 [Cout, 9, C]; out planar 4-D (n, co, h, w) bf16 or fp32."""
+    _chk_bf16(x)
+    assert out.stride(3) == 1 and out.stride(2) == W
+    Cout = w.shape[0]
+    check(_ffi.lib().vx_conv_out(ptr(x), c_ll(x.stride(0)), c_int(NB), c_int(H), c_int(W), c_int(x.shape[1]), c_int(Cout),
+                                 ptr(w), ptr(bias), ptr(out), c_ll(out.stride(0)), c_ll(out.stride(1)),
+                                 c_int(int(out.dtype == torch.float32)), c_int(int(post)), stream_ptr()), "vx_conv_out")
+    return out
+
+
+def im2col_s2(x, NB, H, W, out=None):
+    _chk_bf16(x)
+    C = x.shape[-1]
+    if out is None:
+        out = torch.empty((NB * (H // 2) * (W // 2), 9 * C), device=x.device, dtype=BF16)
+    check(_ffi.lib().vx_im2col_s2(ptr(x), c_int(NB), c_int(H), c_int(W), c_int(C), ptr(out), stream_ptr()), "vx_im2col_s2")
+    return out
+
+
+def upsample2x(x, NB, H, W, out=None):
+    _chk_bf16(x)
+    C = x.shape[-1]
+    if out is None:
+        out = torch.empty((NB * 4 * H * W, C), device=x.device, dtype=BF16)
+    check(_ffi.lib().vx_upsample2x(ptr(x), c_int(NB), c_int(H), c_int(W), c_int(C), ptr(out), stream_ptr()), "vx_upsample2x")
+    return out
+
+
+def skinny_linear(x, w, bias, act_in=False, act_out=False, out=None):
+    assert x.dtype == torch.float32 and w.dtype == BF16 and x.is_contiguous() and w.is_contiguous()
+    rows, K = x.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty((rows, N), device=x.device, dtype=torch.float32)
+    check(_ffi.lib().vx_skinny_linear(ptr(x), c_int(rows), c_int(K), ptr(w), ptr(bias), c_int(N), c_int(int(act_in)),
+                                      c_int(int(act_out)), ptr(out), stream_ptr()), "vx_skinny_linear")
+    return out
+
+
+def timestep_embed(t, dim, out=None):
+    assert t.dtype == torch.float32
+    if out is None:
+        out = torch.empty((t.shape[0], dim), device=t.device, dtype=torch.float32)
+    check(_ffi.lib().vx_timestep_embed(ptr(t), c_int(t.shape[0]), c_int(dim), ptr(out), stream_ptr()), "vx_timestep_embed")
+    return out
+
+
+def cfg_overlap_accumulate(noise, f, hw, L, do_cfg, win, count, guidance, acc):
+    check(_ffi.lib().vx_cfg_overlap_accumulate(ptr(noise), c_int(f), c_int(hw), c_int(L), c_int(int(do_cfg)), ptr(win),
+                                               ptr(count), c_float(guidance), ptr(acc), stream_ptr()),
+          "vx_cfg_overlap_accumulate")
+
+
+def ddim_step(latents, acc, sqrt_a, sqrt_1ma, sqrt_aprev, sqrt_1maprev):
+    check(_ffi.lib().vx_ddim_step(ptr(latents), ptr(acc), c_ll(latents.numel()), c_float(sqrt_a), c_float(sqrt_1ma),
+                                  c_float(sqrt_aprev), c_float(sqrt_1maprev), stream_ptr()), "vx_ddim_step")
