@@ -26,7 +26,8 @@ def _gen(seed):
 @pytest.mark.parametrize("B,N,heads,hd,kv_div,Nk", [(2, 256, 8, 160, 1, 256), (2, 1024, 8, 80, 1, 1024),
                                                     (2, 4096, 8, 40, 1, 4096), (4, 64, 8, 160, 1, 64),
                                                     (4, 1024, 8, 80, 2, 1024), (4, 256, 8, 16, 2, 256),
-                                                    (2, 128, 2, 32, 1, 384), (3, 64, 8, 8, 1, 64)])
+                                                    (2, 128, 2, 32, 1, 384), (3, 64, 8, 8, 1, 64),
+                                                    (8, 4, 8, 32, 1, 4), (4, 36, 8, 16, 2, 36)])
 def test_flash_attention(ops, B, N, heads, hd, kv_div, Nk):
     g = _gen(B * N + hd)
     C = heads * hd

@@ -243,6 +243,64 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
   }
 }
 
+// Fallback for key counts the tensor-core tiling cannot express (Nk < 16 or Nk % 16 != 0, e.g. the 2x2 / 12x12
+// maps of reduced test resolutions): one warp per (batch, head, query), exact softmax, CUDA cores.
+struct GaArgs {
+  const __nv_bfloat16* q; long long ldq;
+  const __nv_bfloat16* k; long long ldk;
+  const __nv_bfloat16* v; long long ldv;
+  __nv_bfloat16* out; long long ldo;
+  int Bq, Nq, Nk, heads, hd, kv_div;
+  float scale;
+};
+
+__global__ void __launch_bounds__(128) generic_attn_kernel(const GaArgs p) {
+  extern __shared__ float sc_all[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* sc = sc_all + warp * p.Nk;
+  const long long item = (long long)blockIdx.x * 4 + warp;
+  const long long total = (long long)p.Bq * p.heads * p.Nq;
+  if (item >= total) return;
+  const int qi = (int)(item % p.Nq);
+  const int head = (int)((item / p.Nq) % p.heads);
+  const int b = (int)(item / ((long long)p.Nq * p.heads));
+  const __nv_bfloat16* qp = p.q + ((long long)b * p.Nq + qi) * p.ldq + head * p.hd;
+  const long long kv0 = (long long)(b / p.kv_div) * p.Nk;
+  float mx = -INFINITY;
+  for (int j = lane; j < p.Nk; j += 32) {
+    const __nv_bfloat16* kp = p.k + (kv0 + j) * p.ldk + head * p.hd;
+    float acc = 0.f;
+    for (int c = 0; c < p.hd; c += 2) {
+      const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(qp + c));
+      const float2 bb = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(kp + c));
+      acc += a.x * bb.x + a.y * bb.y;
+    }
+    acc *= p.scale;
+    sc[j] = acc;
+    mx = fmaxf(mx, acc);
+  }
+  for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float sum = 0.f;
+  for (int j = lane; j < p.Nk; j += 32) {
+    const float e = __expf(sc[j] - mx);
+    sc[j] = e;
+    sum += e;
+  }
+  for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  __syncwarp();
+  const float inv = 1.f / sum;
+  for (int c = lane * 2; c < p.hd; c += 64) {
+    float o0 = 0.f, o1 = 0.f;
+    for (int j = 0; j < p.Nk; ++j) {
+      const float2 vv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p.v + (kv0 + j) * p.ldv + head * p.hd + c));
+      o0 += sc[j] * vv.x;
+      o1 += sc[j] * vv.y;
+    }
+    *reinterpret_cast<__nv_bfloat162*>(p.out + ((long long)b * p.Nq + qi) * p.ldo + head * p.hd + c) =
+        __floats2bfloat162_rn(o0 * inv, o1 * inv);
+  }
+}
+
 }  // namespace vx
 
 using namespace vx;
@@ -255,6 +313,15 @@ extern "C" int vx_flash_attention(const void* q, long long ldq, const void* k, l
   VX_REQUIRE(hd % 8 == 0 && hd <= 256, "vx_flash_attention: hd=%d unsupported", hd);
   VX_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0, "vx_flash_attention: ld must be %%8");
   VX_REQUIRE(kv_div >= 1 && (Bq + kv_div - 1) / kv_div <= Bkv, "vx_flash_attention: kv_div=%d Bq=%d Bkv=%d", kv_div, Bq, Bkv);
+  if (Nk < 16 || Nk % 16 != 0) {
+    VX_REQUIRE(Nk * 4 * 4 <= 48 * 1024, "vx_flash_attention: Nk=%d not a multiple of 16 and too long for the fallback", Nk);
+    GaArgs g{(const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)k, ldk, (const __nv_bfloat16*)v, ldv,
+             (__nv_bfloat16*)out, ldo, Bq, Nq, Nk, heads, hd, kv_div, 1.0f / sqrtf((float)hd)};
+    const long long items = (long long)Bq * heads * Nq;
+    generic_attn_kernel<<<(unsigned)((items + 3) / 4), 128, (size_t)Nk * 4 * 4, (cudaStream_t)stream>>>(g);
+    VX_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   const int hdp = (hd + 15) / 16 * 16;
   int kv_tile = 0;
   const int kv_max = hdp > 96 ? 64 : 128;
