@@ -430,7 +430,7 @@ VAE_CFG = dict(block_out_channels=(128, 256, 512, 512), layers_per_block=2, late
                norm_num_groups=32, out_channels=3)
 
 
-def small_vae_cfg(width=(32, 64, 128, 128)):
+def small_vae_cfg(width=(64, 64, 128, 128)):
     c = dict(VAE_CFG)
     c["block_out_channels"] = tuple(width)
     return c

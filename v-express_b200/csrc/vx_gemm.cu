@@ -43,6 +43,7 @@ struct GemmArgs {
   long long ldr;
   __nv_bfloat16* out;
   long long ldc;
+  int out_f32;  // 1: `out` is float* (used for attention scores that feed an fp32 softmax)
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -198,6 +199,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             }
           }
         }
+        if (p.out_f32) {
+          float4* fp = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + m * p.ldc + n);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) fp[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+          continue;
+        }
         uint4* op = reinterpret_cast<uint4*>(p.out + m * p.ldc + n);
         op[0] = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
         op[1] = make_uint4(pack_bf16(f[8], f[9]), pack_bf16(f[10], f[11]), pack_bf16(f[12], f[13]),
@@ -267,7 +274,7 @@ using namespace vx;
 extern "C" int vx_gemm_bf16(const void* A, long long lda, int K1, const void* A2, long long lda2, int K2,
                             const void* Wt, long long ldw, int M, int N, const float* bias, const float* bias2,
                             int bias2_div, float scale, const void* residual, long long ldr, void* out,
-                            long long ldc, int block_n, void* stream) {
+                            long long ldc, int out_f32, int block_n, void* stream) {
   VX_REQUIRE(M > 0 && N > 0 && K1 > 0, "vx_gemm_bf16: bad shape M=%d N=%d K1=%d", M, N, K1);
   VX_REQUIRE(N % 16 == 0, "vx_gemm_bf16: N=%d must be a multiple of 16", N);
   VX_REQUIRE(K1 % 8 == 0 && K2 % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && ldc % 8 == 0,
@@ -308,7 +315,7 @@ extern "C" int vx_gemm_bf16(const void* A, long long lda, int K1, const void* A2
   a.W = a.H = 1;
   a.bias = bias; a.bias2 = bias2; a.bias2_div = bias2_div > 0 ? bias2_div : 1; a.scale = scale;
   a.residual = (const __nv_bfloat16*)residual; a.ldr = ldr;
-  a.out = (__nv_bfloat16*)out; a.ldc = ldc;
+  a.out = (__nv_bfloat16*)out; a.ldc = ldc; a.out_f32 = out_f32;
   return launch(mA, mA2, mB, a, (cudaStream_t)stream);
 }
 

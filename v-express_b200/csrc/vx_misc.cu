@@ -21,8 +21,11 @@ struct ConvInArgs {
   int NB, H, W, Cin, Cout;
   const float* w; const float* bias;
   const __nv_bfloat16* addend; const int* add_frame; long long add_ld;
+  float pre_scale; const float* pre_w; const float* pre_b;  // optional per-pixel 1x1 pre-transform
   __nv_bfloat16* out; long long ldo;
 };
+
+__device__ __forceinline__ float rbf16(float v) { return __bfloat162float(__float2bfloat16(v)); }
 
 __global__ void conv_in_kernel(const ConvInArgs p) {
   extern __shared__ float sw[];  // [Cin*9][Cout] transposed for conflict-free reads
@@ -44,16 +47,25 @@ __global__ void conv_in_kernel(const ConvInArgs p) {
     float acc[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = p.bias ? p.bias[cv * 8 + i] : 0.f;
-    for (int c = 0; c < p.Cin; ++c) {
-      const __nv_bfloat16* plane = p.in + n * p.sn + c * p.sc;
 #pragma unroll
-      for (int t = 0; t < 9; ++t) {
-        const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
-        if (yy < 0 || yy >= p.H || xx < 0 || xx >= p.W) continue;
-        const float v = __bfloat162float(plane[yy * p.W + xx]);
+    for (int t = 0; t < 9; ++t) {
+      const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
+      if (yy < 0 || yy >= p.H || xx < 0 || xx >= p.W) continue;
+      float vin[8];
+      for (int c = 0; c < p.Cin; ++c) vin[c] = __bfloat162float(p.in[n * p.sn + c * p.sc + yy * p.W + xx]);
+      if (p.pre_w) {
+        float tmp[8];
+        for (int c = 0; c < p.Cin; ++c) tmp[c] = rbf16(p.pre_scale * vin[c]);
+        for (int c = 0; c < p.Cin; ++c) {
+          float a = p.pre_b ? p.pre_b[c] : 0.f;
+          for (int k = 0; k < p.Cin; ++k) a += p.pre_w[c * p.Cin + k] * tmp[k];
+          vin[c] = rbf16(a);
+        }
+      }
+      for (int c = 0; c < p.Cin; ++c) {
         const float* wr = sw + (c * 9 + t) * p.Cout + cv * 8;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] += v * wr[i];
+        for (int i = 0; i < 8; ++i) acc[i] += vin[c] * wr[i];
       }
     }
     if (p.addend) {
@@ -284,10 +296,11 @@ using namespace vx;
 
 extern "C" int vx_conv_in(const void* in, long long sn, long long sc, int NB, int H, int W, int Cin, int Cout,
                           const float* w, const float* bias, const void* addend, const int* add_frame,
-                          long long add_ld, void* out, long long ldo, void* stream) {
-  VX_REQUIRE(Cout % 8 == 0 && Cin * 9 * Cout * 4 <= 200 * 1024, "vx_conv_in: Cin=%d Cout=%d unsupported", Cin, Cout);
+                          long long add_ld, float pre_scale, const float* pre_w, const float* pre_b, void* out,
+                          long long ldo, void* stream) {
+  VX_REQUIRE(Cout % 8 == 0 && Cin <= 8 && Cin * 9 * Cout * 4 <= 200 * 1024, "vx_conv_in: Cin=%d Cout=%d unsupported", Cin, Cout);
   ConvInArgs a{(const __nv_bfloat16*)in, sn, sc, NB, H, W, Cin, Cout, w, bias, (const __nv_bfloat16*)addend, add_frame,
-               add_ld, (__nv_bfloat16*)out, ldo};
+               add_ld, pre_scale, pre_w, pre_b, (__nv_bfloat16*)out, ldo};
   const size_t smem = (size_t)Cin * 9 * Cout * 4;
   static bool cfg = false;
   if (!cfg) {

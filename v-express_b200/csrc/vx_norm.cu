@@ -233,9 +233,53 @@ __global__ void geglu_kernel(const __nv_bfloat16* __restrict__ x, long long ldx,
   }
 }
 
+// ------------------------------------------------------------------ row softmax (fp32 scores -> bf16 probs)
+// one CTA per row; used by the single-head hd=512 attention of the VAE decoder mid block
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ x, long long ldx, int n,
+                                                           __nv_bfloat16* __restrict__ out, long long ldo) {
+  __shared__ float red[8];
+  const float* row = x + (long long)blockIdx.x * ldx;
+  float mx = -INFINITY;
+  for (int i = threadIdx.x * 4; i < n; i += 1024) {
+    const float4 v = *reinterpret_cast<const float4*>(row + i);
+    mx = fmaxf(fmaxf(mx, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+  }
+  for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = red[0];
+  for (int i = 1; i < 8; ++i) mx = fmaxf(mx, red[i]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int i = threadIdx.x * 4; i < n; i += 1024) {
+    const float4 v = *reinterpret_cast<const float4*>(row + i);
+    sum += __expf(v.x - mx) + __expf(v.y - mx) + __expf(v.z - mx) + __expf(v.w - mx);
+  }
+  for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  sum = 0.f;
+  for (int i = 0; i < 8; ++i) sum += red[i];
+  const float inv = 1.f / sum;
+  __nv_bfloat16* orow = out + (long long)blockIdx.x * ldo;
+  for (int i = threadIdx.x * 4; i < n; i += 1024) {
+    const float4 v = *reinterpret_cast<const float4*>(row + i);
+    *reinterpret_cast<uint2*>(orow + i) = make_uint2(pack_bf16(__expf(v.x - mx) * inv, __expf(v.y - mx) * inv),
+                                                     pack_bf16(__expf(v.z - mx) * inv, __expf(v.w - mx) * inv));
+  }
+}
+
 }  // namespace vx
 
 using namespace vx;
+
+extern "C" int vx_softmax_rows(const float* x, long long ldx, long long rows, int n, void* out, long long ldo,
+                               void* stream) {
+  VX_REQUIRE(n % 4 == 0 && ldx % 4 == 0 && ldo % 4 == 0, "vx_softmax_rows: n=%d must be a multiple of 4", n);
+  softmax_rows_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(x, ldx, n, (__nv_bfloat16*)out, ldo);
+  VX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
 
 static int gn_block(int C, int* R) {
   const int V = C / 8;

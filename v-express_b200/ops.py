@@ -19,20 +19,21 @@ def _chk_bf16(*ts):
             assert t.is_cuda and t.dtype == BF16 and t.stride(-1) == 1, (t.dtype, t.device, t.stride())
 
 
-def gemm(a, w, bias=None, *, a2=None, bias2=None, bias2_div=1, scale=1.0, residual=None, out=None, block_n=0):
-    """out = (concat(a, a2) @ w.T + bias + bias2[row // bias2_div]) * scale + residual."""
-    _chk_bf16(a, w, a2, residual, out)
+def gemm(a, w, bias=None, *, a2=None, bias2=None, bias2_div=1, scale=1.0, residual=None, out=None, block_n=0,
+         out_f32=False):
+    """out = (concat(a, a2) @ w.T + bias + bias2[row // bias2_div]) * scale + residual  (bf16, or fp32 if out_f32)."""
+    _chk_bf16(a, w, a2, residual, None if out_f32 else out)
     M, K1 = a.shape
     K2 = 0 if a2 is None else a2.shape[1]
     N = w.shape[0]
     assert w.shape[1] == K1 + K2
     if out is None:
-        out = torch.empty((M, N), device=a.device, dtype=BF16)
+        out = torch.empty((M, N), device=a.device, dtype=torch.float32 if out_f32 else BF16)
     check(_ffi.lib().vx_gemm_bf16(
         ptr(a), c_ll(a.stride(0)), c_int(K1), ptr(a2), c_ll(0 if a2 is None else a2.stride(0)), c_int(K2),
         ptr(w), c_ll(w.stride(0)), c_int(M), c_int(N), ptr(bias), ptr(bias2), c_int(bias2_div), c_float(scale),
         ptr(residual), c_ll(0 if residual is None else residual.stride(0)), ptr(out), c_ll(out.stride(0)),
-        c_int(block_n), stream_ptr()), "vx_gemm_bf16")
+        c_int(int(out_f32)), c_int(block_n), stream_ptr()), "vx_gemm_bf16")
     return out
 
 
@@ -174,16 +175,18 @@ def geglu(x, out=None):
 
 
 # ----------------------------------------------------------------------------- misc
-def conv_in(x, w, bias, Cout, addend=None, add_frame=None, out=None):
-    """x: planar bf16 (n, c, h, w) given as a 4-D tensor whose (h, w) plane is contiguous."""
+def conv_in(x, w, bias, Cout, addend=None, add_frame=None, out=None, pre_scale=1.0, pre_w=None, pre_b=None):
+    """x: planar bf16 (n, c, h, w) given as a 4-D tensor whose (h, w) plane is contiguous.
+    Optional per-pixel pre-transform  v -> bf16(pre_w @ bf16(pre_scale * v) + pre_b)  (VAE: 1/0.18215 scaling and
+    the 1x1 post_quant_conv) applied to in-bounds pixels before the 3x3 taps."""
     assert x.dtype == BF16 and x.stride(3) == 1 and x.stride(2) == x.shape[3]
     NB, Cin, H, W = x.shape
     if out is None:
         out = torch.empty((NB * H * W, Cout), device=x.device, dtype=BF16)
     check(_ffi.lib().vx_conv_in(ptr(x), c_ll(x.stride(0)), c_ll(x.stride(1)), c_int(NB), c_int(H), c_int(W), c_int(Cin),
                                 c_int(Cout), ptr(w), ptr(bias), ptr(addend), ptr(add_frame),
-                                c_ll(0 if addend is None else addend.stride(0)), ptr(out), c_ll(out.stride(0)),
-                                stream_ptr()), "vx_conv_in")
+                                c_ll(0 if addend is None else addend.stride(0)), c_float(pre_scale), ptr(pre_w), ptr(pre_b),
+                                ptr(out), c_ll(out.stride(0)), stream_ptr()), "vx_conv_in")
     return out
 
 
@@ -244,3 +247,14 @@ def cfg_overlap_accumulate(noise, f, hw, L, do_cfg, win, count, guidance, acc):
 def ddim_step(latents, acc, sqrt_a, sqrt_1ma, sqrt_aprev, sqrt_1maprev):
     check(_ffi.lib().vx_ddim_step(ptr(latents), ptr(acc), c_ll(latents.numel()), c_float(sqrt_a), c_float(sqrt_1ma),
                                   c_float(sqrt_aprev), c_float(sqrt_1maprev), stream_ptr()), "vx_ddim_step")
+
+
+def softmax_rows(x, out=None):
+    """Row softmax of fp32 scores [rows, n] -> bf16 probabilities."""
+    assert x.dtype == torch.float32 and x.stride(1) == 1
+    rows, n = x.shape
+    if out is None:
+        out = torch.empty((rows, n), device=x.device, dtype=BF16)
+    check(_ffi.lib().vx_softmax_rows(ptr(x), c_ll(x.stride(0)), c_ll(rows), c_int(n), ptr(out), c_ll(out.stride(0)),
+                                     stream_ptr()), "vx_softmax_rows")
+    return out

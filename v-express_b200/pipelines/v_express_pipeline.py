@@ -1,0 +1,325 @@
+"""B200-native ``VExpressPipeline``: drop-in for the reference's ``pipelines/v_express_pipeline.py`` denoising
+hot path (``__call__`` -> ``mean_overlap`` :409-589 and ``decode_latents`` :152-166), same call signature and
+return value ((1,3,L,H,W) fp32 on the host, values in [0,1]).
+
+What differs by design:
+  * latents, kps features and audio tokens stay resident in HBM for the whole video (the reference shuttles every
+    window host<->device each step and syncs once per frame);
+  * per step, all windows run through one CUDA-graph-captured UNet forward; CFG + /count + overlap accumulation
+    is one kernel per window and the DDIM update one kernel per step.  The result equals the reference's
+    streaming update (a frame is stepped only after all its windows were visited, :552-572) with identical
+    rounding points in the model dtype;
+  * context windows shard over the GPUs of one box (``do_multi_devices_inference``, a dead flag in the reference):
+    every rank owns a contiguous block of windows and one NCCL all-reduce per step sums the (zero-padded)
+    per-frame noise-prediction buffers; the VAE decode is sharded by frame and gathered on rank 0;
+  * the VAE decodes all frames of a chunk in one batch.
+
+Out of the hot path, kept as overridable hooks exactly like the reference methods:
+``prepare_reference_latent``, ``prepare_kps_feature``, ``prepare_audio_embeddings`` and the ReferenceNet write
+pass; they run whatever torch modules the caller registered.
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable, List, Optional, Union
+
+import torch
+
+from .. import ops
+from ..modules.mutual_self_attention import ReferenceAttentionControl
+from ..modules.unet_3d import UNet3DConditionModel
+from .context import window_table
+from .scheduler import ddim_coefficients
+
+BF16 = torch.bfloat16
+
+
+def retrieve_timesteps(scheduler, num_inference_steps=None, device=None, timesteps=None, **kwargs):
+    """Reference pipelines/v_express_pipeline.py:27-68 (custom timestep lists are not used on this path)."""
+    if timesteps is not None:
+        raise ValueError("custom timestep schedules are not supported by the DDIM hot path")
+    scheduler.set_timesteps(num_inference_steps, device=device, **kwargs)
+    return scheduler.timesteps, num_inference_steps
+
+
+def partition_windows(num_windows: int, world_size: int, rank: int):
+    """Contiguous, balanced block of window indices owned by ``rank`` (47 windows over 8 ranks ->
+    6,6,6,6,6,6,6,5)."""
+    base, rem = divmod(num_windows, world_size)
+    start = rank * base + min(rank, rem)
+    return list(range(start, start + base + (1 if rank < rem else 0)))
+
+
+class _GraphedUNet:
+    """One CUDA graph of ``UNetEngine.forward_frames`` per (b, f, h, w) signature with static I/O buffers."""
+
+    def __init__(self, engine, b, f, h, w, enc_tokens, cross_dim, use_graph=True):
+        dev = engine.dev
+        self.engine, self.b, self.f = engine, b, f
+        self.frames = torch.zeros((b * f, 4, h, w), device=dev, dtype=BF16)
+        self.enc = torch.zeros((b * f, enc_tokens, cross_dim), device=dev, dtype=BF16)
+        self.kps_idx = torch.zeros((b * f,), device=dev, dtype=torch.int32)
+        self.temb = None
+        self.kps = None
+        self.graph = None
+        self.out = None
+        self.use_graph = use_graph
+
+    def _run(self):
+        return self.engine.forward_frames(self.frames, None, self.enc, self.kps, self.kps_idx, self.b, self.f,
+                                          temb=self.temb)
+
+    def __call__(self, temb, kps):
+        if self.temb is None:
+            self.temb = torch.empty_like(temb)
+        self.temb.copy_(temb)
+        if not self.use_graph:
+            self.kps = kps
+            return self._run()
+        if self.graph is None or self.kps is not kps:
+            self.kps = kps
+            # warm-up on a side stream (allocator + lazy module state), then capture
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                self._run()
+            torch.cuda.current_stream().wait_stream(s)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.out = self._run()
+        self.graph.replay()
+        return self.out
+
+
+class VExpressPipeline:
+    _optional_components: List[str] = []
+
+    def __init__(self, vae, reference_net, denoising_unet, v_kps_guider, audio_processor, audio_encoder,
+                 audio_projection, scheduler, image_proj_model=None, tokenizer=None, text_encoder=None):
+        self.vae = vae
+        self.reference_net = reference_net
+        self.denoising_unet = denoising_unet
+        self.v_kps_guider = v_kps_guider
+        self.audio_processor = audio_processor
+        self.audio_encoder = audio_encoder
+        self.audio_projection = audio_projection
+        self.scheduler = scheduler
+        self.image_proj_model, self.tokenizer, self.text_encoder = image_proj_model, tokenizer, text_encoder
+        boc = getattr(getattr(vae, "config", {}), "get", lambda *_: None)("block_out_channels")
+        self.vae_scale_factor = 2 ** (len(boc) - 1) if boc else 8
+        self.use_cuda_graph = True
+        self.vae_chunk = 16
+        self._graphs = {}
+
+    # ------------------------------------------------------------------ diffusers-style conveniences
+    @property
+    def device(self):
+        return self.denoising_unet.device
+
+    @property
+    def dtype(self):
+        return self.denoising_unet.dtype
+
+    def to(self, *args, **kwargs):
+        for m in (self.vae, self.reference_net, self.denoising_unet, self.v_kps_guider, self.audio_encoder,
+                  self.audio_projection):
+            if isinstance(m, torch.nn.Module):
+                m.to(*args, **kwargs)
+        return self
+
+    def progress_bar(self, iterable=None, total=None):
+        from tqdm import tqdm
+        return tqdm(iterable, total=total, disable=True)
+
+    # ------------------------------------------------------------------ prologue hooks (outside the hot path)
+    def prepare_reference_latent(self, reference_image, height, width):
+        raise NotImplementedError("prologue hook: VAE encode of the reference image is outside the hot path "
+                                  "(SURVEY.md 8f-f4); override or pass precomputed banks")
+
+    def prepare_kps_feature(self, kps_images, height, width, do_classifier_free_guidance):
+        raise NotImplementedError("prologue hook: VKpsGuider is outside the hot path (SURVEY.md 8f-f2)")
+
+    def prepare_audio_embeddings(self, audio_waveform, video_length, num_pad_audio_frames, do_classifier_free_guidance):
+        raise NotImplementedError("prologue hook: wav2vec2 + AudioProjection are outside the hot path (SURVEY.md 8f)")
+
+    def run_reference_net(self, reference_image_latents, writer):
+        """Reference pipelines/v_express_pipeline.py:502-508: one ReferenceNet pass at t=0 fills the writer banks."""
+        enc = torch.zeros((1, 1, 768), dtype=self.dtype, device=self.device)
+        self.reference_net(reference_image_latents, timestep=0, encoder_hidden_states=enc, return_dict=False)
+
+    def prepare_latents(self, batch_size, num_channels_latents, width, height, video_length, dtype, device, generator,
+                        latents=None):
+        """Reference :189-224: noise is drawn on the HOST in the model dtype so seeds reproduce (:514-523)."""
+        shape = (batch_size, num_channels_latents, video_length, height // self.vae_scale_factor,
+                 width // self.vae_scale_factor)
+        if isinstance(generator, list) and len(generator) != batch_size:
+            raise ValueError(f"You have passed a list of generators of length {len(generator)}, but requested an "
+                             f"effective batch size of {batch_size}. Make sure the batch size matches the length of "
+                             f"the generators.")
+        if latents is None:
+            latents = torch.randn(shape, generator=generator, device="cpu", dtype=dtype)
+        return latents * self.scheduler.init_noise_sigma
+
+    def get_timesteps(self, num_inference_steps, strength, device):
+        init_timestep = min(int(num_inference_steps * strength), num_inference_steps)
+        t_start = max(num_inference_steps - init_timestep, 0)
+        return self.scheduler.timesteps[t_start * self.scheduler.order:], num_inference_steps - t_start
+
+    # ------------------------------------------------------------------ decode
+    @torch.no_grad()
+    def decode_latents(self, latents, frame_ids=None):
+        """latents (1,4,L,h,w) on the device -> (1,3,L,H,W) fp32 on the host in [0,1] (reference :152-166).
+        ``frame_ids`` restricts the decode to a subset (multi-GPU sharding)."""
+        L = latents.shape[2]
+        ids = list(range(L)) if frame_ids is None else list(frame_ids)
+        z = latents[0].permute(1, 0, 2, 3)[ids].contiguous()                    # (n,4,h,w)
+        outs = []
+        for i in range(0, z.shape[0], self.vae_chunk):
+            outs.append(self.vae.decode_latents(z[i:i + self.vae_chunk]))
+        video = torch.cat(outs) if outs else torch.empty((0, 3, latents.shape[3] * 8, latents.shape[4] * 8),
+                                                         device=latents.device)
+        return video                                                            # (n,3,H,W) fp32, device
+
+    # ------------------------------------------------------------------ the hot loop
+    @torch.no_grad()
+    def denoise(self, latents, kps_feature, audio_embeddings, timesteps, guidance_scale, context_frames,
+                context_overlap, context_schedule="uniform", distributed=False, callback=None, callback_steps=1):
+        """latents (1,4,L,h,w) bf16 device (updated in place and returned); kps_feature (b,C0,L,h,w) device;
+        audio_embeddings (b,L,T,768) device.  Steps x windows with overlap averaging, CFG and DDIM
+        (reference :486-500,514-589)."""
+        unet: UNet3DConditionModel = self.denoising_unet
+        eng = unet.engine()
+        dev = latents.device
+        _, _, L, h, w = latents.shape
+        hw = h * w
+        do_cfg = guidance_scale > 1.0
+        b = 2 if do_cfg else 1
+        windows, count = window_table(L, context_frames, context_overlap, context_schedule)
+        if any(len(set(wn)) != len(wn) for wn in windows):
+            # reflected tail windows repeat frames; the reference's bookkeeping for them is inconsistent
+            #  and its CLI always picks a tiling length, so refuse instead of guessing
+            raise ValueError(f"video_length={L} does not tile with context_frames={context_frames}, "
+                             f"context_overlap={context_overlap}: a window would contain duplicate frames")
+        rank, world = 0, 1
+        if distributed and torch.distributed.is_available() and torch.distributed.is_initialized():
+            rank, world = torch.distributed.get_rank(), torch.distributed.get_world_size()
+        mine = partition_windows(len(windows), world, rank)
+        count_dev = torch.from_numpy(count).to(device=dev, dtype=torch.int32)
+        # channels-last kps for all frames, row block (bi*L + frame); stays resident for the whole video
+        C0 = kps_feature.shape[1]
+        kps_nhwc = kps_feature.to(device=dev, dtype=BF16).permute(0, 2, 3, 4, 1).reshape(b * L * hw, C0).contiguous()
+        audio = audio_embeddings.to(device=dev, dtype=BF16)
+        T = audio.shape[2]
+        acc = torch.zeros((4, L, hw), device=dev, dtype=torch.float32)
+        win_dev = [torch.tensor(wn, device=dev, dtype=torch.int32) for wn in windows]
+        win_long = [t.long() for t in win_dev]
+        lat = latents[0]                                                        # (4, L, h, w) view
+        graphs = {}
+        for i, t in enumerate(timesteps):
+            temb = eng.time_embedding(int(t))
+            acc.zero_()
+            for wi in mine:
+                window = windows[wi]
+                f = len(window)
+                key = (b, f, h, w)
+                g = graphs.get(key)
+                if g is None:
+                    g = graphs[key] = _GraphedUNet(eng, b, f, h, w, T, audio.shape[-1], self.use_cuda_graph)
+                x = lat[:, win_long[wi]].permute(1, 0, 2, 3)                    # (f,4,h,w)
+                g.frames[:f].copy_(x)
+                if do_cfg:
+                    g.frames[f:].copy_(x)
+                g.enc.copy_(audio[:, win_long[wi]].reshape(b * f, T, -1))
+                for bi in range(b):
+                    g.kps_idx[bi * f:(bi + 1) * f].copy_(win_dev[wi] + bi * L)
+                noise = g(temb, kps_nhwc)                                       # ((b f),4,h,w) bf16
+                ops.cfg_overlap_accumulate(noise, f, hw, L, do_cfg, win_dev[wi], count_dev, float(guidance_scale), acc)
+            if world > 1:
+                torch.distributed.all_reduce(acc, op=torch.distributed.ReduceOp.SUM)
+            sa, sb, sap, sbp = ddim_coefficients(self.scheduler, int(t))
+            ops.ddim_step(lat, acc, sa, sb, sap, sbp)
+            if callback is not None and i % callback_steps == 0:
+                callback(i, t, latents)
+        return latents
+
+    @torch.no_grad()
+    def mean_overlap(self, reference_image, kps_images, audio_waveform, width, height, video_length,
+                     num_inference_steps, guidance_scale, strength=1., num_images_per_prompt=1, eta: float = 0.0,
+                     generator: Optional[Union[torch.Generator, List[torch.Generator]]] = None,
+                     output_type: Optional[str] = "tensor", return_dict: bool = True,
+                     callback: Optional[Callable] = None, callback_steps: Optional[int] = 1,
+                     context_schedule="uniform", context_frames=24, context_overlap=4, reference_attention_weight=1.,
+                     audio_attention_weight=1., num_pad_audio_frames=2, do_multi_devices_inference=False,
+                     save_gpu_memory=False, **kwargs):
+        if eta != 0.0:
+            raise ValueError("the DDIM hot path is deterministic (eta = 0), like the reference CLI")
+        device = self.device
+        do_cfg = guidance_scale > 1.0
+        batch_size = 1
+        timesteps, num_inference_steps = retrieve_timesteps(self.scheduler, num_inference_steps, device, None)
+        timesteps, num_inference_steps = self.get_timesteps(num_inference_steps, strength, device)
+
+        writer = ReferenceAttentionControl(self.reference_net, do_classifier_free_guidance=do_cfg, mode="write",
+                                           batch_size=batch_size, fusion_blocks="full")
+        reader = ReferenceAttentionControl(self.denoising_unet, do_classifier_free_guidance=do_cfg, mode="read",
+                                           batch_size=batch_size, fusion_blocks="full",
+                                           reference_attention_weight=reference_attention_weight,
+                                           audio_attention_weight=audio_attention_weight)
+        num_channels_latents = self.denoising_unet.in_channels
+        reference_image_latents = self.prepare_reference_latent(reference_image, height, width)
+        kps_feature = self.prepare_kps_feature(kps_images, height, width, do_cfg)
+        audio_embeddings = self.prepare_audio_embeddings(audio_waveform, video_length, num_pad_audio_frames, do_cfg)
+        self.run_reference_net(reference_image_latents, writer)
+        reader.update(getattr(self.reference_net, "writer_view", writer), do_cfg, dtype=self.dtype)
+
+        latents = self.prepare_latents(batch_size * num_images_per_prompt, num_channels_latents, width, height,
+                                       video_length, self.dtype, torch.device("cpu"), generator)
+        latents = latents.to(device=device, dtype=BF16, non_blocking=True)      # one H2D for the whole video
+        distributed = bool(do_multi_devices_inference)
+        latents = self.denoise(latents, kps_feature, audio_embeddings, timesteps, guidance_scale, context_frames,
+                               context_overlap, context_schedule, distributed, callback, callback_steps)
+        reader.clear()
+        if hasattr(writer, "clear") and isinstance(getattr(writer, "unet", None), torch.nn.Module):
+            try:
+                writer.clear()
+            except Exception:
+                pass
+        return self._decode_to_host(latents, distributed)
+
+    def _decode_to_host(self, latents, distributed):
+        L = latents.shape[2]
+        rank, world = 0, 1
+        if distributed and torch.distributed.is_available() and torch.distributed.is_initialized():
+            rank, world = torch.distributed.get_rank(), torch.distributed.get_world_size()
+        if world == 1:
+            video = self.decode_latents(latents)
+            video = video.cpu()                                                  # one D2H for the whole video
+            return video.permute(1, 0, 2, 3).unsqueeze(0).contiguous()
+        per = math.ceil(L / world)
+        ids = list(range(rank * per, min(L, (rank + 1) * per)))
+        part = self.decode_latents(latents, ids)
+        H, W = latents.shape[3] * 8, latents.shape[4] * 8
+        buf = torch.zeros((per, 3, H, W), device=latents.device, dtype=torch.float32)
+        buf[:part.shape[0]].copy_(part)
+        gathered = [torch.empty_like(buf) for _ in range(world)] if rank == 0 else None
+        torch.distributed.gather(buf, gathered, dst=0)
+        if rank != 0:
+            return None
+        video = torch.cat(gathered)[:L].cpu()
+        return video.permute(1, 0, 2, 3).unsqueeze(0).contiguous()
+
+    def __call__(self, reference_image, kps_images, audio_waveform, width, height, video_length, num_inference_steps,
+                 guidance_scale, strength=1., num_images_per_prompt=1, eta: float = 0.0, generator=None,
+                 output_type: Optional[str] = "tensor", return_dict: bool = True, callback=None, callback_steps=1,
+                 context_schedule="uniform", context_frames=24, context_overlap=4, reference_attention_weight=1.,
+                 audio_attention_weight=1., num_pad_audio_frames=2, do_multi_devices_inference=False,
+                 save_gpu_memory=False, **kwargs):
+        return self.mean_overlap(
+            reference_image=reference_image, kps_images=kps_images, audio_waveform=audio_waveform, width=width,
+            height=height, video_length=video_length, num_inference_steps=num_inference_steps,
+            guidance_scale=guidance_scale, strength=strength, num_images_per_prompt=num_images_per_prompt, eta=eta,
+            generator=generator, output_type=output_type, return_dict=return_dict, callback=callback,
+            callback_steps=callback_steps, context_schedule=context_schedule, context_frames=context_frames,
+            context_overlap=context_overlap, reference_attention_weight=reference_attention_weight,
+            audio_attention_weight=audio_attention_weight, num_pad_audio_frames=num_pad_audio_frames,
+            do_multi_devices_inference=do_multi_devices_inference, save_gpu_memory=save_gpu_memory, **kwargs)
