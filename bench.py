@@ -1,0 +1,471 @@
+#!/usr/bin/env python
+"""Benchmark of the V-Express denoising hot path on B200 (contract: see the task brief / DESIGN.md section 6).
+
+  python bench.py --gpus N --steps K --warmup W            # our arm (CUDA kernels through the C ABI)
+  python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host cores (oracle port)
+
+One bench "step" = one pass of the whole hot path over one synthetic video: 25 DDIM steps x all context windows
+through the denoising UNet (CFG, overlap averaging) followed by the VAE decode of every frame.
+N = 1 runs BASELINE.json configs[1] (512x512, one 16-frame window, 25 steps, bf16).  N > 1 is weak scaling: N windows
+of 16 frames (overlap 8), one per rank, one NCCL all-reduce of the overlap noise-prediction sums per DDIM step,
+VAE decode sharded by frame.  Rank 0 prints ONE JSON line.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+UNET_EXTRA = dict(
+    use_inflated_groupnorm=True, unet_use_cross_frame_attention=False, unet_use_temporal_attention=False,
+    use_motion_module=True, motion_module_resolutions=[1, 2, 4, 8], motion_module_mid_block=True,
+    motion_module_decoder_only=False, motion_module_type="Vanilla",
+    motion_module_kwargs=dict(num_attention_heads=8, num_transformer_block=1,
+                              attention_block_types=["Temporal_Self", "Temporal_Self"],
+                              temporal_position_encoding=True, temporal_position_encoding_max_len=32,
+                              temporal_attention_dim_div=1))
+
+# canonical algorithmic work (SURVEY.md 8d / BASELINE.md 3), bf16, per CFG window-forward (b=2, f=16) at 512^2
+UNET_TFLOP_PER_FRAME_EVAL = 1.2768
+VAE_TFLOP_PER_FRAME = 2.515
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d["bf16_tflops_sustained"],
+                    source="measured")
+    return dict(hbm_gbs=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
+
+
+# --------------------------------------------------------------------------------------------- synthetic model
+def fill_synthetic_(module, seed):
+    """Random init in the reference's state_dict layout: W ~ randn/sqrt(fan_in), biases 0.02 randn,
+    norm weights 1 + 0.02 randn; zero-initialised branches (motion proj_out, attn2.to_out) are NOT zeroed."""
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    for name, p in module.named_parameters():
+        mod = name.split(".")[-2]
+        is_norm = "norm" in mod or (len(name.split(".")) > 2 and name.split(".")[-3] == "norms")
+        if is_norm:
+            p.data = (1.0 if name.endswith("weight") else 0.0) + 0.02 * torch.randn(p.shape, device="cuda", generator=g)
+        elif name.endswith(".bias"):
+            p.data = 0.02 * torch.randn(p.shape, device="cuda", generator=g)
+        else:
+            fan_in = int(math.prod(p.shape[1:]))
+            p.data = torch.randn(p.shape, device="cuda", generator=g) / math.sqrt(fan_in)
+
+
+def ln_rows(x):
+    return torch.nn.functional.layer_norm(x, (x.shape[-1],))
+
+
+def build_ours(L, h, device):
+    from vexpress_b200.modules import UNet3DConditionModel
+    from vexpress_b200.modules.unet_3d import attention_block_order
+    from vexpress_b200.modules.vae import AutoencoderKL
+    from vexpress_b200.pipelines.scheduler import DDIMScheduler
+    from vexpress_b200.pipelines.v_express_pipeline import VExpressPipeline
+    with torch.device(device):
+        unet = UNet3DConditionModel(cross_attention_dim=768, **UNET_EXTRA)
+        vae = AutoencoderKL()
+    fill_synthetic_(unet, 1234)
+    fill_synthetic_(vae, 1235)
+    unet = unet.to(torch.bfloat16)
+    vae = vae.to(torch.bfloat16)
+    g = torch.Generator().manual_seed(42)
+    lat = torch.randn(1, 4, L, h, h, generator=g).to(torch.bfloat16)
+    kps = torch.cat([torch.zeros(1, 320, L, h, h), 0.1 * torch.randn(1, 320, L, h, h, generator=g)]).to(torch.bfloat16)
+    audio = ln_rows(torch.randn(1, L, 5, 768, generator=g))
+    audio = torch.cat([torch.zeros_like(audio), audio]).to(torch.bfloat16)
+    mods = dict(unet.named_modules())
+    banks = []
+    for name in attention_block_order(unet):
+        C = mods[name].norm1.normalized_shape[0]
+        parts = name.split(".")
+        lvl = int(parts[1]) if parts[0] == "down_blocks" else (3 - int(parts[1]) if parts[0] == "up_blocks" else 3)
+        N = (h >> lvl) ** 2
+        banks.append(ln_rows(torch.randn(1, N, C, generator=g)).to(device=device, dtype=torch.bfloat16))
+    host = dict(lat=lat.pin_memory(), kps=kps.pin_memory(), audio=audio.pin_memory())
+
+    class Writer:
+        pass
+    wv = Writer()
+    wv.banks = banks
+
+    class RefNetStub(torch.nn.Module):
+        writer_view = wv
+
+        def forward(self, *a, **k):
+            return None
+
+    class Pipe(VExpressPipeline):
+        # synthetic prologue: precomputed dummy conditioning, host resident (north_star)
+        def prepare_reference_latent(self, *a, **k):
+            return None
+
+        def prepare_kps_feature(self, *a, **k):
+            return host["kps"]
+
+        def prepare_audio_embeddings(self, *a, **k):
+            return host["audio"]
+
+        def run_reference_net(self, *a, **k):
+            return None
+
+        def prepare_latents(self, *a, **k):
+            return host["lat"]
+
+    pipe = Pipe(vae=vae, reference_net=RefNetStub(), denoising_unet=unet, v_kps_guider=None, audio_processor=None,
+                audio_encoder=None, audio_projection=None, scheduler=DDIMScheduler())
+    return pipe, host, banks
+
+
+# --------------------------------------------------------------------------------------------- clocks sampler
+class Clocks:
+    def __init__(self, index):
+        self.rows, self.stop, self.index = [], False, index
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop:
+            try:
+                o = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                   capture_output=True, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.rows.append([c.strip() for c in o.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["unavailable"])
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=int(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
+                    reasons=reasons, samples=len(self.rows))
+
+
+# --------------------------------------------------------------------------------------------- kernel timing
+def kernel_roofline(pipe, host, L, h):
+    """Time every launch of the dominant kernel (tcgen05 GEMM / implicit-GEMM conv) of ONE eager UNet forward with
+    CUDA events on the launching stream; achieved = sum(2*M*N*K) / sum(duration)."""
+    from vexpress_b200 import ops
+    recs = []
+    orig = dict(gemm=ops.gemm, conv3x3=ops.conv3x3, flash_attention=ops.flash_attention)
+
+    def timed(name, fn, flops_of):
+        def w(*a, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = fn(*a, **k)
+            e1.record()
+            recs.append((name, flops_of(a, k, out), e0, e1))
+            return out
+        return w
+
+    def f_gemm(a, k, out):
+        K = a[0].shape[1] + (k["a2"].shape[1] if k.get("a2") is not None else 0)
+        return 2.0 * a[0].shape[0] * a[1].shape[0] * K
+
+    def f_conv(a, k, out):
+        nb, hh, ww, c = a[0].shape
+        return 2.0 * nb * hh * ww * 9 * c * a[1].shape[0]
+
+    def f_fa(a, k, out):
+        q, heads, nq, nk = a[0], a[3], a[4], a[5]
+        return 4.0 * q.shape[0] * nk * q.shape[1]
+
+    ops.gemm = timed("gemm", orig["gemm"], f_gemm)
+    ops.conv3x3 = timed("conv3x3", orig["conv3x3"], f_conv)
+    ops.flash_attention = timed("flash", orig["flash_attention"], f_fa)
+    try:
+        eng = pipe.denoising_unet.engine()
+        f = min(L, 16)
+        frames = host["lat"].cuda()[0, :, :f].permute(1, 0, 2, 3).repeat(2, 1, 1, 1).contiguous()
+        enc = host["audio"].cuda()[:, :f].reshape(2 * f, 5, 768)
+        kps = host["kps"].cuda()[:, :, :f].permute(0, 2, 3, 4, 1).reshape(2 * f * h * h, 320).contiguous()
+        for it in range(2):                      # first pass warms caches / lazily packed state
+            recs.clear()
+            eng.forward_frames(frames, 499, enc, kps, None, 2, f)
+            torch.cuda.synchronize()
+    finally:
+        ops.gemm, ops.conv3x3, ops.flash_attention = orig["gemm"], orig["conv3x3"], orig["flash_attention"]
+    agg = {}
+    for name, fl, e0, e1 in recs:
+        d = agg.setdefault(name, [0.0, 0.0, 0])
+        d[0] += fl
+        d[1] += e0.elapsed_time(e1) * 1e-3
+        d[2] += 1
+    return {k: dict(tflops=v[0] / v[1] / 1e12, seconds=v[1], launches=v[2], flop=v[0]) for k, v in agg.items()}
+
+
+# --------------------------------------------------------------------------------------------- CPU arms
+def cpu_sample(threads=None):
+    """Bounded sample of the reference algorithm (oracle port, fp32) on the host cores: one full-width UNet forward
+    at (b=2, f=1, 64x64) = the per-frame cost of one CFG denoise step, and one 1-frame VAE decode at 512x512.
+    frames/s of the 25-step workload = 1 / (25 * t_unet + t_vae)."""
+    from oracle import vx_oracle as O
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    cfg, vcfg = O.DEFAULT_CFG, O.VAE_CFG
+    g = torch.Generator().manual_seed(0)
+
+    def synth(shapes):
+        sd = {}
+        for k, shp in shapes.items():
+            if k.endswith("pos_encoder.pe"):
+                sd[k] = O.positional_encoding(shp[2], shp[1])
+            elif len(shp) == 1:
+                sd[k] = (1.0 if ("norm" in k and k.endswith("weight")) else 0.0) + 0.02 * torch.randn(shp, generator=g)
+            else:
+                sd[k] = torch.randn(shp, generator=g) / math.sqrt(math.prod(shp[1:]))
+        return sd
+    sd = synth(O.unet_param_shapes(cfg))
+    vsd = synth(O.vae_param_shapes(vcfg))
+    lat, kps, audio, banks = O.synth_inputs(cfg, 1, 64, 64, True, 42)
+    x = lat.repeat(2, 1, 1, 1, 1)
+    enc = audio.reshape(-1, 5, 768)
+    z = torch.randn(1, 4, 64, 64, generator=g)
+
+    def run():
+        with torch.no_grad():
+            t0 = time.perf_counter()
+            O.unet_forward(sd, cfg, x, 499, enc, kps, banks, 0.95, 3.0)
+            t1 = time.perf_counter()
+            O.vae_decode(vsd, vcfg, z)
+            t2 = time.perf_counter()
+        return t1 - t0, t2 - t1
+    return run, threads
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    run, threads = cpu_sample()
+    for _ in range(args.warmup):
+        run()
+    tu = tv = 0.0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        a, b = run()
+        tu += a
+        tv += b
+    wall = time.perf_counter() - t0
+    tu /= args.steps
+    tv /= args.steps
+    fps = 1.0 / (25 * tu + tv)
+    sample = (f"per step: 1 full-width UNet forward (b=2 CFG, f=1, 64x64 latents, fp32) = {tu:.2f}s and 1 VAE decode of one "
+              f"512x512 frame = {tv:.2f}s; frames/s = 1/(25*t_unet + t_vae)")
+    line = dict(metric="frames_per_sec_512x512_25step", value=fps, unit="frames/s", n_gpus=args.gpus, steps=args.steps,
+                warmup=args.warmup, ms_per_step=wall / args.steps * 1e3, higher_is_better=True, scaling="weak",
+                vs_baseline=None, dtype="f32", data="synthetic", impl="reference",
+                config=workload_config(args.gpus),
+                cpu_baseline=dict(value=fps, unit="frames/s", cores=threads, kind="port", sample=sample),
+                e2e=dict(value=fps, unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                unet_ms_per_step=tu * 16 * 1e3)
+    print(json.dumps(line))
+
+
+def workload_config(n):
+    L = 16 if n == 1 else 8 * n + 8
+    return dict(workload=("BASELINE configs[1]: 512x512, single 16-frame context window, 25 DDIM steps, CFG 3.5, bf16"
+                          if n == 1 else
+                          f"512x512, {L} frames = {n} context windows (window 16, overlap 8), one window per rank, 25 DDIM "
+                          f"steps, CFG 3.5, bf16, NCCL all-reduce of overlap noise-pred per step, VAE decode sharded by frame"),
+                video_length=L, context_frames=16, context_overlap=8, num_inference_steps=25, guidance_scale=3.5,
+                l2="inputs+weights per step (2.7 GB weights, >10 GB activations) far exceed the 126 MB L2; no flush needed",
+                parallelism=f"windows-dp{n}")
+
+
+# --------------------------------------------------------------------------------------------- our arm
+def ours(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = world > 1
+    if dist:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.distributed.init_process_group("nccl", device_id=dev)
+    n = world
+    cfgw = workload_config(n)
+    L, h, steps_ddim, gs = cfgw["video_length"], 64, 25, 3.5
+    from vexpress_b200 import _ffi
+    pipe, host, banks = build_ours(L, h, dev)
+    from vexpress_b200.modules import ReferenceAttentionControl
+    from vexpress_b200.pipelines.v_express_pipeline import retrieve_timesteps
+    reader = ReferenceAttentionControl(pipe.denoising_unet, do_classifier_free_guidance=True, mode="read",
+                                       fusion_blocks="full", reference_attention_weight=0.95, audio_attention_weight=3.0)
+    reader.update(pipe.reference_net.writer_view, True, dtype=torch.bfloat16)
+    timesteps, _ = retrieve_timesteps(pipe.scheduler, steps_ddim, dev)
+    kps_dev, audio_dev, lat_dev = host["kps"].to(dev), host["audio"].to(dev), host["lat"].to(dev)
+
+    def barrier():
+        if dist:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def resident_pass():
+        lat = pipe.denoise(lat_dev.clone(), kps_dev, audio_dev, timesteps, gs, 16, 8, distributed=dist)
+        return pipe_decode_device(pipe, lat, dist)
+
+    def e2e_pass():
+        return pipe(reference_image=None, kps_images=None, audio_waveform=None, width=512, height=512, video_length=L,
+                    num_inference_steps=steps_ddim, guidance_scale=gs, context_frames=16, context_overlap=8,
+                    reference_attention_weight=0.95, audio_attention_weight=3.0, do_multi_devices_inference=dist)
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = _ffi.LAUNCHES
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = max(e0.elapsed_time(e1), 0.0)
+        t = torch.tensor([ms, wall * 1e3], device=dev)
+        if dist:
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        return t[0].item() / 1e3, t[1].item() / 1e3, _ffi.LAUNCHES - l0
+
+    for _ in range(args.warmup):
+        resident_pass()
+    with Clocks(local) as clk:
+        sec, _, launches_direct = timed(resident_pass, args.steps)
+    clocks = clk.summary()
+    for _ in range(max(1, min(args.warmup, 1))):
+        e2e_pass()
+    _, e2e_wall, _ = timed(e2e_pass, args.steps)
+
+    # UNet-only time per DDIM step (device events around the denoise loop)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    pipe.denoise(lat_dev.clone(), kps_dev, audio_dev, timesteps, gs, 16, 8, distributed=dist)
+    e1.record()
+    torch.cuda.synchronize()
+    unet_ms_per_step = e0.elapsed_time(e1) / steps_ddim
+
+    if rank == 0:
+        pk = peaks()
+        roof_k = kernel_roofline(pipe, host, L, h) if n == 1 else None
+        fps = L * args.steps / sec
+        e2e_fps = L * args.steps / e2e_wall
+        windows = n
+        work_tflop = steps_ddim * windows * 32 * UNET_TFLOP_PER_FRAME_EVAL + L * VAE_TFLOP_PER_FRAME
+        line = dict(metric="frames_per_sec_512x512_25step", value=fps, unit="frames/s", n_gpus=n, steps=args.steps,
+                    warmup=args.warmup, ms_per_step=sec / args.steps * 1e3, higher_is_better=True, scaling="weak",
+                    vs_baseline=None, dtype="bf16", data="synthetic (random-init weights, dummy audio/kps/bank tensors)",
+                    config=cfgw, clocks=clocks,
+                    e2e=dict(value=e2e_fps, unit="frames/s",
+                             h2d_bytes_per_step=int(sum(v.numel() * v.element_size() for v in host.values())),
+                             d2h_bytes_per_step=int(L * 3 * 512 * 512 * 4)),
+                    gpu_launches=int(launches_direct),
+                    unet_ms_per_step=unet_ms_per_step,
+                    whole_path=dict(tflop_per_pass=work_tflop, achieved_tflops=work_tflop * args.steps / sec / n,
+                                    frac_of_sustained_peak=work_tflop * args.steps / sec / n / pk["tf_sustained"]))
+        if roof_k:
+            dom = dict(tflops=0.0, seconds=0.0, launches=0, flop=0.0)
+            for k in ("gemm", "conv3x3"):
+                if k in roof_k:
+                    for kk in ("seconds", "launches", "flop"):
+                        dom[kk] += roof_k[k][kk]
+            ach = dom["flop"] / dom["seconds"] / 1e12
+            traffic = None
+            tp = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
+            if os.path.exists(tp):
+                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            line["roofline"] = dict(bound="tensor", kernel="gemm_tcgen05_kernel (GEMM + implicit-GEMM 3x3 conv)",
+                                    achieved=ach, peak=pk["tf_sustained"], unit="TFLOP/s", frac=ach / pk["tf_sustained"],
+                                    traffic=traffic, peak_source=pk["source"] + " (sustained cuBLAS bf16)",
+                                    launches_per_forward=dom["launches"], seconds_per_forward=dom["seconds"],
+                                    flash_attention=roof_k.get("flash"))
+        print(json.dumps(line))
+    if dist:
+        torch.distributed.destroy_process_group()
+
+
+def pipe_decode_device(pipe, latents, dist):
+    """Decode with the result left on the device (HBM-resident `value` measurement); rank 0 gathers the shards."""
+    L = latents.shape[2]
+    if not dist:
+        return pipe.decode_latents(latents)
+    rank, world = torch.distributed.get_rank(), torch.distributed.get_world_size()
+    per = math.ceil(L / world)
+    ids = list(range(rank * per, min(L, (rank + 1) * per)))
+    part = pipe.decode_latents(latents, ids)
+    buf = torch.zeros((per, 3, latents.shape[3] * 8, latents.shape[4] * 8), device=latents.device, dtype=torch.float32)
+    buf[:part.shape[0]].copy_(part)
+    gathered = [torch.empty_like(buf) for _ in range(world)] if rank == 0 else None
+    torch.distributed.gather(buf, gathered, dst=0)
+    return gathered
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU path; use --impl reference for the CPU baseline)")
+    ours_with_cpu_baseline(args)
+
+
+def ours_with_cpu_baseline(args):
+    # cpu_baseline is measured on rank 0 at N=1 in a subprocess (bounded sample) and merged into the line
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cpu = None
+    if rank == 0 and world == 1 and not os.environ.get("VX_BENCH_NO_CPU"):
+        try:
+            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1",
+                                  "--warmup", "0"], capture_output=True, text=True, timeout=900)
+            cpu = json.loads(out.stdout.strip().splitlines()[-1])["cpu_baseline"]
+        except Exception as e:  # the CPU leg must never take the GPU number down with it
+            cpu = dict(value=None, unit="frames/s", cores=os.cpu_count(), kind="port", sample=f"failed: {e}")
+    import io
+    from contextlib import redirect_stdout
+    buf = io.StringIO()
+    with redirect_stdout(buf):
+        ours(args)
+    txt = buf.getvalue().strip()
+    if rank == 0 and txt:
+        line = json.loads(txt.splitlines()[-1])
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,141 @@
+"""Host-side logic and the C-ABI surface, no GPU: symbol export, product context scheduler vs reference golden,
+parameter layout vs oracle, DDIM tables, window partition, 2-rank gloo check of the overlap all-reduce."""
+import ctypes
+import json
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+def test_library_exports_every_declared_symbol():
+    from vexpress_b200 import _ffi
+    lib = _ffi.lib()
+    hdr = open(os.path.join(ROOT, "include", "vxb200.h")).read()
+    syms = sorted(set(re.findall(r"\b(vx_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(syms) >= 24
+    for s in syms:
+        assert getattr(lib, s) is not None, s
+    assert lib.vx_abi_version() == 1
+    lib.vx_groupnorm_stats_ws_floats.restype = ctypes.c_int
+    assert lib.vx_groupnorm_stats_ws_floats(4, 32, 8) == 4 * 32 * 8 * 3
+
+
+def test_product_fails_loudly_without_gpu():
+    """No CPU fallback: building the engine on a CPU box must raise, not silently compute."""
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from vexpress_b200.modules import UNet3DConditionModel
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_unet_gpu import UNET_EXTRA
+    m = UNet3DConditionModel(block_out_channels=(64, 128, 256, 256), cross_attention_dim=768, **UNET_EXTRA)
+    with pytest.raises(Exception):
+        m(torch.zeros(2, 4, 2, 16, 16), 10, encoder_hidden_states=torch.zeros(4, 5, 768))
+
+
+def test_product_context_scheduler_bit_exact(golden_dir):
+    from vexpress_b200.pipelines import context as C
+    g = json.load(open(os.path.join(golden_dir, "context_windows.json")))
+    for c in g["pipeline_calls"]:
+        wins, cnt = C.window_table(c["L"], c["S"], c["O"])
+        assert wins == c["windows"] and cnt.tolist() == c["num_frame_context"], c
+    for c in g["uniform_calls"]:
+        assert list(C.uniform(c["step"], c["L"], c["S"], c["stride"], c["O"], c["closed"])) == c["windows"]
+    for k, v in g["ordered_halving"].items():
+        assert C.ordered_halving(int(k)) == v
+    with pytest.raises(ValueError):
+        C.get_context_scheduler("nope")
+    assert C.compute_num_context(930, 24, 4) == 46 and C.compute_context_indices(2, 24, 4) == [(0, 23), (20, 43)]
+
+
+def test_product_param_layout_matches_oracle_and_reference():
+    from oracle import vx_oracle as O
+    from vexpress_b200.modules.unet_3d import _unet_keys
+    from vexpress_b200.modules.vae import _vae_keys
+    assert _unet_keys((320, 640, 1280, 1280), 768, 2, 4, 4, 32) == O.unet_param_shapes(O.DEFAULT_CFG)
+    assert _vae_keys((128, 256, 512, 512), 2, 4, 3) == O.vae_param_shapes(O.VAE_CFG)
+
+
+def test_product_ddim_tables(golden_dir):
+    from vexpress_b200.pipelines.scheduler import DDIMScheduler, ddim_coefficients
+    from oracle import vx_oracle as O
+    g = json.load(open(os.path.join(golden_dir, "ddim_kat.json")))
+    s, o = DDIMScheduler(), O.DDIM()
+    assert torch.equal(s.alphas_cumprod, o.alphas_cumprod)
+    for n in (2, 25, 50):
+        s.set_timesteps(n)
+        assert s.timesteps.tolist() == g[f"timesteps_{n}"]
+    s.set_timesteps(25)
+    o.set_timesteps(25)
+    for t in (999, 959, 39):
+        sa, sb, sap, sbp = ddim_coefficients(s, t)
+        a_t, a_p = o.coeffs(t)
+        assert sa == float(a_t ** 0.5) and sbp == float((1 - a_p) ** 0.5)
+    with pytest.raises(ValueError):
+        DDIMScheduler(prediction_type="epsilon")
+
+
+def test_unsupported_unet_config_is_rejected():
+    from vexpress_b200.modules import UNet3DConditionModel
+    with pytest.raises(ValueError):
+        UNet3DConditionModel()                       # no motion modules / inflated groupnorm -> not this model
+    with pytest.raises(ValueError):
+        UNet3DConditionModel(mid_block_type="Other")
+
+
+def test_partition_windows():
+    from vexpress_b200.pipelines.v_express_pipeline import partition_windows
+    parts = [partition_windows(47, 8, r) for r in range(8)]
+    assert [len(p) for p in parts] == [6, 6, 6, 6, 6, 6, 6, 5]
+    assert sum(parts, []) == list(range(47))
+    assert partition_windows(1, 4, 0) == [0] and partition_windows(1, 4, 3) == []
+
+
+def _gloo_worker(rank, world, port, L, S, Ov, ret):
+    """Each rank scatters its windows' noise/count into a zero buffer, all-reduces, and must obtain bit-identically
+    the single-process sequential sum (bf16 values, <= 2 contributions per frame)."""
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from vexpress_b200.pipelines.context import window_table
+    from vexpress_b200.pipelines.v_express_pipeline import partition_windows
+    wins, cnt = window_table(L, S, Ov)
+    g = torch.Generator().manual_seed(0)
+    noise = [torch.randn(4, len(w), 16, generator=g).bfloat16() for w in wins]        # per-window predictions
+    cntt = torch.from_numpy(cnt)
+    acc = torch.zeros(4, L, 16)
+    for wi in partition_windows(len(wins), world, rank):
+        w = torch.tensor(wins[wi])
+        v = (noise[wi] / cntt[w].to(torch.bfloat16)[None, :, None])
+        acc[:, w] = (acc[:, w].bfloat16() + v).float()
+    dist.all_reduce(acc)
+    seq = [None] * L                                                                   # reference streaming order
+    for wi, wn in enumerate(wins):
+        v = noise[wi] / cntt[torch.tensor(wn)].to(torch.bfloat16)[None, :, None]
+        for li, fi in enumerate(wn):
+            seq[fi] = v[:, li].clone() if seq[fi] is None else seq[fi] + v[:, li]
+    seq = torch.stack(seq, 1)
+    ok = torch.equal(acc.bfloat16(), seq)
+    if rank == 0:
+        ret.put(bool(ok))
+    dist.destroy_process_group()
+
+
+def test_overlap_allreduce_bit_identical_two_ranks():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, 40, 16, 8, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert ret.get(timeout=5) is True

@@ -27,9 +27,15 @@ def lib():
     return _lib
 
 
+LAUNCHES = 0        # kernels launched through the C ABI by this process (one per successful op call)
+_TIMING = None      # when set to a list, every op call is bracketed by CUDA events: (name, start, end, meta)
+
+
 def check(rc, what=""):
+    global LAUNCHES
     if rc != 0:
         raise VxError(f"{what}: {lib().vx_last_error().decode()}")
+    LAUNCHES += 1
 
 
 def ptr(t):

@@ -25,7 +25,7 @@ from typing import Callable, List, Optional, Union
 
 import torch
 
-from .. import ops
+from .. import _ffi, ops
 from ..modules.mutual_self_attention import ReferenceAttentionControl
 from ..modules.unet_3d import UNet3DConditionModel
 from .context import window_table
@@ -85,9 +85,13 @@ class _GraphedUNet:
                 self._run()
             torch.cuda.current_stream().wait_stream(s)
             self.graph = torch.cuda.CUDAGraph()
+            before = _ffi.LAUNCHES
             with torch.cuda.graph(self.graph):
                 self.out = self._run()
+            self.captured_launches = _ffi.LAUNCHES - before
+            _ffi.LAUNCHES = before            # capture enqueues nothing; replays are counted below
         self.graph.replay()
+        _ffi.LAUNCHES += self.captured_launches
         return self.out
 
 
