@@ -359,10 +359,13 @@ def ours(args):
     with Clocks(local) as clk:
         sec, _, launches_direct = timed(resident_pass, args.steps)
     clocks = clk.summary()
-    for _ in range(max(1, min(args.warmup, 1))):
-        e2e_pass()
-    _, e2e_wall, _ = timed(e2e_pass, args.steps)
-
+    if os.environ.get("VX_NCU_REGION"):
+        # `ncu --profile-from-start off ... python bench.py`: exactly one more pass of the same timed workload
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        resident_pass()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
     # UNet-only time per DDIM step (device events around the denoise loop)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -371,6 +374,12 @@ def ours(args):
     e1.record()
     torch.cuda.synchronize()
     unet_ms_per_step = e0.elapsed_time(e1) / steps_ddim
+
+    for _ in range(max(1, min(args.warmup, 1))):
+        e2e_pass()
+    _, e2e_wall, _ = timed(e2e_pass, args.steps)
+
+    reader.update(pipe.reference_net.writer_view, True, dtype=torch.bfloat16)   # the pipeline call cleared the banks
 
     if rank == 0:
         pk = peaks()
