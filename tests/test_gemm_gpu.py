@@ -61,3 +61,27 @@ def test_conv3x3(ops, NB, H, W, C, Cout):
     err = _rel(out, ref)
     print(f"conv {NB}x{H}x{W}x{C}->{Cout} rel={err:.3e}")
     assert err < 5e-3
+
+
+@pytest.mark.parametrize("M,C", [(1024, 64), (4096, 320), (2048, 1280), (300, 128)])
+def test_gemm_geglu_epilogue(ops, M, C):
+    g = torch.Generator(device="cuda").manual_seed(M + C)
+    x = torch.randn(M, C, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(8 * C, C, device="cuda", generator=g) / C ** 0.5).bfloat16()
+    b = torch.randn(8 * C, device="cuda", generator=g)
+    wp, bp, bn = ops.pack_geglu(w, b)
+    out = ops.gemm(x, wp, bp, geglu=True)
+    h, gate = (x.float() @ w.float().t() + b).chunk(2, -1)
+    ref = h * torch.nn.functional.gelu(gate)
+    err = _rel(out, ref)
+    print(f"geglu-gemm M={M} C={C} bn={bn} rel={err:.3e}")
+    assert out.shape == (M, 4 * C) and err < 5e-3
+
+
+def test_gemm_fp32_out(ops):
+    g = torch.Generator(device="cuda").manual_seed(3)
+    q = torch.randn(4096, 512, device="cuda", generator=g).bfloat16()
+    k = torch.randn(4096, 512, device="cuda", generator=g).bfloat16()
+    out = ops.gemm(q, k, scale=512 ** -0.5, out_f32=True)
+    ref = (q.float() @ k.float().t()) * 512 ** -0.5
+    assert out.dtype == torch.float32 and (out - ref).abs().max().item() < 1e-3

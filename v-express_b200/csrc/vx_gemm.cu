@@ -1,11 +1,11 @@
-// tcgen05 GEMM / implicit-GEMM convolution for sm_100a.
+// tcgen05 GEMM / implicit-GEMM convolution for sm_100a (persistent, warp-specialised).
 //
 //   out[m, n] = (sum_k A[m, k] * W[n, k] + bias[n] + bias2[m / bias2_div, n]) * scale + residual[m, n]
+//   GEGLU mode: W rows are packed per tile as (value | gate); out[m, j] = (v + bias_v) * gelu_erf(g + bias_g)
 //
 // A is bf16 row-major (K contiguous), W is bf16 [N, K] (K contiguous): both operands are K-major, so every
 // 64-wide K block of a 128-row tile is one TMA box that lands in shared memory in the canonical 128B-swizzled
-// K-major layout tcgen05.mma consumes.  Accumulation is fp32 in TMEM; the epilogue reads it back with
-// tcgen05.ld, applies bias / per-sample bias (time embedding) / scale / residual and stores bf16.
+// K-major layout tcgen05.mma consumes.  Accumulation is fp32 in TMEM (two accumulator stages of 256 columns).
 //
 // Three producers share the same MMA + epilogue:
 //   * plain GEMM, optionally split-K over two sources (A | A2) -- the `torch.cat([h, skip])` of the up blocks
@@ -14,8 +14,11 @@
 //     rectangle shifted by (dy-1, dx-1) through a 4-D tensor map (C, W, H, N) whose out-of-bounds reads are
 //     zero-filled by the TMA unit = the zero padding of nn.Conv2d (reference modules/resnet.py:9-17).
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected lane),
-// warps 2..5 = epilogue (one TMEM lane quadrant each).
+// One persistent CTA per SM walks output tiles (n fastest, so concurrently running CTAs share the A rows in L2).
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected lane),
+// warps 2..9 = epilogue: while the MMA warp fills accumulator stage s^1 they drain stage s:
+//   tcgen05.ld -> bias/scale (+ residual read from a TMA-prefetched, 64B-swizzled smem tile) -> bf16 -> same smem
+//   tile -> TMA store (coalesced, clipped at the M/N edges by the tensor map).
 #include "vx_host.h"
 #include "vx_ptx.cuh"
 
@@ -23,62 +26,89 @@ namespace vx {
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;
+constexpr int kEpiThreads = 256;
+constexpr int kPanelCols = 32;                         // staging panel: 32 bf16 = 64 B rows, 64B swizzle
+constexpr int kPanelBytes = kBlockM * kPanelCols * 2;  // 8 KB
 
 struct GemmArgs {
-  int M, N;
-  int kblocks1;   // 64-wide K blocks taken from A (per tap for conv)
-  int kblocks2;   // ... then from A2 (plain mode only)
-  int taps;       // 1 = plain GEMM, 9 = 3x3 conv
-  int block_n;    // UMMA N (multiple of 16, <= 256)
+  int M, N;        // N = number of accumulator columns overall (2x the output width in GEGLU mode)
+  int kblocks1;    // 64-wide K blocks taken from A (per tap for conv)
+  int kblocks2;    // ... then from A2 (plain mode only)
+  int taps;        // 1 = plain GEMM, 9 = 3x3 conv
+  int block_n;     // UMMA N (multiple of 32, <= 256)
   int stages;
   int rows_valid;  // output rows covered by one tile (128 for plain; wbox*hbox*nbox for conv)
   int W, H;        // conv image size
-  int tmem_cols;
+  int tiles_m, tiles_n;
+  int geglu;
+  int has_residual;
+  int out_f32;     // 1: `out` is float* written directly (attention scores feeding an fp32 softmax)
   const float* bias;
   const float* bias2;
   int bias2_div;
   float scale;
-  const __nv_bfloat16* residual;
-  long long ldr;
-  __nv_bfloat16* out;
+  float* out32;
   long long ldc;
-  int out_f32;  // 1: `out` is float* (used for attention scores that feed an fp32 softmax)
 };
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+__device__ __forceinline__ float gelu_erf(float g) { return 0.5f * g * (1.f + erff(g * 0.70710678118654752f)); }
 
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapA2,
-                    const __grid_constant__ CUtensorMap mapB, const GemmArgs p) {
+                    const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapR,
+                    const __grid_constant__ CUtensorMap mapC, const GemmArgs p) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment required by the 128B swizzle atom
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int a_bytes = kBlockM * kBlockK * 2;
   const int b_bytes = p.block_n * kBlockK * 2;
   const int stage_bytes = a_bytes + b_bytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
+  uint8_t* sC = smem + p.stages * stage_bytes;  // staging: (block_n or block_n/2)/32 panels of 8 KB
+  const int out_cols = p.geglu ? p.block_n / 2 : p.block_n;
+  const int npanels = out_cols / kPanelCols;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sC + (p.out_f32 ? 0 : npanels) * kPanelBytes);
   uint64_t* empty_bar = full_bar + p.stages;
-  uint64_t* tmem_full_bar = empty_bar + p.stages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full = empty_bar + p.stages;  // [2]
+  uint64_t* tmem_empty = tmem_full + 2;        // [2]
+  uint64_t* res_full = tmem_empty + 2;         // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int tile_n = blockIdx.x;
-  const int tile_m = blockIdx.y;
   const int total_kb = p.taps * p.kblocks1 + p.kblocks2;
+  const int num_tiles = p.tiles_m * p.tiles_n;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA);
     tma_prefetch_desc(&mapB);
     if (p.kblocks2) tma_prefetch_desc(&mapA2);
+    if (!p.out_f32) tma_prefetch_desc(&mapC);
+    if (p.has_residual) tma_prefetch_desc(&mapR);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], kEpiThreads / 32);
+    }
+    mbar_init(res_full, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -89,37 +119,40 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      int n0 = 0, y0 = 0, x0 = 0;
-      const long long m0 = (long long)tile_m * p.rows_valid;
-      if (p.taps == 9) {
-        const long long hw = (long long)p.H * p.W;
-        n0 = (int)(m0 / hw);
-        const int rem = (int)(m0 % hw);
-        y0 = rem / p.W;
-        x0 = rem % p.W;
-      }
-      const uint32_t tx_bytes = (uint32_t)(p.rows_valid * kBlockK * 2 + b_bytes);
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < total_kb; ++kb) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* sa = smem + stage * stage_bytes;
-        uint8_t* sb = sa + a_bytes;
-        mbar_expect_tx(&full_bar[stage], tx_bytes);
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int tile_n = t % p.tiles_n, tile_m = t / p.tiles_n;
+        int n0 = 0, y0 = 0, x0 = 0;
+        const long long m0 = (long long)tile_m * p.rows_valid;
         if (p.taps == 9) {
-          const int tap = kb / p.kblocks1;
-          const int cb = kb - tap * p.kblocks1;
-          const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-          tma_load_4d(sa, &mapA, &full_bar[stage], cb * kBlockK, x0 + dx, y0 + dy, n0);
-        } else if (kb < p.kblocks1) {
-          tma_load_2d(sa, &mapA, &full_bar[stage], kb * kBlockK, (int)m0);
-        } else {
-          tma_load_2d(sa, &mapA2, &full_bar[stage], (kb - p.kblocks1) * kBlockK, (int)m0);
+          const long long hw = (long long)p.H * p.W;
+          n0 = (int)(m0 / hw);
+          const int rem = (int)(m0 % hw);
+          y0 = rem / p.W;
+          x0 = rem % p.W;
         }
-        tma_load_2d(sb, &mapB, &full_bar[stage], kb * kBlockK, tile_n * p.block_n);
-        if (++stage == p.stages) {
-          stage = 0;
-          phase ^= 1;
+        const uint32_t tx_bytes = (uint32_t)(p.rows_valid * kBlockK * 2 + b_bytes);
+        for (int kb = 0; kb < total_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * stage_bytes;
+          uint8_t* sb = sa + a_bytes;
+          mbar_expect_tx(&full_bar[stage], tx_bytes);
+          if (p.taps == 9) {
+            const int tap = kb / p.kblocks1;
+            const int cb = kb - tap * p.kblocks1;
+            const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+            tma_load_4d(sa, &mapA, &full_bar[stage], cb * kBlockK, x0 + dx, y0 + dy, n0);
+          } else if (kb < p.kblocks1) {
+            tma_load_2d(sa, &mapA, &full_bar[stage], kb * kBlockK, (int)m0);
+          } else {
+            tma_load_2d(sa, &mapA2, &full_bar[stage], (kb - p.kblocks1) * kBlockK, (int)m0);
+          }
+          tma_load_2d(sb, &mapB, &full_bar[stage], kb * kBlockK, tile_n * p.block_n);
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
         }
       }
     }
@@ -129,116 +162,165 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       const uint32_t idesc = make_idesc_bf16(kBlockM, (uint32_t)p.block_n, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < total_kb; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
+      int it = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+        const int as = it & 1;
+        mbar_wait(&tmem_empty[as], (uint32_t)(((it >> 1) & 1) ^ 1));
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + stage * stage_bytes);
-        const uint32_t sb = sa + a_bytes;
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * 256);
+        for (int kb = 0; kb < total_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+          const uint32_t sb = sa + a_bytes;
 #pragma unroll
-        for (int k = 0; k < kBlockK / 16; ++k) {
-          const uint64_t da = make_smem_desc(sa + k * 32, 16, 1024, SWZ_128B);
-          const uint64_t db = make_smem_desc(sb + k * 32, 16, 1024, SWZ_128B);
-          umma_ss(tmem_base, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            const uint64_t da = make_smem_desc(sa + k * 32, 16, 1024, SWZ_128B);
+            const uint64_t db = make_smem_desc(sb + k * 32, 16, 1024, SWZ_128B);
+            umma_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
         }
-        umma_commit(&empty_bar[stage]);
-        if (++stage == p.stages) {
-          stage = 0;
-          phase ^= 1;
-        }
+        umma_commit(&tmem_full[as]);
       }
-      umma_commit(tmem_full_bar);
     }
   } else {
-    // ------------------------------------------------------------ epilogue (warps 2..5)
-    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    // ------------------------------------------------------------ epilogue (warps 2..9)
+    const int ew = warp - 2;
+    const int q = warp & 3;    // TMEM lane quadrant this warp may access
+    const int half = ew >> 2;  // which half of the output chunks this warp drains
     const int row = q * 32 + lane;
-    const long long m = (long long)tile_m * p.rows_valid + row;
-    const bool row_ok = row < p.rows_valid && m < p.M;
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    const int nbase = tile_n * p.block_n;
-    const float* b2 = p.bias2 ? p.bias2 + (row_ok ? (m / p.bias2_div) : 0) * (long long)p.N : nullptr;
-    for (int c = 0; c < p.block_n; c += 16) {
-      uint32_t v[16];
-      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
-      tmem_ld_wait();
-      const int n = nbase + c;
-      if (row_ok && n < p.N) {
+    const bool leader = threadIdx.x == 64;
+    const int nchunks = out_cols / 16;
+    const int c_begin = half ? (nchunks + 1) / 2 : 0;
+    const int c_end = half ? nchunks : (nchunks + 1) / 2;
+    const uint32_t res_bytes = (uint32_t)(p.rows_valid * out_cols * 2);
+    if (leader && p.has_residual && (int)blockIdx.x < num_tiles) {
+      const int tile_n = blockIdx.x % p.tiles_n, tile_m = blockIdx.x / p.tiles_n;
+      mbar_expect_tx(res_full, res_bytes);
+      for (int pn = 0; pn < npanels; ++pn)
+        tma_load_2d(sC + pn * kPanelBytes, &mapR, res_full, tile_n * out_cols + pn * kPanelCols, tile_m * p.rows_valid);
+    }
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int tile_n = t % p.tiles_n, tile_m = t / p.tiles_n;
+      const int as = it & 1;
+      const long long m = (long long)tile_m * p.rows_valid + row;
+      const bool row_ok = row < p.rows_valid && m < p.M;
+      mbar_wait(&tmem_full[as], (uint32_t)((it >> 1) & 1));
+      tc_fence_after();
+      if (p.has_residual) mbar_wait(res_full, (uint32_t)(it & 1));
+      const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256);
+      const int nbase = tile_n * p.block_n;  // accumulator column base (bias index)
+      const float* b2 = p.bias2 ? p.bias2 + (row_ok ? (m / p.bias2_div) : 0) * (long long)p.N : nullptr;
+      for (int c = c_begin; c < c_end; ++c) {
+        uint32_t v[16];
         float f[16];
+        tmem_ld16(tacc + (uint32_t)(c * 16), v);
+        if (p.geglu) {
+          uint32_t g[16];
+          tmem_ld16(tacc + (uint32_t)(out_cols + c * 16), g);
+          tmem_ld_wait();
+          const int nv = nbase + c * 16, ng = nbase + out_cols + c * 16;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
-        if (p.bias) {
-#pragma unroll
-          for (int i = 0; i < 16; i += 4) {
-            const float4 bv = *reinterpret_cast<const float4*>(p.bias + n + i);
-            f[i] += bv.x; f[i + 1] += bv.y; f[i + 2] += bv.z; f[i + 3] += bv.w;
+          for (int i = 0; i < 16; ++i) {
+            const float val = __uint_as_float(v[i]) + (p.bias ? p.bias[nv + i] : 0.f);
+            const float gate = __uint_as_float(g[i]) + (p.bias ? p.bias[ng + i] : 0.f);
+            f[i] = val * gelu_erf(gate);
           }
-        }
-        if (b2) {
+        } else {
+          tmem_ld_wait();
+          const int n = nbase + c * 16;
 #pragma unroll
-          for (int i = 0; i < 16; i += 4) {
-            const float4 bv = *reinterpret_cast<const float4*>(b2 + n + i);
-            f[i] += bv.x; f[i + 1] += bv.y; f[i + 2] += bv.z; f[i + 3] += bv.w;
-          }
-        }
-        if (p.scale != 1.0f) {
+          for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+          if (n < p.N) {
+            if (p.bias) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) f[i] *= p.scale;
-        }
-        if (p.residual) {
-          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + m * p.ldr + n);
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const uint4 r = rp[h];
-            const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float2 t = unpack_bf16(rr[i]);
-              f[h * 8 + 2 * i] += t.x;
-              f[h * 8 + 2 * i + 1] += t.y;
+              for (int i = 0; i < 16; i += 4) {
+                const float4 bv = *reinterpret_cast<const float4*>(p.bias + n + i);
+                f[i] += bv.x; f[i + 1] += bv.y; f[i + 2] += bv.z; f[i + 3] += bv.w;
+              }
             }
+            if (b2) {
+#pragma unroll
+              for (int i = 0; i < 16; i += 4) {
+                const float4 bv = *reinterpret_cast<const float4*>(b2 + n + i);
+                f[i] += bv.x; f[i + 1] += bv.y; f[i + 2] += bv.z; f[i + 3] += bv.w;
+              }
+            }
+          }
+          if (p.scale != 1.0f) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] *= p.scale;
           }
         }
         if (p.out_f32) {
-          float4* fp = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + m * p.ldc + n);
+          const int n = nbase + c * 16;
+          if (row_ok && n < p.N) {
+            float4* fp = reinterpret_cast<float4*>(p.out32 + m * p.ldc + n);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) fp[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+            for (int i = 0; i < 4; ++i) fp[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+          }
           continue;
         }
-        uint4* op = reinterpret_cast<uint4*>(p.out + m * p.ldc + n);
-        op[0] = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
-        op[1] = make_uint4(pack_bf16(f[8], f[9]), pack_bf16(f[10], f[11]), pack_bf16(f[12], f[13]),
-                           pack_bf16(f[14], f[15]));
+        // staging tile: panel (c/2), 16-byte chunks (c&1)*2 + {0,1} of the 64-byte row, 64B swizzle:
+        // byte offset o = row*64 + chunk*16 is stored at o ^ (((o >> 7) & 3) << 4)
+        uint8_t* panel = sC + (c >> 1) * kPanelBytes;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t o = (uint32_t)(row * 64 + ((c & 1) * 2 + h) * 16);
+          o ^= ((o >> 7) & 3u) << 4;
+          uint4* sp = reinterpret_cast<uint4*>(panel + o);
+          if (p.has_residual) {
+            const uint4 r = *sp;
+            const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 tt = unpack_bf16(rr[i]);
+              f[h * 8 + 2 * i] += tt.x;
+              f[h * 8 + 2 * i + 1] += tt.y;
+            }
+          }
+          *sp = make_uint4(pack_bf16(f[h * 8], f[h * 8 + 1]), pack_bf16(f[h * 8 + 2], f[h * 8 + 3]),
+                           pack_bf16(f[h * 8 + 4], f[h * 8 + 5]), pack_bf16(f[h * 8 + 6], f[h * 8 + 7]));
+        }
+      }
+      // accumulator stage drained: hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[as]);
+      if (!p.out_f32) {
+        fence_proxy_async_smem();
+        epi_bar_sync();
+        if (leader) {
+          for (int pn = 0; pn < npanels; ++pn)
+            tma_store_2d(&mapC, sC + pn * kPanelBytes, tile_n * out_cols + pn * kPanelCols, tile_m * p.rows_valid);
+          tma_store_commit();
+          tma_store_wait_read();  // staging tile may be overwritten again
+          const int tn = t + gridDim.x;
+          if (p.has_residual && tn < num_tiles) {
+            const int ntile_n = tn % p.tiles_n, ntile_m = tn / p.tiles_n;
+            mbar_expect_tx(res_full, res_bytes);
+            for (int pn = 0; pn < npanels; ++pn)
+              tma_load_2d(sC + pn * kPanelBytes, &mapR, res_full, ntile_n * out_cols + pn * kPanelCols,
+                          ntile_m * p.rows_valid);
+          }
+        }
+        epi_bar_sync();
       }
     }
+    if (leader && !p.out_f32) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    tmem_dealloc(tmem_base, 512);
   }
-}
-
-static int pow2_cols(int n) {
-  int c = 32;
-  while (c < n) c <<= 1;
-  return c;
-}
-
-static int pick_block_n(int M, int N, int rows_per_tile) {
-  static const int cand[] = {256, 240, 224, 208, 192, 176, 160, 144, 128, 112, 96, 80, 64, 48, 32, 16};
-  const long long tiles_m = (M + rows_per_tile - 1) / rows_per_tile;
-  int best = 0;
-  for (int bn : cand) {
-    if (N % bn) continue;
-    if (!best) best = bn;                      // largest divisor
-    if (tiles_m * (N / bn) >= 148 && bn >= 128) return bn;  // largest divisor that still fills the chip
-  }
-  // small problem: prefer >=128-wide tiles when they exist, else the largest divisor
-  for (int bn : cand)
-    if (N % bn == 0 && bn <= 160 && bn >= 64) return bn;
-  return best;
 }
 
 static int env_int(const char* name, int dflt) {
@@ -246,24 +328,73 @@ static int env_int(const char* name, int dflt) {
   return s ? atoi(s) : dflt;
 }
 
-static int launch(const CUtensorMap& mA, const CUtensorMap& mA2, const CUtensorMap& mB, GemmArgs& a, cudaStream_t st) {
-  const int stage_bytes = kBlockM * kBlockK * 2 + a.block_n * kBlockK * 2;
-  int stages = env_int("VX_GEMM_STAGES", 0);
-  if (stages <= 0) stages = (a.block_n > 128) ? 4 : 6;
-  const int total_kb = a.taps * a.kblocks1 + a.kblocks2;
-  if (stages > total_kb) stages = total_kb < 2 ? 2 : total_kb;
-  while (stages * stage_bytes + 2048 > 227 * 1024) --stages;
-  a.stages = stages;
-  a.tmem_cols = pow2_cols(a.block_n);
-  const size_t smem = (size_t)stages * stage_bytes + 2048;
-  static size_t configured = 0;
-  if (smem > configured) {
-    VX_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = 227 * 1024;
+static int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
   }
-  dim3 grid((a.N + a.block_n - 1) / a.block_n, (a.M + a.rows_valid - 1) / a.rows_valid);
-  gemm_tcgen05_kernel<<<grid, kThreads, smem, st>>>(mA, mA2, mB, a);
+  return n;
+}
+
+// Pick the UMMA N: among the multiples of `gran` that divide N, minimise
+//   waves(tiles) x cycles per k-block, with cycles = max(MMA issue 2*bn, smem feed 128 + bn).
+static int pick_block_n(long long tiles_m, int N, int gran) {
+  const int sms = num_sms();
+  int best = 0;
+  double best_cost = 1e30;
+  for (int bn = 256; bn >= gran; bn -= gran) {
+    if (N % bn) continue;
+    const long long tiles = tiles_m * (N / bn);
+    const double waves = (double)((tiles + sms - 1) / sms);
+    const double cyc = (2.0 * bn > 128.0 + bn) ? 2.0 * bn : 128.0 + bn;
+    const double cost = waves * (cyc + 40.0);  // + per-k-block issue overhead
+    if (cost < best_cost * 0.999) {
+      best_cost = cost;
+      best = bn;
+    }
+  }
+  return best;
+}
+
+static int launch(const CUtensorMap& mA, const CUtensorMap& mA2, const CUtensorMap& mB, const CUtensorMap& mR,
+                  const CUtensorMap& mC, GemmArgs& a, cudaStream_t st) {
+  const int stage_bytes = kBlockM * kBlockK * 2 + a.block_n * kBlockK * 2;
+  const int out_cols = a.geglu ? a.block_n / 2 : a.block_n;
+  const int stage_c = a.out_f32 ? 0 : out_cols / kPanelCols * kPanelBytes;
+  int stages = env_int("VX_GEMM_STAGES", 0);
+  if (stages <= 0) stages = 6;
+  while (stages > 2 && (size_t)stages * stage_bytes + stage_c + 2048 > 227 * 1024) --stages;
+  a.stages = stages;
+  const size_t smem = (size_t)stages * stage_bytes + stage_c + 2048;
+  static bool configured = false;
+  if (!configured) {
+    VX_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
+  const int tiles = a.tiles_m * a.tiles_n;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  gemm_tcgen05_kernel<<<grid, kThreads, smem, st>>>(mA, mA2, mB, mR, mC, a);
   VX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int make_out_maps(CUtensorMap* mR, CUtensorMap* mC, const void* residual, long long ldr, void* out,
+                         long long ldc, long long M, int out_N, int rows_valid) {
+  uint64_t dims[2] = {(uint64_t)out_N, (uint64_t)M};
+  uint32_t box[2] = {kPanelCols, (uint32_t)rows_valid};
+  {
+    uint64_t str[1] = {(uint64_t)ldc * 2};
+    if (make_tmap_bf16(mC, out, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
+  }
+  if (residual) {
+    uint64_t str[1] = {(uint64_t)ldr * 2};
+    if (make_tmap_bf16(mR, residual, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
+  } else {
+    *mR = *mC;
+  }
   return 0;
 }
 
@@ -271,20 +402,28 @@ static int launch(const CUtensorMap& mA, const CUtensorMap& mA2, const CUtensorM
 
 using namespace vx;
 
+// epilogue: 0 = linear (bias, bias2, scale, residual); 1 = GEGLU (W / bias packed per tile as value|gate halves,
+// see vx_geglu_pack_rows; out has N/2 columns)
 extern "C" int vx_gemm_bf16(const void* A, long long lda, int K1, const void* A2, long long lda2, int K2,
                             const void* Wt, long long ldw, int M, int N, const float* bias, const float* bias2,
                             int bias2_div, float scale, const void* residual, long long ldr, void* out,
                             long long ldc, int out_f32, int block_n, void* stream) {
+  const int geglu = out_f32 == 2 ? 1 : 0;  // out_f32: 0 bf16, 1 fp32, 2 bf16 + GEGLU epilogue
+  if (geglu) out_f32 = 0;
   VX_REQUIRE(M > 0 && N > 0 && K1 > 0, "vx_gemm_bf16: bad shape M=%d N=%d K1=%d", M, N, K1);
-  VX_REQUIRE(N % 16 == 0, "vx_gemm_bf16: N=%d must be a multiple of 16", N);
+  const int gran = geglu ? 64 : (out_f32 ? 16 : 32);
+  VX_REQUIRE(N % gran == 0, "vx_gemm_bf16: N=%d must be a multiple of %d", N, gran);
   VX_REQUIRE(K1 % 8 == 0 && K2 % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && ldc % 8 == 0,
              "vx_gemm_bf16: K/ld must be multiples of 8 elements (16-byte TMA strides)");
   VX_REQUIRE(K2 == 0 || (K1 % kBlockK == 0 && lda2 % 8 == 0), "vx_gemm_bf16: split-K needs K1 %% 64 == 0");
-  VX_REQUIRE(!residual || ldr % 8 == 0, "vx_gemm_bf16: ldr must be a multiple of 8");
+  VX_REQUIRE(!residual || (ldr % 8 == 0 && !out_f32 && !geglu), "vx_gemm_bf16: residual needs bf16 linear epilogue, ldr %%8");
+  VX_REQUIRE(!geglu || (!bias2 && scale == 1.0f), "vx_gemm_bf16: GEGLU epilogue takes only the packed bias");
+  const int tiles_m = (M + kBlockM - 1) / kBlockM;
   if (block_n <= 0) block_n = env_int("VX_GEMM_BN", 0);
-  if (block_n <= 0) block_n = pick_block_n(M, N, kBlockM);
-  VX_REQUIRE(block_n % 16 == 0 && block_n >= 16 && block_n <= 256, "vx_gemm_bf16: block_n=%d invalid", block_n);
-  CUtensorMap mA, mA2, mB;
+  if (block_n <= 0) block_n = pick_block_n(tiles_m, N, gran);
+  VX_REQUIRE(block_n >= gran && block_n % gran == 0 && block_n <= 256 && N % block_n == 0,
+             "vx_gemm_bf16: block_n=%d invalid for N=%d", block_n, N);
+  CUtensorMap mA, mA2, mB, mR, mC;
   {
     uint64_t dims[2] = {(uint64_t)K1, (uint64_t)M};
     uint64_t str[1] = {(uint64_t)lda * 2};
@@ -305,6 +444,12 @@ extern "C" int vx_gemm_bf16(const void* A, long long lda, int K1, const void* A2
     uint32_t box[2] = {kBlockK, (uint32_t)block_n};
     if (make_tmap_bf16(&mB, Wt, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
   }
+  if (!out_f32) {
+    if (make_out_maps(&mR, &mC, residual, ldr, out, ldc, M, geglu ? N / 2 : N, kBlockM)) return 1;
+  } else {
+    mR = mA;
+    mC = mA;
+  }
   GemmArgs a{};
   a.M = M; a.N = N;
   a.kblocks1 = (K1 + kBlockK - 1) / kBlockK;
@@ -313,10 +458,14 @@ extern "C" int vx_gemm_bf16(const void* A, long long lda, int K1, const void* A2
   a.block_n = block_n;
   a.rows_valid = kBlockM;
   a.W = a.H = 1;
+  a.tiles_m = tiles_m;
+  a.tiles_n = N / block_n;
+  a.geglu = geglu;
+  a.has_residual = residual ? 1 : 0;
+  a.out_f32 = out_f32;
   a.bias = bias; a.bias2 = bias2; a.bias2_div = bias2_div > 0 ? bias2_div : 1; a.scale = scale;
-  a.residual = (const __nv_bfloat16*)residual; a.ldr = ldr;
-  a.out = (__nv_bfloat16*)out; a.ldc = ldc; a.out_f32 = out_f32;
-  return launch(mA, mA2, mB, a, (cudaStream_t)stream);
+  a.out32 = (float*)out; a.ldc = ldc;
+  return launch(mA, mA2, mB, mR, mC, a, (cudaStream_t)stream);
 }
 
 // X: NHWC bf16 [NB, H, W, C];  Wt: [Cout, 9*C] with K index = (ky*3+kx)*C + c;  out: [NB*H*W, ldc]
@@ -324,7 +473,8 @@ extern "C" int vx_conv3x3_bf16(const void* X, int NB, int H, int W, int C, const
                                const float* bias, const float* bias2, int bias2_div, float scale,
                                const void* residual, long long ldr, void* out, long long ldc, int block_n,
                                void* stream) {
-  VX_REQUIRE(C % 8 == 0 && Cout % 16 == 0, "vx_conv3x3_bf16: C=%d must be %%8, Cout=%d %%16", C, Cout);
+  VX_REQUIRE(C % kBlockK == 0 && Cout % 32 == 0, "vx_conv3x3_bf16: C=%d must be %%64, Cout=%d %%32", C, Cout);
+  VX_REQUIRE(ldc % 8 == 0 && (!residual || ldr % 8 == 0), "vx_conv3x3_bf16: ld must be %%8");
   // pixel rectangle of <= 128 output rows that is contiguous in NHWC row order
   int wbox, hbox = 1, nbox = 1;
   if (W >= kBlockM) {
@@ -338,6 +488,7 @@ extern "C" int vx_conv3x3_bf16(const void* X, int NB, int H, int W, int C, const
       nbox = kBlockM / (W * H);
       if (nbox > NB) nbox = NB;
       if (nbox < 1) nbox = 1;
+      while (NB % nbox) --nbox;
     } else {
       while (H % hbox) --hbox;
     }
@@ -345,10 +496,12 @@ extern "C" int vx_conv3x3_bf16(const void* X, int NB, int H, int W, int C, const
   const int rows_valid = wbox * hbox * nbox;
   const long long M = (long long)NB * H * W;
   VX_REQUIRE(M % rows_valid == 0, "vx_conv3x3_bf16: NB*H*W=%lld not tileable by %d", M, rows_valid);
+  const long long tiles_m = M / rows_valid;
   if (block_n <= 0) block_n = env_int("VX_GEMM_BN", 0);
-  if (block_n <= 0) block_n = pick_block_n((int)M, Cout, rows_valid);
-  VX_REQUIRE(block_n % 16 == 0 && block_n >= 16 && block_n <= 256, "vx_conv3x3_bf16: block_n=%d invalid", block_n);
-  CUtensorMap mA, mB;
+  if (block_n <= 0) block_n = pick_block_n(tiles_m, Cout, 32);
+  VX_REQUIRE(block_n % 32 == 0 && block_n >= 32 && block_n <= 256 && Cout % block_n == 0,
+             "vx_conv3x3_bf16: block_n=%d invalid for Cout=%d", block_n, Cout);
+  CUtensorMap mA, mB, mR, mC;
   {
     uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)NB};
     uint64_t str[3] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
@@ -361,7 +514,7 @@ extern "C" int vx_conv3x3_bf16(const void* X, int NB, int H, int W, int C, const
     uint32_t box[2] = {kBlockK, (uint32_t)block_n};
     if (make_tmap_bf16(&mB, Wt, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
   }
-  VX_REQUIRE(C % kBlockK == 0, "vx_conv3x3_bf16: C=%d must be a multiple of 64", C);
+  if (make_out_maps(&mR, &mC, residual, ldr, out, ldc, M, Cout, rows_valid)) return 1;
   GemmArgs a{};
   a.M = (int)M; a.N = Cout;
   a.kblocks1 = C / kBlockK;
@@ -370,8 +523,12 @@ extern "C" int vx_conv3x3_bf16(const void* X, int NB, int H, int W, int C, const
   a.block_n = block_n;
   a.rows_valid = rows_valid;
   a.W = W; a.H = H;
+  a.tiles_m = (int)tiles_m;
+  a.tiles_n = Cout / block_n;
+  a.geglu = 0;
+  a.has_residual = residual ? 1 : 0;
+  a.out_f32 = 0;
   a.bias = bias; a.bias2 = bias2; a.bias2_div = bias2_div > 0 ? bias2_div : 1; a.scale = scale;
-  a.residual = (const __nv_bfloat16*)residual; a.ldr = ldr;
-  a.out = (__nv_bfloat16*)out; a.ldc = ldc;
-  return launch(mA, mA, mB, a, (cudaStream_t)stream);
+  a.out32 = (float*)out; a.ldc = ldc;
+  return launch(mA, mA, mB, mR, mC, a, (cudaStream_t)stream);
 }

@@ -407,6 +407,9 @@ class UNetEngine:
                 W[p + ".kv"] = torch.cat([W[p + ".to_k.weight"], W[p + ".to_v.weight"]], 0).contiguous()
             elif k.endswith("pos_encoder.pe"):
                 W[k] = sd[k].to(device=self.dev, dtype=BF16).float()[0].contiguous()          # [max_len, C]
+            elif k.endswith("ff.net.0.proj.weight"):
+                p = k[:-len(".weight")]
+                W[p + ".geglu_w"], W[p + ".geglu_b"], _ = ops.pack_geglu(W[k], W[p + ".bias"])
 
     # ---------------------------------------------------------------- banks
     def _bank_kv(self, name: str, block: TemporalBasicTransformerBlock):
@@ -442,7 +445,7 @@ class UNetEngine:
 
     def _ff(self, p, n, res):
         W = self.W
-        g = ops.geglu(ops.gemm(n, W[p + ".net.0.proj.weight"], W[p + ".net.0.proj.bias"]))
+        g = ops.gemm(n, W[p + ".net.0.proj.geglu_w"], W[p + ".net.0.proj.geglu_b"], geglu=True)   # GEGLU in the epilogue
         return ops.gemm(g, W[p + ".net.2.weight"], W[p + ".net.2.bias"], residual=res)
 
     def _spatial(self, p, x, NB, HW, f, enc_flat):

@@ -19,21 +19,45 @@ def _chk_bf16(*ts):
             assert t.is_cuda and t.dtype == BF16 and t.stride(-1) == 1, (t.dtype, t.device, t.stride())
 
 
+def geglu_block_n(N):
+    """UMMA N used for a GEGLU-fused GEMM with N = 2*inner accumulator columns (fixed at weight-packing time)."""
+    for bn in (256, 128, 64):
+        if N % bn == 0:
+            return bn
+    raise ValueError(f"GEGLU GEMM needs N % 64 == 0, got {N}")
+
+
+def pack_geglu(w, bias):
+    """Reorder the rows of FeedForward.net.0.proj ([2*inner, K]: value rows then gate rows) so that every
+    block_n-wide output tile holds block_n/2 value columns followed by the matching block_n/2 gate columns."""
+    N = w.shape[0]
+    bn = geglu_block_n(N)
+    inner, hb = N // 2, bn // 2
+    idx = torch.arange(N, device=w.device).view(N // bn, 2, hb)
+    t = torch.arange(N // bn, device=w.device).view(-1, 1)
+    j = torch.arange(hb, device=w.device).view(1, -1)
+    idx = torch.stack([t * hb + j, inner + t * hb + j], 1).reshape(-1)
+    return w[idx].contiguous(), (None if bias is None else bias[idx].contiguous()), bn
+
+
 def gemm(a, w, bias=None, *, a2=None, bias2=None, bias2_div=1, scale=1.0, residual=None, out=None, block_n=0,
-         out_f32=False):
-    """out = (concat(a, a2) @ w.T + bias + bias2[row // bias2_div]) * scale + residual  (bf16, or fp32 if out_f32)."""
+         out_f32=False, geglu=False):
+    """out = (concat(a, a2) @ w.T + bias + bias2[row // bias2_div]) * scale + residual  (bf16, or fp32 if out_f32).
+    geglu=True: w/bias packed by pack_geglu; out[:, j] = (v_j + b) * gelu(g_j + b) with N/2 columns."""
     _chk_bf16(a, w, a2, residual, None if out_f32 else out)
     M, K1 = a.shape
     K2 = 0 if a2 is None else a2.shape[1]
     N = w.shape[0]
     assert w.shape[1] == K1 + K2
+    if geglu:
+        block_n = geglu_block_n(N)
     if out is None:
-        out = torch.empty((M, N), device=a.device, dtype=torch.float32 if out_f32 else BF16)
+        out = torch.empty((M, N // 2 if geglu else N), device=a.device, dtype=torch.float32 if out_f32 else BF16)
     check(_ffi.lib().vx_gemm_bf16(
         ptr(a), c_ll(a.stride(0)), c_int(K1), ptr(a2), c_ll(0 if a2 is None else a2.stride(0)), c_int(K2),
         ptr(w), c_ll(w.stride(0)), c_int(M), c_int(N), ptr(bias), ptr(bias2), c_int(bias2_div), c_float(scale),
         ptr(residual), c_ll(0 if residual is None else residual.stride(0)), ptr(out), c_ll(out.stride(0)),
-        c_int(int(out_f32)), c_int(block_n), stream_ptr()), "vx_gemm_bf16")
+        c_int(2 if geglu else int(out_f32)), c_int(block_n), stream_ptr()), "vx_gemm_bf16")
     return out
 
 
