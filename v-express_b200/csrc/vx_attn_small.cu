@@ -11,7 +11,10 @@
 
 namespace vx {
 
-// one warp per (b, pixel, head); 4 warps per CTA = 4 consecutive heads of one pixel (contiguous channels)
+// One warp per (b, pixel); lane = (head slot, query frame): G = 32 / fpad heads are processed per pass
+// (fpad = 16 for f <= 16, else 32).  K/V of the pass are staged in shared memory (bf16) and read as warp
+// broadcasts; each thread keeps its q row packed in registers, does the f scores, an in-thread softmax and the
+// P.V product -- no shuffles, fp32 math, FMA-bound.
 struct TemporalArgs {
   const __nv_bfloat16* q; const __nv_bfloat16* k; const __nv_bfloat16* v; long long ld;  // rows = (b f hw)
   __nv_bfloat16* out; long long ldo;
@@ -19,77 +22,96 @@ struct TemporalArgs {
   float scale;
 };
 
+template <int HD>
 __global__ void __launch_bounds__(128) temporal_attn_kernel(const TemporalArgs p) {
   extern __shared__ uint8_t sm_raw[];
+  constexpr int VEC = HD / 8;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int hdp = p.hd + 8;  // padded row (bank spread)
-  const size_t per_warp = (size_t)3 * p.f * hdp * sizeof(__nv_bfloat16) + (size_t)p.f * p.f * sizeof(float);
-  uint8_t* base = sm_raw + warp * ((per_warp + 15) & ~size_t(15));
-  __nv_bfloat16* sq = reinterpret_cast<__nv_bfloat16*>(base);
-  __nv_bfloat16* sk = sq + p.f * hdp;
-  __nv_bfloat16* sv = sk + p.f * hdp;
-  float* ss = reinterpret_cast<float*>(sv + p.f * hdp);
-
-  const long long item = (long long)blockIdx.x * 4 + warp;  // (b, pixel, head), head fastest
-  const long long nitems = (long long)p.b * p.HW * p.heads;
-  if (item >= nitems) return;
-  const int head = (int)(item % p.heads);
-  const long long bp = item / p.heads;
-  const int px = (int)(bp % p.HW);
-  const int bb = (int)(bp / p.HW);
-  const int vec = p.hd / 8;
+  const int fpad = p.f <= 16 ? 16 : 32;
+  const int G = 32 / fpad;                               // heads per pass
+  const size_t per_warp = (size_t)2 * G * p.f * HD * sizeof(__nv_bfloat16);
+  __nv_bfloat16* sk = reinterpret_cast<__nv_bfloat16*>(sm_raw + warp * per_warp);
+  __nv_bfloat16* sv = sk + G * p.f * HD;
+  const long long item = (long long)blockIdx.x * 4 + warp;   // (b, pixel)
+  if (item >= (long long)p.b * p.HW) return;
+  const int px = (int)(item % p.HW);
+  const int bb = (int)(item / p.HW);
   const long long row0 = (long long)bb * p.f * p.HW + px;
-  for (int idx = lane; idx < p.f * vec; idx += 32) {
-    const int fr = idx / vec, c = (idx % vec) * 8;
-    const long long off = (row0 + (long long)fr * p.HW) * p.ld + head * p.hd + c;
-    *reinterpret_cast<uint4*>(sq + fr * hdp + c) = *reinterpret_cast<const uint4*>(p.q + off);
-    *reinterpret_cast<uint4*>(sk + fr * hdp + c) = *reinterpret_cast<const uint4*>(p.k + off);
-    *reinterpret_cast<uint4*>(sv + fr * hdp + c) = *reinterpret_cast<const uint4*>(p.v + off);
-  }
-  __syncwarp();
-  for (int idx = lane; idx < p.f * p.f; idx += 32) {
-    const int i = idx / p.f, j = idx % p.f;
-    float acc = 0.f;
-    for (int c = 0; c < p.hd; c += 2) {
-      const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(sq + i * hdp + c));
-      const float2 bk = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(sk + j * hdp + c));
-      acc += a.x * bk.x + a.y * bk.y;
+  const int hs = lane / fpad, qi = lane % fpad;          // head slot, query frame of this thread
+  const bool active = qi < p.f;
+  for (int h0 = 0; h0 < p.heads; h0 += G) {
+    __syncwarp();
+    // stage K, V of heads [h0, h0+G): [G][f][HD]
+    for (int idx = lane; idx < G * p.f * VEC; idx += 32) {
+      const int c = (idx % VEC) * 8;
+      const int fr = (idx / VEC) % p.f;
+      const int g = idx / (VEC * p.f);
+      const long long off = (row0 + (long long)fr * p.HW) * p.ld + (h0 + g) * HD + c;
+      *reinterpret_cast<uint4*>(sk + (g * p.f + fr) * HD + c) = *reinterpret_cast<const uint4*>(p.k + off);
+      *reinterpret_cast<uint4*>(sv + (g * p.f + fr) * HD + c) = *reinterpret_cast<const uint4*>(p.v + off);
     }
-    ss[idx] = acc * p.scale;
-  }
-  __syncwarp();
-  if (lane < p.f) {
+    uint4 qreg[VEC];
+    const int head = h0 + hs;
+    const long long qoff = (row0 + (long long)(active ? qi : 0) * p.HW) * p.ld + head * HD;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) qreg[i] = *reinterpret_cast<const uint4*>(p.q + qoff + i * 8);
+    __syncwarp();
+    float s[32];
     float mx = -INFINITY;
-    for (int j = 0; j < p.f; ++j) mx = fmaxf(mx, ss[lane * p.f + j]);
-    float sum = 0.f;
-    for (int j = 0; j < p.f; ++j) {
-      const float e = __expf(ss[lane * p.f + j] - mx);
-      ss[lane * p.f + j] = e;
-      sum += e;
+    const __nv_bfloat16* kh = sk + hs * p.f * HD;
+    const __nv_bfloat16* vh = sv + hs * p.f * HD;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (j >= p.f) break;
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        const uint4 kk = *reinterpret_cast<const uint4*>(kh + j * HD + i * 8);
+        const uint32_t a[4] = {qreg[i].x, qreg[i].y, qreg[i].z, qreg[i].w};
+        const uint32_t bq[4] = {kk.x, kk.y, kk.z, kk.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float2 x = unpack_bf16(a[t]), y = unpack_bf16(bq[t]);
+          acc = fmaf(x.x, y.x, acc);
+          acc = fmaf(x.y, y.y, acc);
+        }
+      }
+      acc *= p.scale;
+      s[j] = acc;
+      mx = fmaxf(mx, acc);
     }
-    const float inv = 1.f / sum;
-    for (int j = 0; j < p.f; ++j) ss[lane * p.f + j] *= inv;
-  }
-  __syncwarp();
-  for (int idx = lane; idx < p.f * vec; idx += 32) {
-    const int i = idx / vec, c = (idx % vec) * 8;
-    float o[8];
+    float sum = 0.f;
 #pragma unroll
-    for (int t = 0; t < 8; ++t) o[t] = 0.f;
-    for (int j = 0; j < p.f; ++j) {
-      const float w = ss[i * p.f + j];
-      const uint4 u = *reinterpret_cast<const uint4*>(sv + j * hdp + c);
-      const uint32_t ww[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const float2 x = unpack_bf16(ww[t]);
-        o[2 * t] += w * x.x;
-        o[2 * t + 1] += w * x.y;
+    for (int j = 0; j < 32; ++j) {
+      if (j < p.f) {
+        s[j] = __expf(s[j] - mx);
+        sum += s[j];
       }
     }
-    const long long off = (row0 + (long long)i * p.HW) * p.ldo + head * p.hd + c;
-    *reinterpret_cast<uint4*>(p.out + off) =
-        make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+    const float inv = 1.f / sum;
+    __nv_bfloat16* op = p.out + (row0 + (long long)qi * p.HW) * p.ldo + head * HD;
+#pragma unroll 1
+    for (int i = 0; i < VEC; ++i) {
+      float o[8];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) o[t] = 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (j < p.f) {
+          const uint4 vv = *reinterpret_cast<const uint4*>(vh + j * HD + i * 8);
+          const uint32_t w4[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const float2 x = unpack_bf16(w4[t]);
+            o[2 * t] = fmaf(s[j], x.x, o[2 * t]);
+            o[2 * t + 1] = fmaf(s[j], x.y, o[2 * t + 1]);
+          }
+        }
+      }
+      if (active)
+        *reinterpret_cast<uint4*>(op + i * 8) = make_uint4(pack_bf16(o[0] * inv, o[1] * inv), pack_bf16(o[2] * inv, o[3] * inv),
+                                                           pack_bf16(o[4] * inv, o[5] * inv), pack_bf16(o[6] * inv, o[7] * inv));
+    }
   }
 }
 
@@ -173,19 +195,36 @@ using namespace vx;
 // q/k/v: [(b f hw), ld] slices (same ld); out [(b f hw), ldo]; attention over f for each (b, pixel, head)
 extern "C" int vx_temporal_attention(const void* q, const void* k, const void* v, long long ld, void* out,
                                      long long ldo, int b, int f, int HW, int heads, int hd, void* stream) {
-  VX_REQUIRE(hd % 8 == 0 && f >= 1 && f <= 32 && ld % 8 == 0 && ldo % 8 == 0, "vx_temporal_attention: bad hd=%d f=%d", hd, f);
+  VX_REQUIRE(f >= 1 && f <= 32 && ld % 8 == 0 && ldo % 8 == 0, "vx_temporal_attention: bad f=%d", f);
   TemporalArgs a{(const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, ld, (__nv_bfloat16*)out,
                  ldo, b, f, HW, heads, hd, 1.0f / sqrtf((float)hd)};
-  const size_t per_warp = (((size_t)3 * f * (hd + 8) * 2 + (size_t)f * f * 4) + 15) & ~size_t(15);
-  const size_t smem = per_warp * 4;
+  const int G = f <= 16 ? 2 : 1;
+  VX_REQUIRE(heads % G == 0, "vx_temporal_attention: heads=%d must be even", heads);
+  const size_t smem = (size_t)4 * 2 * G * f * hd * 2;
   VX_REQUIRE(smem <= 200 * 1024, "vx_temporal_attention: smem %zu", smem);
-  static bool cfg = false;
-  if (!cfg) {
-    VX_CHECK_CUDA(cudaFuncSetAttribute(temporal_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    cfg = true;
+  const long long items = (long long)b * HW;
+  const unsigned grid = (unsigned)((items + 3) / 4);
+  auto st = (cudaStream_t)stream;
+#define TA_LAUNCH(HD)                                                                                               \
+  do {                                                                                                              \
+    static bool cfg = false;                                                                                        \
+    if (!cfg) {                                                                                                     \
+      VX_CHECK_CUDA(cudaFuncSetAttribute(temporal_attn_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                         200 * 1024));                                                              \
+      cfg = true;                                                                                                   \
+    }                                                                                                               \
+    temporal_attn_kernel<HD><<<grid, 128, smem, st>>>(a);                                                           \
+  } while (0)
+  switch (hd) {
+    case 8: TA_LAUNCH(8); break;
+    case 16: TA_LAUNCH(16); break;
+    case 32: TA_LAUNCH(32); break;
+    case 40: TA_LAUNCH(40); break;
+    case 80: TA_LAUNCH(80); break;
+    case 160: TA_LAUNCH(160); break;
+    default: return fail("vx_temporal_attention: head dim %d not instantiated (8,16,32,40,80,160)", hd);
   }
-  const long long items = (long long)b * HW * heads;
-  temporal_attn_kernel<<<(unsigned)((items + 3) / 4), 128, smem, (cudaStream_t)stream>>>(a);
+#undef TA_LAUNCH
   VX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

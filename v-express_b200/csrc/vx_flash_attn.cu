@@ -243,6 +243,235 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// v2: 256 query rows per CTA as two 128-row tiles, each owned by its own softmax warpgroup (ping-pong): while
+// warpgroup 0 runs exp2 on S0_j the tensor core computes S1_j / P1.V, and vice versa.  K/V tiles are loaded once
+// for both query tiles; the whole S row (128 fp32) is pulled from TMEM in one pass.  Used when hd <= 128,
+// Nq % 256 == 0 and Nk % 128 == 0 (the 64x64 and 32x32 levels, ~98 % of the attention FLOPs at 512^2).
+constexpr int kFa2Threads = 320;
+
+struct Fa2Args {
+  int Nq, Nk, hd, hdp, kv_div, stages;
+  float scale_log2;
+  __nv_bfloat16* out;
+  long long ldo;
+  int q_bytes, kv_bytes;  // per 128-row tile
+};
+
+__global__ void __launch_bounds__(kFa2Threads, 1)
+flash_attn2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
+                   const __grid_constant__ CUtensorMap mapV, const Fa2Args p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  constexpr int kP = 128 * 128 * 2;  // P tile bytes
+  uint8_t* sQ = smem;                               // 2 x q_bytes
+  uint8_t* sK = sQ + 2 * p.q_bytes;                 // stages x kv_bytes
+  uint8_t* sV = sK + p.stages * p.kv_bytes;         // stages x kv_bytes
+  uint8_t* sP = sV + p.stages * p.kv_bytes;         // 2 x 32 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kP);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;             // [stages <= 3]
+  uint64_t* kv_empty = kv_full + 3;         // [3]
+  uint64_t* s_full = kv_empty + 3;          // [2]
+  uint64_t* p_ready = s_full + 2;           // [2]
+  uint64_t* pv_done = p_ready + 2;          // [2]
+  uint64_t* o_full = pv_done + 2;           // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q_pair = blockIdx.x, head = blockIdx.y, bq = blockIdx.z;
+  const int T = p.Nk / 128;
+  {
+    const int total16 = (2 * p.q_bytes + 2 * p.stages * p.kv_bytes) / 16;
+    uint4* z = reinterpret_cast<uint4*>(sQ);
+    for (int i = threadIdx.x; i < total16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+  }
+  if (threadIdx.x == 0) {
+    mbar_init(q_full, 1);
+    for (int s = 0; s < 3; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 2);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&s_full[s], 1);
+      mbar_init(&p_ready[s], 128);
+      mbar_init(&pv_done[s], 1);
+    }
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&mapQ);
+      tma_prefetch_desc(&mapK);
+      tma_prefetch_desc(&mapV);
+      const int col_chunk = head * p.hd / 8;
+      mbar_expect_tx(q_full, 2 * 128 * p.hd * 2);
+      tma_load_3d(sQ, &mapQ, q_full, 0, bq * p.Nq + q_pair * 256, col_chunk);
+      tma_load_3d(sQ + p.q_bytes, &mapQ, q_full, 0, bq * p.Nq + q_pair * 256 + 128, col_chunk);
+      const int kv_row0 = (bq / p.kv_div) * p.Nk;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < T; ++j) {
+        mbar_wait(&kv_empty[stage], phase ^ 1);
+        mbar_expect_tx(&kv_full[stage], 2 * 128 * p.hd * 2);
+        tma_load_3d(sK + stage * p.kv_bytes, &mapK, &kv_full[stage], 0, kv_row0 + j * 128, col_chunk);
+        tma_load_3d(sV + stage * p.kv_bytes, &mapV, &kv_full[stage], 0, kv_row0 + j * 128, col_chunk);
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+      const uint32_t idesc_o = make_idesc_bf16(128, (uint32_t)p.hdp, 0, 1);
+      auto issue_s = [&](int q, int j) {
+        const uint32_t q_addr = smem_u32(sQ + q * p.q_bytes);
+        const uint32_t k_addr = smem_u32(sK + (j % p.stages) * p.kv_bytes);
+        const uint32_t d = tmem_base + (uint32_t)(q * 128);
+        for (int k = 0; k < p.hdp / 16; ++k) {
+          const uint64_t da = make_smem_desc(q_addr + k * 4096, 2048, 128, SWZ_NONE);
+          const uint64_t db = make_smem_desc(k_addr + k * 4096, 2048, 128, SWZ_NONE);
+          umma_ss(d, da, db, idesc_s, k ? 1u : 0u);
+        }
+        umma_commit(&s_full[q]);
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(&kv_full[0], 0);
+      tc_fence_after();
+      issue_s(0, 0);
+      issue_s(1, 0);
+      for (int j = 0; j < T; ++j) {
+        if (j + 1 < T) {
+          mbar_wait(&kv_full[(j + 1) % p.stages], (uint32_t)(((j + 1) / p.stages) & 1));
+          tc_fence_after();
+        }
+        const int stage = j % p.stages;
+        const uint32_t v_addr = smem_u32(sV + stage * p.kv_bytes);
+        for (int q = 0; q < 2; ++q) {
+          mbar_wait(&p_ready[q], (uint32_t)(j & 1));
+          tc_fence_after();
+          if (j + 1 < T) issue_s(q, j + 1);
+          const uint32_t p_addr = smem_u32(sP + q * kP);
+          const uint32_t d = tmem_base + 256u + (uint32_t)(q * 128);
+          for (int k = 0; k < 8; ++k) {
+            const uint64_t da = make_smem_desc(p_addr + k * 4096, 2048, 128, SWZ_NONE);
+            const uint64_t db = make_smem_desc(v_addr + k * 256, 128, 2048, SWZ_NONE);
+            umma_ss(d, da, db, idesc_o, (j | k) ? 1u : 0u);
+          }
+          umma_commit(&kv_empty[stage]);
+          umma_commit(&pv_done[q]);
+        }
+      }
+      umma_commit(o_full);
+    }
+  } else {
+    const int q = (warp - 2) >> 2;  // query tile / softmax warpgroup
+    const int qd = warp & 3;
+    const int row = qd * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
+    const uint32_t ts = tmem_base + lane_addr + (uint32_t)(q * 128);
+    const uint32_t to = tmem_base + lane_addr + 256u + (uint32_t)(q * 128);
+    float m_used = -INFINITY, l = 0.f;
+    const float c = p.scale_log2;
+    uint8_t* pb = sP + q * kP + row * 16;
+    for (int j = 0; j < T; ++j) {
+      mbar_wait(&s_full[q], (uint32_t)(j & 1));
+      tc_fence_after();
+      uint32_t v[4][32];
+      tmem_ld32(ts, v[0]);
+      tmem_ld32(ts + 32, v[1]);
+      tmem_ld32(ts + 64, v[2]);
+      tmem_ld32(ts + 96, v[3]);
+      tmem_ld_wait();
+      float mx = -INFINITY;
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[g][i]));
+      if (j > 0) {
+        mbar_wait(&pv_done[q], (uint32_t)((j - 1) & 1));
+        tc_fence_after();
+      }
+      const float m_new = fmaxf(m_used, mx);
+      const bool need = (m_new - m_used) * c > 8.0f;
+      if (__any_sync(0xffffffffu, need)) {
+        const float alpha = (m_used == -INFINITY) ? 0.f : exp2f((m_used - m_new) * c);
+        l *= alpha;
+        m_used = m_new;
+        if (j > 0) {
+          for (int cb = 0; cb < p.hdp; cb += 16) {
+            uint32_t o[16];
+            tmem_ld16(to + cb, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st16(to + cb, o);
+          }
+          tmem_st_wait();
+        }
+      }
+      const float mc = m_used * c;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          float e[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            e[i] = exp2f(fmaf(__uint_as_float(v[g][h * 8 + i]), c, -mc));
+            l += e[i];
+          }
+          *reinterpret_cast<uint4*>(pb + (g * 4 + h) * 2048) =
+              make_uint4(pack_bf16(e[0], e[1]), pack_bf16(e[2], e[3]), pack_bf16(e[4], e[5]), pack_bf16(e[6], e[7]));
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(&p_ready[q]);
+    }
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    const int qrow = q_pair * 256 + q * 128 + row;
+    const float inv = 1.f / l;
+    __nv_bfloat16* op = p.out + ((long long)bq * p.Nq + qrow) * p.ldo + head * p.hd;
+    for (int cb = 0; cb < p.hdp; cb += 16) {
+      uint32_t o[16];
+      tmem_ld16(to + cb, o);
+      tmem_ld_wait();
+#pragma unroll
+      for (int h8 = 0; h8 < 2; ++h8) {
+        if (cb + h8 * 8 < p.hd) {
+          const int b8 = h8 * 8;
+          *reinterpret_cast<uint4*>(op + cb + b8) = make_uint4(
+              pack_bf16(__uint_as_float(o[b8]) * inv, __uint_as_float(o[b8 + 1]) * inv),
+              pack_bf16(__uint_as_float(o[b8 + 2]) * inv, __uint_as_float(o[b8 + 3]) * inv),
+              pack_bf16(__uint_as_float(o[b8 + 4]) * inv, __uint_as_float(o[b8 + 5]) * inv),
+              pack_bf16(__uint_as_float(o[b8 + 6]) * inv, __uint_as_float(o[b8 + 7]) * inv));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // Fallback for key counts the tensor-core tiling cannot express (Nk < 16 or Nk % 16 != 0, e.g. the 2x2 / 12x12
 // maps of reduced test resolutions): one warp per (batch, head, query), exact softmax, CUDA cores.
 struct GaArgs {
@@ -323,6 +552,39 @@ extern "C" int vx_flash_attention(const void* q, long long ldq, const void* k, l
     return 0;
   }
   const int hdp = (hd + 15) / 16 * 16;
+  if (hdp <= 128 && Nq % 256 == 0 && Nk % 128 == 0 && !getenv("VX_FA_V1")) {
+    Fa2Args a{};
+    a.Nq = Nq; a.Nk = Nk; a.hd = hd; a.hdp = hdp; a.kv_div = kv_div;
+    a.scale_log2 = 1.4426950408889634f / sqrtf((float)hd);
+    a.out = (__nv_bfloat16*)out; a.ldo = ldo;
+    a.q_bytes = 128 * hdp * 2;
+    a.kv_bytes = 128 * hdp * 2;
+    a.stages = 3;
+    auto need = [&](int st) { return (size_t)2 * a.q_bytes + (size_t)2 * st * a.kv_bytes + 2 * 32768 + 256 + 128; };
+    if (need(3) > 227 * 1024) a.stages = 2;
+    const size_t smem2 = need(a.stages);
+    VX_REQUIRE(smem2 <= 227 * 1024, "vx_flash_attention: smem %zu too large (hd=%d)", smem2, hd);
+    CUtensorMap mQ, mK, mV;
+    const void* ptrs[3] = {q, k, v};
+    const long long lds[3] = {ldq, ldk, ldv};
+    const long long rows[3] = {(long long)Bq * Nq, (long long)Bkv * Nk, (long long)Bkv * Nk};
+    CUtensorMap* maps[3] = {&mQ, &mK, &mV};
+    for (int i = 0; i < 3; ++i) {
+      uint64_t dims[3] = {8, (uint64_t)rows[i], (uint64_t)lds[i] / 8};
+      uint64_t str[2] = {(uint64_t)lds[i] * 2, 16};
+      uint32_t box[3] = {8, 128, (uint32_t)hd / 8};
+      if (make_tmap_bf16(maps[i], ptrs[i], 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
+    }
+    static bool cfg2 = false;
+    if (!cfg2) {
+      VX_CHECK_CUDA(cudaFuncSetAttribute(flash_attn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      cfg2 = true;
+    }
+    dim3 grid2(Nq / 256, heads, Bq);
+    flash_attn2_kernel<<<grid2, kFa2Threads, smem2, (cudaStream_t)stream>>>(mQ, mK, mV, a);
+    VX_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   int kv_tile = 0;
   const int kv_max = hdp > 96 ? 64 : 128;
   for (int t = kv_max; t >= 16; t -= 16)

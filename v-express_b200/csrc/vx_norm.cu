@@ -204,11 +204,15 @@ __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long 
     const int v = lane + i * 32;
     if (v < V) {
       float y[8];
+      const float4 g0 = *reinterpret_cast<const float4*>(gamma + v * 8), g1 = *reinterpret_cast<const float4*>(gamma + v * 8 + 4);
+      const float4 b0 = *reinterpret_cast<const float4*>(beta + v * 8), b1 = *reinterpret_cast<const float4*>(beta + v * 8 + 4);
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int c = v * 8 + j;
-        y[j] = (f[i][j] - mean) * rstd * gamma[c] + beta[c];
-        if (perow) y[j] += perow[c];
+      for (int j = 0; j < 8; ++j) y[j] = (f[i][j] - mean) * rstd * gg[j] + bb[j];
+      if (perow) {
+        const float4 p0 = *reinterpret_cast<const float4*>(perow + v * 8), p1 = *reinterpret_cast<const float4*>(perow + v * 8 + 4);
+        y[0] += p0.x; y[1] += p0.y; y[2] += p0.z; y[3] += p0.w; y[4] += p1.x; y[5] += p1.y; y[6] += p1.z; y[7] += p1.w;
       }
       store8(out + (long long)warp * ldo + v * 8, y);
     }

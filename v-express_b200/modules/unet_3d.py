@@ -424,8 +424,11 @@ class UNetEngine:
             return hit[1]
         bflat = bank.to(device=self.dev, dtype=BF16).reshape(-1, bank.shape[-1]).contiguous()
         kv = ops.gemm(bflat, self.W[name + ".attn1_5.kv"])
-        self._bank_cache[name] = (key, kv)
-        return kv
+        # CFG: the uncond half of the bank is all zeros (reference mutual_self_attention.py:359) -> K = V = 0 ->
+        # softmax-uniform x 0: the attention output of those frames is exactly 0, so it is not computed
+        uncond_zero = bool(bank.shape[0] == 2 and torch.count_nonzero(bank[0]).item() == 0)
+        self._bank_cache[name] = (key, (kv, uncond_zero))
+        return kv, uncond_zero
 
     # ---------------------------------------------------------------- blocks
     def _resnet(self, p, x, x2, NB, H, Wd, temb):
@@ -465,9 +468,14 @@ class UNetEngine:
         # attn1_5: reference attention, K/V from the bank (one per CFG half, shared by the f frames)
         n = ops.layernorm(h, W[t + ".norm1_5.weight"], W[t + ".norm1_5.bias"])
         q = ops.gemm(n, W[t + ".attn1_5.to_q.weight"])
-        kv = self._bank_kv(t, block)
+        kv, uncond_zero = self._bank_kv(t, block)
         Nk = kv.shape[0] // (NB // f)
-        a = ops.flash_attention(q, kv[:, :C], kv[:, C:], heads, HW, Nk, kv_div=f)
+        if uncond_zero and NB == 2 * f:
+            a = torch.empty((NB * HW, C), device=self.dev, dtype=BF16)
+            a[:f * HW].zero_()
+            ops.flash_attention(q[f * HW:], kv[Nk:, :C], kv[Nk:, C:], heads, HW, Nk, kv_div=f, out=a[f * HW:])
+        else:
+            a = ops.flash_attention(q, kv[:, :C], kv[:, C:], heads, HW, Nk, kv_div=f)
         h = ops.gemm(a, W[t + ".attn1_5.to_out.0.weight"], W[t + ".attn1_5.to_out.0.bias"],
                      scale=float(m.reference_attention_weight), residual=h)
         # attn2: audio cross-attention (5 tokens per frame)
