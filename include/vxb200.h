@@ -85,7 +85,8 @@ int vx_softmax_rows(const float* x, long long ldx, long long rows, int n, void* 
 
 /* ---- conv_in: 3x3 conv from planar (n,c,h,w) bf16 with Cin <= 8 to NHWC, + bias + gathered NHWC addend
  * (kps_features, modules/unet_3d.py:485-487); optional per-pixel pre-transform bf16(pre_w @ bf16(pre_scale*v) + pre_b)
- * (latents / 0.18215 and the VAE post_quant_conv, pipelines/v_express_pipeline.py:155,159). w fp32 [Cout, Cin*9]. */
+ * (latents / 0.18215 and the VAE post_quant_conv, pipelines/v_express_pipeline.py:155,159). w fp32 [Cin*9, Cout]
+ * (transposed), Cin = 4. */
 int vx_conv_in(const void* in, long long sn, long long sc, int NB, int H, int W, int Cin, int Cout, const float* w,
                const float* bias, const void* addend, const int* add_frame, long long add_ld, float pre_scale,
                const float* pre_w, const float* pre_b, void* out, long long ldo, void* stream);

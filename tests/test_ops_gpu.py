@@ -145,7 +145,7 @@ def test_conv_in_out_im2col_upsample(ops):
     kps = torch.randn(10 * H * W, Cout, device="cuda", generator=g).bfloat16()
     frames = torch.tensor([7, 1, 3, 9, 0, 2], device="cuda", dtype=torch.int32)
     xin = x.permute(0, 2, 1, 3, 4).reshape(NB, 4, H, W)                                     # strided view, planes contiguous
-    out = ops.conv_in(xin, w.reshape(Cout, 36).contiguous(), bias, Cout, addend=kps, add_frame=frames)
+    out = ops.conv_in(xin, w.reshape(Cout, 36).t().contiguous(), bias, Cout, addend=kps, add_frame=frames)
     ref = F.conv2d(xin.float(), w, bias, padding=1).permute(0, 2, 3, 1).reshape(-1, Cout)
     ref = ref + kps.float().view(10, H * W, Cout)[frames.long()].reshape(-1, Cout)
     assert _rel(out, ref) < 4e-3

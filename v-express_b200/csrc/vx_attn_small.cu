@@ -26,40 +26,91 @@ template <int HD>
 __global__ void __launch_bounds__(128) temporal_attn_kernel(const TemporalArgs p) {
   extern __shared__ uint8_t sm_raw[];
   constexpr int VEC = HD / 8;
+  constexpr bool F32 = HD <= 80;                       // K/V staged as fp32 (no unpack in the inner loops)
+  constexpr int ESZ = F32 ? 4 : 2;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int fpad = p.f <= 16 ? 16 : 32;
-  const int G = 32 / fpad;                               // heads per pass
-  const size_t per_warp = (size_t)2 * G * p.f * HD * sizeof(__nv_bfloat16);
-  __nv_bfloat16* sk = reinterpret_cast<__nv_bfloat16*>(sm_raw + warp * per_warp);
-  __nv_bfloat16* sv = sk + G * p.f * HD;
-  const long long item = (long long)blockIdx.x * 4 + warp;   // (b, pixel)
-  if (item >= (long long)p.b * p.HW) return;
-  const int px = (int)(item % p.HW);
-  const int bb = (int)(item / p.HW);
+  const int G = 32 / fpad;                             // heads per warp
+  const int passes = p.heads / G;
+  const size_t per_warp = (size_t)2 * G * p.f * HD * ESZ;
+  uint8_t* base = sm_raw + warp * per_warp;
+  const long long item = (long long)blockIdx.x * 4 + warp;   // (b, pixel, head group), head group fastest
+  if (item >= (long long)p.b * p.HW * passes) return;
+  const int h0 = (int)(item % passes) * G;
+  const long long bp = item / passes;
+  const int px = (int)(bp % p.HW);
+  const int bb = (int)(bp / p.HW);
   const long long row0 = (long long)bb * p.f * p.HW + px;
-  const int hs = lane / fpad, qi = lane % fpad;          // head slot, query frame of this thread
+  const int hs = lane / fpad, qi = lane % fpad;        // head slot, query frame of this thread
   const bool active = qi < p.f;
-  for (int h0 = 0; h0 < p.heads; h0 += G) {
-    __syncwarp();
-    // stage K, V of heads [h0, h0+G): [G][f][HD]
-    for (int idx = lane; idx < G * p.f * VEC; idx += 32) {
-      const int c = (idx % VEC) * 8;
-      const int fr = (idx / VEC) % p.f;
-      const int g = idx / (VEC * p.f);
-      const long long off = (row0 + (long long)fr * p.HW) * p.ld + (h0 + g) * HD + c;
-      *reinterpret_cast<uint4*>(sk + (g * p.f + fr) * HD + c) = *reinterpret_cast<const uint4*>(p.k + off);
-      *reinterpret_cast<uint4*>(sv + (g * p.f + fr) * HD + c) = *reinterpret_cast<const uint4*>(p.v + off);
+  const int head = h0 + hs;
+  // stage K, V of heads [h0, h0+G): [G][f][HD]
+  for (int idx = lane; idx < G * p.f * VEC; idx += 32) {
+    const int c = (idx % VEC) * 8;
+    const int fr = (idx / VEC) % p.f;
+    const int g = idx / (VEC * p.f);
+    const long long off = (row0 + (long long)fr * p.HW) * p.ld + (h0 + g) * HD + c;
+    const uint4 uk = *reinterpret_cast<const uint4*>(p.k + off);
+    const uint4 uv = *reinterpret_cast<const uint4*>(p.v + off);
+    const int e = (g * p.f + fr) * HD + c;
+    if (F32) {
+      float* fk = reinterpret_cast<float*>(base) + e;
+      float* fv = reinterpret_cast<float*>(base) + G * p.f * HD + e;
+      const uint32_t wk[4] = {uk.x, uk.y, uk.z, uk.w}, wv[4] = {uv.x, uv.y, uv.z, uv.w};
+      float a[8], bq[8];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 x = unpack_bf16(wk[t]), y = unpack_bf16(wv[t]);
+        a[2 * t] = x.x; a[2 * t + 1] = x.y; bq[2 * t] = y.x; bq[2 * t + 1] = y.y;
+      }
+      *reinterpret_cast<float4*>(fk) = make_float4(a[0], a[1], a[2], a[3]);
+      *reinterpret_cast<float4*>(fk + 4) = make_float4(a[4], a[5], a[6], a[7]);
+      *reinterpret_cast<float4*>(fv) = make_float4(bq[0], bq[1], bq[2], bq[3]);
+      *reinterpret_cast<float4*>(fv + 4) = make_float4(bq[4], bq[5], bq[6], bq[7]);
+    } else {
+      *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(base) + e) = uk;
+      *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(base) + G * p.f * HD + e) = uv;
     }
+  }
+  const long long qoff = (row0 + (long long)(active ? qi : 0) * p.HW) * p.ld + head * HD;
+  float s[32];
+  float mx = -INFINITY;
+  if (F32) {
+    float qf[HD];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const uint4 u = *reinterpret_cast<const uint4*>(p.q + qoff + i * 8);
+      const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 x = unpack_bf16(w4[t]);
+        qf[i * 8 + 2 * t] = x.x * p.scale;
+        qf[i * 8 + 2 * t + 1] = x.y * p.scale;
+      }
+    }
+    __syncwarp();
+    const float* kh = reinterpret_cast<const float*>(base) + hs * p.f * HD;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (j >= p.f) break;
+      float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+      for (int i = 0; i < HD / 4; ++i) {
+        const float4 kk = *reinterpret_cast<const float4*>(kh + j * HD + i * 4);
+        a0 = fmaf(qf[4 * i], kk.x, a0);
+        a1 = fmaf(qf[4 * i + 1], kk.y, a1);
+        a0 = fmaf(qf[4 * i + 2], kk.z, a0);
+        a1 = fmaf(qf[4 * i + 3], kk.w, a1);
+      }
+      s[j] = a0 + a1;
+      mx = fmaxf(mx, s[j]);
+    }
+  } else {
     uint4 qreg[VEC];
-    const int head = h0 + hs;
-    const long long qoff = (row0 + (long long)(active ? qi : 0) * p.HW) * p.ld + head * HD;
 #pragma unroll
     for (int i = 0; i < VEC; ++i) qreg[i] = *reinterpret_cast<const uint4*>(p.q + qoff + i * 8);
     __syncwarp();
-    float s[32];
-    float mx = -INFINITY;
-    const __nv_bfloat16* kh = sk + hs * p.f * HD;
-    const __nv_bfloat16* vh = sv + hs * p.f * HD;
+    const __nv_bfloat16* kh = reinterpret_cast<const __nv_bfloat16*>(base) + hs * p.f * HD;
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
       if (j >= p.f) break;
@@ -76,29 +127,43 @@ __global__ void __launch_bounds__(128) temporal_attn_kernel(const TemporalArgs p
           acc = fmaf(x.y, y.y, acc);
         }
       }
-      acc *= p.scale;
-      s[j] = acc;
-      mx = fmaxf(mx, acc);
+      s[j] = acc * p.scale;
+      mx = fmaxf(mx, s[j]);
     }
-    float sum = 0.f;
+  }
+  float sum = 0.f;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      if (j < p.f) {
-        s[j] = __expf(s[j] - mx);
-        sum += s[j];
-      }
+  for (int j = 0; j < 32; ++j) {
+    if (j < p.f) {
+      s[j] = __expf(s[j] - mx);
+      sum += s[j];
     }
-    const float inv = 1.f / sum;
-    __nv_bfloat16* op = p.out + (row0 + (long long)qi * p.HW) * p.ldo + head * HD;
+  }
+  const float inv = 1.f / sum;
+  __nv_bfloat16* op = p.out + (row0 + (long long)qi * p.HW) * p.ldo + head * HD;
 #pragma unroll 1
-    for (int i = 0; i < VEC; ++i) {
-      float o[8];
+  for (int i = 0; i < VEC; ++i) {
+    float o[8];
 #pragma unroll
-      for (int t = 0; t < 8; ++t) o[t] = 0.f;
+    for (int t = 0; t < 8; ++t) o[t] = 0.f;
+    if (F32) {
+      const float* vh = reinterpret_cast<const float*>(base) + (G + hs) * p.f * HD + i * 8;
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         if (j < p.f) {
-          const uint4 vv = *reinterpret_cast<const uint4*>(vh + j * HD + i * 8);
+          const float4 v0 = *reinterpret_cast<const float4*>(vh + j * HD);
+          const float4 v1 = *reinterpret_cast<const float4*>(vh + j * HD + 4);
+          o[0] = fmaf(s[j], v0.x, o[0]); o[1] = fmaf(s[j], v0.y, o[1]); o[2] = fmaf(s[j], v0.z, o[2]);
+          o[3] = fmaf(s[j], v0.w, o[3]); o[4] = fmaf(s[j], v1.x, o[4]); o[5] = fmaf(s[j], v1.y, o[5]);
+          o[6] = fmaf(s[j], v1.z, o[6]); o[7] = fmaf(s[j], v1.w, o[7]);
+        }
+      }
+    } else {
+      const __nv_bfloat16* vh = reinterpret_cast<const __nv_bfloat16*>(base) + (G + hs) * p.f * HD + i * 8;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (j < p.f) {
+          const uint4 vv = *reinterpret_cast<const uint4*>(vh + j * HD);
           const uint32_t w4[4] = {vv.x, vv.y, vv.z, vv.w};
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
@@ -108,10 +173,10 @@ __global__ void __launch_bounds__(128) temporal_attn_kernel(const TemporalArgs p
           }
         }
       }
-      if (active)
-        *reinterpret_cast<uint4*>(op + i * 8) = make_uint4(pack_bf16(o[0] * inv, o[1] * inv), pack_bf16(o[2] * inv, o[3] * inv),
-                                                           pack_bf16(o[4] * inv, o[5] * inv), pack_bf16(o[6] * inv, o[7] * inv));
     }
+    if (active)
+      *reinterpret_cast<uint4*>(op + i * 8) = make_uint4(pack_bf16(o[0] * inv, o[1] * inv), pack_bf16(o[2] * inv, o[3] * inv),
+                                                         pack_bf16(o[4] * inv, o[5] * inv), pack_bf16(o[6] * inv, o[7] * inv));
   }
 }
 
@@ -200,9 +265,9 @@ extern "C" int vx_temporal_attention(const void* q, const void* k, const void* v
                  ldo, b, f, HW, heads, hd, 1.0f / sqrtf((float)hd)};
   const int G = f <= 16 ? 2 : 1;
   VX_REQUIRE(heads % G == 0, "vx_temporal_attention: heads=%d must be even", heads);
-  const size_t smem = (size_t)4 * 2 * G * f * hd * 2;
+  const size_t smem = (size_t)4 * 2 * G * f * hd * (hd <= 80 ? 4 : 2);
   VX_REQUIRE(smem <= 200 * 1024, "vx_temporal_attention: smem %zu", smem);
-  const long long items = (long long)b * HW;
+  const long long items = (long long)b * HW * (heads / G);
   const unsigned grid = (unsigned)((items + 3) / 4);
   auto st = (cudaStream_t)stream;
 #define TA_LAUNCH(HD)                                                                                               \

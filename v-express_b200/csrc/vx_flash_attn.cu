@@ -250,6 +250,12 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
 // Nq % 256 == 0 and Nk % 128 == 0 (the 64x64 and 32x32 levels, ~98 % of the attention FLOPs at 512^2).
 constexpr int kFa2Threads = 320;
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 struct Fa2Args {
   int Nq, Nk, hd, hdp, kv_div, stages;
   float scale_log2;
@@ -396,11 +402,16 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
       tmem_ld32(ts + 64, v[2]);
       tmem_ld32(ts + 96, v[3]);
       tmem_ld_wait();
-      float mx = -INFINITY;
+      // 8 independent max chains (the single softmax warp per SM sub-partition has no other ILP)
+      float mxs[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) mxs[i] = __uint_as_float(v[0][i]);
 #pragma unroll
       for (int g = 0; g < 4; ++g)
 #pragma unroll
-        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[g][i]));
+        for (int i = 0; i < 32; ++i) mxs[i & 7] = fmaxf(mxs[i & 7], __uint_as_float(v[g][i]));
+      const float mx = fmaxf(fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3])),
+                             fmaxf(fmaxf(mxs[4], mxs[5]), fmaxf(mxs[6], mxs[7])));
       if (j > 0) {
         mbar_wait(&pv_done[q], (uint32_t)((j - 1) & 1));
         tc_fence_after();
@@ -424,6 +435,7 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
         }
       }
       const float mc = m_used * c;
+      float ls[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
 #pragma unroll
@@ -431,13 +443,14 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
           float e[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            e[i] = exp2f(fmaf(__uint_as_float(v[g][h * 8 + i]), c, -mc));
-            l += e[i];
+            e[i] = ex2_approx(fmaf(__uint_as_float(v[g][h * 8 + i]), c, -mc));
+            ls[i & 3] += e[i];
           }
           *reinterpret_cast<uint4*>(pb + (g * 4 + h) * 2048) =
               make_uint4(pack_bf16(e[0], e[1]), pack_bf16(e[2], e[3]), pack_bf16(e[4], e[5]), pack_bf16(e[6], e[7]));
         }
       }
+      l += (ls[0] + ls[1]) + (ls[2] + ls[3]);
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(&p_ready[q]);

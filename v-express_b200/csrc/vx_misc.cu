@@ -14,12 +14,12 @@ namespace vx {
 
 // ------------------------------------------------------------------ conv_in
 // in: planar, element (img n, ch c, y, x) at in[n*sn + c*sc + y*W + x]  (bf16)
-// w: fp32 [Cout][Cin*9] ; out NHWC [n*H*W + y*W + x][Cout]
+// wt: fp32 [Cin*9][Cout] (transposed conv weight) ; out NHWC [n*H*W + y*W + x][Cout]
 // addend (optional): NHWC bf16 rows indexed by add_row[n] (frame gather) or n when add_row == null
 struct ConvInArgs {
   const __nv_bfloat16* in; long long sn, sc;
   int NB, H, W, Cin, Cout;
-  const float* w; const float* bias;
+  const float* wt; const float* bias;
   const __nv_bfloat16* addend; const int* add_frame; long long add_ld;
   float pre_scale; const float* pre_w; const float* pre_b;  // optional per-pixel 1x1 pre-transform
   __nv_bfloat16* out; long long ldo;
@@ -27,13 +27,11 @@ struct ConvInArgs {
 
 __device__ __forceinline__ float rbf16(float v) { return __bfloat162float(__float2bfloat16(v)); }
 
+template <int CIN>
 __global__ void conv_in_kernel(const ConvInArgs p) {
-  extern __shared__ float sw[];  // [Cin*9][Cout] transposed for conflict-free reads
-  const int K = p.Cin * 9;
-  for (int i = threadIdx.x; i < K * p.Cout; i += blockDim.x) {
-    const int co = i / K, kk = i % K;
-    sw[kk * p.Cout + co] = p.w[i];
-  }
+  extern __shared__ float sw[];  // [Cin*9][Cout]: p.w is pre-transposed on the host side of the ABI (wt)
+  constexpr int K = CIN * 9;
+  for (int i = threadIdx.x; i < K * p.Cout; i += blockDim.x) sw[i] = p.wt[i];
   __syncthreads();
   const int vecs = p.Cout / 8;
   const long long total = (long long)p.NB * p.H * p.W * vecs;
@@ -51,18 +49,23 @@ __global__ void conv_in_kernel(const ConvInArgs p) {
     for (int t = 0; t < 9; ++t) {
       const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
       if (yy < 0 || yy >= p.H || xx < 0 || xx >= p.W) continue;
-      float vin[8];
-      for (int c = 0; c < p.Cin; ++c) vin[c] = __bfloat162float(p.in[n * p.sn + c * p.sc + yy * p.W + xx]);
+      float vin[CIN];
+#pragma unroll
+      for (int c = 0; c < CIN; ++c) vin[c] = __bfloat162float(p.in[n * p.sn + c * p.sc + yy * p.W + xx]);
       if (p.pre_w) {
-        float tmp[8];
-        for (int c = 0; c < p.Cin; ++c) tmp[c] = rbf16(p.pre_scale * vin[c]);
-        for (int c = 0; c < p.Cin; ++c) {
+        float tmp[CIN];
+#pragma unroll
+        for (int c = 0; c < CIN; ++c) tmp[c] = rbf16(p.pre_scale * vin[c]);
+#pragma unroll
+        for (int c = 0; c < CIN; ++c) {
           float a = p.pre_b ? p.pre_b[c] : 0.f;
-          for (int k = 0; k < p.Cin; ++k) a += p.pre_w[c * p.Cin + k] * tmp[k];
+#pragma unroll
+          for (int k = 0; k < CIN; ++k) a += p.pre_w[c * CIN + k] * tmp[k];
           vin[c] = rbf16(a);
         }
       }
-      for (int c = 0; c < p.Cin; ++c) {
+#pragma unroll
+      for (int c = 0; c < CIN; ++c) {
         const float* wr = sw + (c * 9 + t) * p.Cout + cv * 8;
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] += vin[c] * wr[i];
@@ -298,19 +301,19 @@ extern "C" int vx_conv_in(const void* in, long long sn, long long sc, int NB, in
                           const float* w, const float* bias, const void* addend, const int* add_frame,
                           long long add_ld, float pre_scale, const float* pre_w, const float* pre_b, void* out,
                           long long ldo, void* stream) {
-  VX_REQUIRE(Cout % 8 == 0 && Cin <= 8 && Cin * 9 * Cout * 4 <= 200 * 1024, "vx_conv_in: Cin=%d Cout=%d unsupported", Cin, Cout);
+  VX_REQUIRE(Cout % 8 == 0 && Cin == 4 && Cin * 9 * Cout * 4 <= 200 * 1024, "vx_conv_in: Cin=%d (must be 4) Cout=%d unsupported", Cin, Cout);
   ConvInArgs a{(const __nv_bfloat16*)in, sn, sc, NB, H, W, Cin, Cout, w, bias, (const __nv_bfloat16*)addend, add_frame,
                add_ld, pre_scale, pre_w, pre_b, (__nv_bfloat16*)out, ldo};
   const size_t smem = (size_t)Cin * 9 * Cout * 4;
   static bool cfg = false;
   if (!cfg) {
-    VX_CHECK_CUDA(cudaFuncSetAttribute(conv_in_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    VX_CHECK_CUDA(cudaFuncSetAttribute(conv_in_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     cfg = true;
   }
   const long long total = (long long)NB * H * W * (Cout / 8);
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  conv_in_kernel<<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(a);
+  conv_in_kernel<4><<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(a);
   VX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

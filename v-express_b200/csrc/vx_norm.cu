@@ -139,21 +139,37 @@ __global__ void gn_apply_kernel(const GnApplyArgs p) {
   const int V = C / 8;
   const int p0 = blockIdx.x * p.chunk;
   const int p1 = min(p.HW, p0 + p.chunk);
-  const long long total = (long long)(p1 - p0) * V;
-  for (long long idx = threadIdx.x; idx < total; idx += blockDim.x) {
-    const int px = p0 + (int)(idx / V);
-    const int c0 = (int)(idx % V) * 8;
-    const long long row = (long long)n * p.HW + px;
-    const __nv_bfloat16* src = c0 >= p.C1 ? p.x2 + row * p.ld2 + (c0 - p.C1) : p.x1 + row * p.ld1 + c0;
+  // thread = (channel vector v, pixel lane r): scale/shift of its 8 channels live in registers
+  const int R = blockDim.x / V;
+  const int v = threadIdx.x % V, r = threadIdx.x / V;
+  if (r >= R) return;
+  const int c0 = v * 8;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    sc[i] = scale[c0 + i];
+    sh[i] = shift[c0 + i];
+  }
+  const bool second = c0 >= p.C1;
+  const __nv_bfloat16* src = second ? p.x2 + (long long)n * p.HW * p.ld2 + (c0 - p.C1)
+                                    : p.x1 + (long long)n * p.HW * p.ld1 + c0;
+  const long long lds = second ? p.ld2 : p.ld1;
+  __nv_bfloat16* dst = p.out + (long long)n * p.HW * p.ldo + c0;
+  for (int px = p0 + r; px < p1; px += R) {
     float f[8];
-    load8(src, f);
+    load8(src + px * lds, f);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      float y = f[i] * scale[c0 + i] + shift[c0 + i];
-      if (p.silu) y = y / (1.f + __expf(-y));
+      float y = fmaf(f[i], sc[i], sh[i]);
+      if (p.silu) {
+        // y * sigmoid(y) with sigmoid(y) = 0.5 + 0.5 * tanh(y / 2): one MUFU op per element
+        float t;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * y));
+        y = y * fmaf(0.5f, t, 0.5f);
+      }
       f[i] = y;
     }
-    store8(p.out + row * p.ldo + c0, f);
+    store8(dst + px * p.ldo, f);
   }
 }
 
@@ -326,7 +342,9 @@ extern "C" int vx_groupnorm_apply(const void* x1, long long ld1, int C1, const v
   if (chunk > HW) chunk = HW;
   a.chunk = chunk;
   const size_t smem = (size_t)(2 * C + 2 * G) * sizeof(float);
-  gn_apply_kernel<<<dim3((HW + chunk - 1) / chunk, NB), 256, smem, (cudaStream_t)stream>>>(a);
+  int Rr;
+  const int threads = gn_block(C, &Rr);
+  gn_apply_kernel<<<dim3((HW + chunk - 1) / chunk, NB), threads, smem, (cudaStream_t)stream>>>(a);
   VX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

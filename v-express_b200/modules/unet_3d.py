@@ -381,7 +381,7 @@ class UNetEngine:
                 continue
             p = k[:-7]
             if p in ("conv_in",):
-                W[k] = self._f32(v).reshape(v.shape[0], -1).contiguous()                     # fp32 [Cout, Cin*9]
+                W[k] = self._f32(v).reshape(v.shape[0], -1).t().contiguous()                 # fp32 [Cin*9, Cout]
             elif p == "conv_out":
                 W[k] = self._f32(v).permute(0, 2, 3, 1).reshape(v.shape[0], 9, v.shape[1]).contiguous()
             elif p.endswith("time_emb_proj"):

@@ -145,7 +145,7 @@ class VaeDecoderEngine:
             if k.endswith(".bias") or v.dim() == 1:
                 self.W[k] = v.to(device=dev, dtype=BF16).float().contiguous()
             elif p == "decoder.conv_in":
-                self.W[k] = v.to(device=dev, dtype=BF16).float().reshape(v.shape[0], -1).contiguous()
+                self.W[k] = v.to(device=dev, dtype=BF16).float().reshape(v.shape[0], -1).t().contiguous()
             elif p == "decoder.conv_out":
                 self.W[k] = v.to(device=dev, dtype=BF16).float().permute(0, 2, 3, 1).reshape(v.shape[0], 9, v.shape[1]).contiguous()
             elif p == "post_quant_conv":
