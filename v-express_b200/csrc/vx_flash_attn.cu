@@ -282,7 +282,8 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
   uint64_t* p_ready = s_full + 2;           // [2]
   uint64_t* pv_done = p_ready + 2;          // [2]
   uint64_t* o_full = pv_done + 2;           // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+  uint64_t* s_free = o_full + 1;            // [2] S(q) has been pulled into registers -> may be overwritten
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q_pair = blockIdx.x, head = blockIdx.y, bq = blockIdx.z;
@@ -302,6 +303,7 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
       mbar_init(&s_full[s], 1);
       mbar_init(&p_ready[s], 128);
       mbar_init(&pv_done[s], 1);
+      mbar_init(&s_free[s], 128);
     }
     mbar_init(o_full, 1);
     fence_barrier_init();
@@ -363,13 +365,19 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
         if (j + 1 < T) {
           mbar_wait(&kv_full[(j + 1) % p.stages], (uint32_t)(((j + 1) / p.stages) & 1));
           tc_fence_after();
+          // S(q, j+1) is issued as soon as softmax(q, j) has pulled S(q, j) into registers, so it is ready
+          // long before that warpgroup finishes its exponentials
+          for (int q = 0; q < 2; ++q) {
+            mbar_wait(&s_free[q], (uint32_t)(j & 1));
+            tc_fence_after();
+            issue_s(q, j + 1);
+          }
         }
         const int stage = j % p.stages;
         const uint32_t v_addr = smem_u32(sV + stage * p.kv_bytes);
         for (int q = 0; q < 2; ++q) {
           mbar_wait(&p_ready[q], (uint32_t)(j & 1));
           tc_fence_after();
-          if (j + 1 < T) issue_s(q, j + 1);
           const uint32_t p_addr = smem_u32(sP + q * kP);
           const uint32_t d = tmem_base + 256u + (uint32_t)(q * 128);
           for (int k = 0; k < 8; ++k) {
@@ -402,6 +410,8 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
       tmem_ld32(ts + 64, v[2]);
       tmem_ld32(ts + 96, v[3]);
       tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&s_free[q]);
       // 8 independent max chains (the single softmax warp per SM sub-partition has no other ILP)
       float mxs[8];
 #pragma unroll
@@ -573,7 +583,7 @@ extern "C" int vx_flash_attention(const void* q, long long ldq, const void* k, l
     a.q_bytes = 128 * hdp * 2;
     a.kv_bytes = 128 * hdp * 2;
     a.stages = 3;
-    auto need = [&](int st) { return (size_t)2 * a.q_bytes + (size_t)2 * st * a.kv_bytes + 2 * 32768 + 256 + 128; };
+    auto need = [&](int st) { return (size_t)2 * a.q_bytes + (size_t)2 * st * a.kv_bytes + 2 * 32768 + 384 + 128; };
     if (need(3) > 227 * 1024) a.stages = 2;
     const size_t smem2 = need(a.stages);
     VX_REQUIRE(smem2 <= 227 * 1024, "vx_flash_attention: smem %zu too large (hd=%d)", smem2, hd);
