@@ -248,7 +248,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
 // warpgroup 0 runs exp2 on S0_j the tensor core computes S1_j / P1.V, and vice versa.  K/V tiles are loaded once
 // for both query tiles; the whole S row (128 fp32) is pulled from TMEM in one pass.  Used when hd <= 128,
 // Nq % 256 == 0 and Nk % 128 == 0 (the 64x64 and 32x32 levels, ~98 % of the attention FLOPs at 512^2).
-constexpr int kFa2Threads = 320;
+constexpr int kFa2Threads = 352;  // TMA warp, 2 MMA warps (one per query tile), 2 x 4 softmax warps
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -281,8 +281,8 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
   uint64_t* s_full = kv_empty + 3;          // [2]
   uint64_t* p_ready = s_full + 2;           // [2]
   uint64_t* pv_done = p_ready + 2;          // [2]
-  uint64_t* o_full = pv_done + 2;           // [1]
-  uint64_t* s_free = o_full + 1;            // [2] S(q) has been pulled into registers -> may be overwritten
+  uint64_t* o_full = pv_done + 2;           // [2]
+  uint64_t* s_free = o_full + 2;            // [2] S(q) has been pulled into registers -> may be overwritten
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -304,8 +304,8 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
       mbar_init(&p_ready[s], 128);
       mbar_init(&pv_done[s], 1);
       mbar_init(&s_free[s], 128);
+      mbar_init(&o_full[s], 1);
     }
-    mbar_init(o_full, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -341,55 +341,50 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 || warp == 10) {
+    // one MMA-issuing warp per query tile: the two tiles advance independently (no cross-tile ordering), so the
+    // softmax warpgroups settle into anti-phase and keep the MUFU pipe busy
     if (lane == 0) {
+      const int q = warp == 1 ? 0 : 1;
       const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
       const uint32_t idesc_o = make_idesc_bf16(128, (uint32_t)p.hdp, 0, 1);
-      auto issue_s = [&](int q, int j) {
-        const uint32_t q_addr = smem_u32(sQ + q * p.q_bytes);
+      const uint32_t q_addr = smem_u32(sQ + q * p.q_bytes);
+      const uint32_t p_addr = smem_u32(sP + q * kP);
+      const uint32_t d_s = tmem_base + (uint32_t)(q * 128);
+      const uint32_t d_o = tmem_base + 256u + (uint32_t)(q * 128);
+      auto issue_s = [&](int j) {
         const uint32_t k_addr = smem_u32(sK + (j % p.stages) * p.kv_bytes);
-        const uint32_t d = tmem_base + (uint32_t)(q * 128);
         for (int k = 0; k < p.hdp / 16; ++k) {
           const uint64_t da = make_smem_desc(q_addr + k * 4096, 2048, 128, SWZ_NONE);
           const uint64_t db = make_smem_desc(k_addr + k * 4096, 2048, 128, SWZ_NONE);
-          umma_ss(d, da, db, idesc_s, k ? 1u : 0u);
+          umma_ss(d_s, da, db, idesc_s, k ? 1u : 0u);
         }
         umma_commit(&s_full[q]);
       };
       mbar_wait(q_full, 0);
       mbar_wait(&kv_full[0], 0);
       tc_fence_after();
-      issue_s(0, 0);
-      issue_s(1, 0);
+      issue_s(0);
       for (int j = 0; j < T; ++j) {
         if (j + 1 < T) {
           mbar_wait(&kv_full[(j + 1) % p.stages], (uint32_t)(((j + 1) / p.stages) & 1));
+          mbar_wait(&s_free[q], (uint32_t)(j & 1));   // S(q, j) is in registers -> overwrite it with S(q, j+1)
           tc_fence_after();
-          // S(q, j+1) is issued as soon as softmax(q, j) has pulled S(q, j) into registers, so it is ready
-          // long before that warpgroup finishes its exponentials
-          for (int q = 0; q < 2; ++q) {
-            mbar_wait(&s_free[q], (uint32_t)(j & 1));
-            tc_fence_after();
-            issue_s(q, j + 1);
-          }
+          issue_s(j + 1);
         }
         const int stage = j % p.stages;
         const uint32_t v_addr = smem_u32(sV + stage * p.kv_bytes);
-        for (int q = 0; q < 2; ++q) {
-          mbar_wait(&p_ready[q], (uint32_t)(j & 1));
-          tc_fence_after();
-          const uint32_t p_addr = smem_u32(sP + q * kP);
-          const uint32_t d = tmem_base + 256u + (uint32_t)(q * 128);
-          for (int k = 0; k < 8; ++k) {
-            const uint64_t da = make_smem_desc(p_addr + k * 4096, 2048, 128, SWZ_NONE);
-            const uint64_t db = make_smem_desc(v_addr + k * 256, 128, 2048, SWZ_NONE);
-            umma_ss(d, da, db, idesc_o, (j | k) ? 1u : 0u);
-          }
-          umma_commit(&kv_empty[stage]);
-          umma_commit(&pv_done[q]);
+        mbar_wait(&p_ready[q], (uint32_t)(j & 1));
+        tc_fence_after();
+        for (int k = 0; k < 8; ++k) {
+          const uint64_t da = make_smem_desc(p_addr + k * 4096, 2048, 128, SWZ_NONE);
+          const uint64_t db = make_smem_desc(v_addr + k * 256, 128, 2048, SWZ_NONE);
+          umma_ss(d_o, da, db, idesc_o, (j | k) ? 1u : 0u);
         }
+        umma_commit(&kv_empty[stage]);
+        umma_commit(&pv_done[q]);
       }
-      umma_commit(o_full);
+      umma_commit(&o_full[q]);
     }
   } else {
     const int q = (warp - 2) >> 2;  // query tile / softmax warpgroup
@@ -465,7 +460,7 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
       tc_fence_before();
       mbar_arrive(&p_ready[q]);
     }
-    mbar_wait(o_full, 0);
+    mbar_wait(&o_full[q], 0);
     tc_fence_after();
     const int qrow = q_pair * 256 + q * 128 + row;
     const float inv = 1.f / l;
