@@ -167,6 +167,66 @@ class Clocks:
 
 
 # --------------------------------------------------------------------------------------------- kernel timing
+def op_table(pipe, host, L, h):
+    """VX_BENCH_OPS=1: per-op / per-shape device time of one UNet forward.  Every unique (op, shapes) call recorded
+    during an eager forward is replayed 8x back-to-back and timed with CUDA events (so host launch overhead overlaps)."""
+    from vexpress_b200 import ops
+    recs = []
+    names = ["gemm", "conv3x3", "flash_attention", "temporal_attention", "smallkv_attention", "groupnorm", "layernorm",
+             "conv_in", "conv_out", "im2col_s2", "upsample2x", "skinny_linear", "timestep_embed"]
+    orig = {n: getattr(ops, n) for n in names}
+
+    def wrap(n, fn):
+        def w(*a, **k):
+            out = fn(*a, **k)
+            sig = tuple(tuple(x.shape) for x in a[:3] if torch.is_tensor(x))
+            extra = tuple(sorted((kk, tuple(v.shape) if torch.is_tensor(v) else v) for kk, v in k.items()
+                                 if kk in ("a2", "residual", "geglu", "kv_div", "silu")))
+            recs.append((n, sig + extra, a, k))
+            return out
+        return w
+    for n in names:
+        setattr(ops, n, wrap(n, orig[n]))
+    try:
+        eng = pipe.denoising_unet.engine()
+        f = min(L, 16)
+        frames = host["lat"].cuda()[0, :, :f].permute(1, 0, 2, 3).repeat(2, 1, 1, 1).contiguous()
+        enc = host["audio"].cuda()[:, :f].reshape(2 * f, 5, 768)
+        kps = host["kps"].cuda()[:, :, :f].permute(0, 2, 3, 4, 1).reshape(2 * f * h * h, 320).contiguous()
+        eng.forward_frames(frames, 499, enc, kps, None, 2, f)
+        recs.clear()
+        eng.forward_frames(frames, 499, enc, kps, None, 2, f)
+        torch.cuda.synchronize()
+    finally:
+        for n in names:
+            setattr(ops, n, orig[n])
+    uniq, count = {}, {}
+    for n, sig, a, k in recs:
+        count[(n, sig)] = count.get((n, sig), 0) + 1
+        uniq.setdefault((n, sig), (a, k))
+    rows = []
+    for (n, sig), (a, k) in uniq.items():
+        k = {kk: v for kk, v in k.items() if kk != "out"}
+        orig[n](*a, **k)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(8):
+            orig[n](*a, **k)
+        e1.record()
+        torch.cuda.synchronize()
+        rows.append((e0.elapsed_time(e1) / 8 * count[(n, sig)], count[(n, sig)], n, sig))
+    tot = sum(r[0] for r in rows)
+    lines = [f"per-op table of one forward (isolated back-to-back timing): total {tot:.2f} ms"]
+    for t, c, n, sig in sorted(rows, reverse=True)[:70]:
+        lines.append(f"{t:8.3f} ms  n={c:3d}  avg={t / c * 1e3:8.1f} us  {n} {sig}")
+    byop = {}
+    for t, c, n, sig in rows:
+        byop[n] = byop.get(n, 0.0) + t
+    lines.append("by op: " + ", ".join(f"{k}={v:.2f}" for k, v in sorted(byop.items(), key=lambda kv: -kv[1])))
+    sys.stderr.write("\n".join(lines) + "\n")
+
+
 def kernel_roofline(pipe, host, L, h):
     """Time every launch of the dominant kernel (tcgen05 GEMM / implicit-GEMM conv) of ONE eager UNet forward with
     CUDA events on the launching stream; achieved = sum(2*M*N*K) / sum(duration)."""
@@ -384,6 +444,8 @@ def ours(args):
     if rank == 0:
         pk = peaks()
         roof_k = kernel_roofline(pipe, host, L, h) if n == 1 else None
+        if n == 1 and os.environ.get("VX_BENCH_OPS"):
+            op_table(pipe, host, L, h)
         fps = L * args.steps / sec
         e2e_fps = L * args.steps / e2e_wall
         windows = n

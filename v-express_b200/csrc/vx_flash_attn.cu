@@ -244,20 +244,39 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// v2: 256 query rows per CTA as two 128-row tiles, each owned by its own softmax warpgroup (ping-pong): while
-// warpgroup 0 runs exp2 on S0_j the tensor core computes S1_j / P1.V, and vice versa.  K/V tiles are loaded once
-// for both query tiles; the whole S row (128 fp32) is pulled from TMEM in one pass.  Used when hd <= 128,
-// Nq % 256 == 0 and Nk % 128 == 0 (the 64x64 and 32x32 levels, ~98 % of the attention FLOPs at 512^2).
-constexpr int kFa2Threads = 352;  // TMA warp, 2 MMA warps (one per query tile), 2 x 4 softmax warps
+// v2: 256 query rows per CTA as two 128-row tiles.  Measured on B200 (profiles/r01c_flash2_ncu_full.md and
+// profiles/tools/fa_ablation.py) the hd = 40 kernel is bound neither by the tensor pipe (19 % active) nor by HBM
+// but by the instruction stream of the softmax warps, so this version maximises softmax thread-level parallelism:
+//   * 16 softmax warps (4 per SM sub-partition): every 128x128 S tile is split into two 64-column halves owned by
+//     two warps of the same TMEM lane quadrant; they exchange the partial row maxima through shared memory;
+//   * one MMA-issuing warp per query tile; S(q, j+1) is issued as soon as S(q, j) sits in registers; P is double
+//     buffered so the softmax never waits for P.V (only the rare lazy O-rescale does);
+//   * half of the exponentials run on the FMA pipe (ex2_poly) to balance the MUFU unit.
+// Used when hd <= 128, Nq % 256 == 0 and Nk % 128 == 0 (the 64x64 and 32x32 levels, ~98 % of the attention FLOPs).
+constexpr int kFa2Threads = 608;  // warps 0..15 softmax, 16 TMA, 17/18 MMA (query tile 0/1)
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// 2^x on the FMA/ALU pipes (Cody-Waite split + degree-3 minimax polynomial, max rel. error 8e-5 -- far below the
+// bf16 rounding of P).
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -125.0f);
+  const float t = x + 12582912.0f;            // 1.5 * 2^23: the low mantissa bits of t hold round(x)
+  const float j = t - 12582912.0f;
+  const float r = x - j;                      // in [-0.5, 0.5]
+  float pl = fmaf(0.05519810691475868f, r, 0.24267712235450745f);
+  pl = fmaf(pl, r, 0.6932618021965027f);
+  pl = fmaf(pl, r, 0.9999227523803711f);
+  return __uint_as_float(__float_as_uint(pl) + (__float_as_uint(t) << 23));   // scale by 2^round(x)
+}
+__device__ __forceinline__ void wg_bar_sync(int q) { asm volatile("bar.sync %0, 256;" ::"r"(q + 1) : "memory"); }
 
 struct Fa2Args {
   int Nq, Nk, hd, hdp, kv_div, stages;
+  int pbufs;              // P tiles per query tile (2 when shared memory allows: softmax never waits for P.V)
   float scale_log2;
   __nv_bfloat16* out;
   long long ldo;
@@ -273,15 +292,16 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
   uint8_t* sQ = smem;                               // 2 x q_bytes
   uint8_t* sK = sQ + 2 * p.q_bytes;                 // stages x kv_bytes
   uint8_t* sV = sK + p.stages * p.kv_bytes;         // stages x kv_bytes
-  uint8_t* sP = sV + p.stages * p.kv_bytes;         // 2 x 32 KB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kP);
+  uint8_t* sP = sV + p.stages * p.kv_bytes;         // 2 query tiles x pbufs x 32 KB
+  float* xchg = reinterpret_cast<float*>(sP + 2 * p.pbufs * kP);  // 3 slots x [2 q][2 halves][128 rows]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(xchg + 3 * 512);
   uint64_t* q_full = bars;
   uint64_t* kv_full = bars + 1;             // [stages <= 3]
   uint64_t* kv_empty = kv_full + 3;         // [3]
   uint64_t* s_full = kv_empty + 3;          // [2]
   uint64_t* p_ready = s_full + 2;           // [2]
-  uint64_t* pv_done = p_ready + 2;          // [2]
-  uint64_t* o_full = pv_done + 2;           // [2]
+  uint64_t* pv_done = p_ready + 2;          // [2 query tiles][2 P buffers]
+  uint64_t* o_full = pv_done + 4;           // [2]
   uint64_t* s_free = o_full + 2;            // [2] S(q) has been pulled into registers -> may be overwritten
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 2);
 
@@ -301,14 +321,15 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&s_full[s], 1);
-      mbar_init(&p_ready[s], 128);
-      mbar_init(&pv_done[s], 1);
-      mbar_init(&s_free[s], 128);
+      mbar_init(&p_ready[s], 256);
+      mbar_init(&pv_done[2 * s], 1);
+      mbar_init(&pv_done[2 * s + 1], 1);
+      mbar_init(&s_free[s], 256);
       mbar_init(&o_full[s], 1);
     }
     fence_barrier_init();
   }
-  if (warp == 1) {
+  if (warp == 17) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
@@ -318,7 +339,7 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp == 16) {
     if (lane == 0) {
       tma_prefetch_desc(&mapQ);
       tma_prefetch_desc(&mapK);
@@ -341,15 +362,14 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
         }
       }
     }
-  } else if (warp == 1 || warp == 10) {
-    // one MMA-issuing warp per query tile: the two tiles advance independently (no cross-tile ordering), so the
-    // softmax warpgroups settle into anti-phase and keep the MUFU pipe busy
+  } else if (warp >= 17) {
+    // one MMA-issuing warp per query tile: the two tiles advance independently
     if (lane == 0) {
-      const int q = warp == 1 ? 0 : 1;
+      const int q = warp - 17;
       const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
       const uint32_t idesc_o = make_idesc_bf16(128, (uint32_t)p.hdp, 0, 1);
       const uint32_t q_addr = smem_u32(sQ + q * p.q_bytes);
-      const uint32_t p_addr = smem_u32(sP + q * kP);
+      const uint32_t p_base = smem_u32(sP + q * p.pbufs * kP);
       const uint32_t d_s = tmem_base + (uint32_t)(q * 128);
       const uint32_t d_o = tmem_base + 256u + (uint32_t)(q * 128);
       auto issue_s = [&](int j) {
@@ -376,65 +396,79 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
         const uint32_t v_addr = smem_u32(sV + stage * p.kv_bytes);
         mbar_wait(&p_ready[q], (uint32_t)(j & 1));
         tc_fence_after();
+        const int pb_i = j % p.pbufs;
+        const uint32_t p_addr = p_base + (uint32_t)(pb_i * kP);
         for (int k = 0; k < 8; ++k) {
           const uint64_t da = make_smem_desc(p_addr + k * 4096, 2048, 128, SWZ_NONE);
           const uint64_t db = make_smem_desc(v_addr + k * 256, 128, 2048, SWZ_NONE);
           umma_ss(d_o, da, db, idesc_o, (j | k) ? 1u : 0u);
         }
         umma_commit(&kv_empty[stage]);
-        umma_commit(&pv_done[q]);
+        umma_commit(&pv_done[2 * q + pb_i]);
       }
       umma_commit(&o_full[q]);
     }
   } else {
-    const int q = (warp - 2) >> 2;  // query tile / softmax warpgroup
+    // ------------------------------------------------------------ softmax: warp = (q, column half, lane quadrant)
+    const int q = warp >> 3;
+    const int half = (warp >> 2) & 1;
     const int qd = warp & 3;
     const int row = qd * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
-    const uint32_t ts = tmem_base + lane_addr + (uint32_t)(q * 128);
+    const uint32_t ts = tmem_base + lane_addr + (uint32_t)(q * 128 + half * 64);
     const uint32_t to = tmem_base + lane_addr + 256u + (uint32_t)(q * 128);
+    float* my_x = xchg + (q * 2 + half) * 128 + row;
+    const float* other_x = xchg + (q * 2 + (half ^ 1)) * 128 + row;
+    // O columns (16-wide chunks) this warp owns for the rescale and the epilogue
+    const int ochunks = p.hdp / 16;
+    const int oc_begin = half ? (ochunks + 1) / 2 : 0, oc_end = half ? ochunks : (ochunks + 1) / 2;
     float m_used = -INFINITY, l = 0.f;
     const float c = p.scale_log2;
-    uint8_t* pb = sP + q * kP + row * 16;
+    uint8_t* pb0 = sP + q * p.pbufs * kP + row * 16 + half * 8 * 2048;
     for (int j = 0; j < T; ++j) {
       mbar_wait(&s_full[q], (uint32_t)(j & 1));
       tc_fence_after();
-      uint32_t v[4][32];
+      uint32_t v[2][32];
       tmem_ld32(ts, v[0]);
       tmem_ld32(ts + 32, v[1]);
-      tmem_ld32(ts + 64, v[2]);
-      tmem_ld32(ts + 96, v[3]);
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(&s_free[q]);
-      // 8 independent max chains (the single softmax warp per SM sub-partition has no other ILP)
-      float mxs[8];
+      float mxs[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) mxs[i] = __uint_as_float(v[0][i]);
+      for (int i = 0; i < 4; ++i) mxs[i] = __uint_as_float(v[0][i]);
 #pragma unroll
-      for (int g = 0; g < 4; ++g)
+      for (int g = 0; g < 2; ++g)
 #pragma unroll
-        for (int i = 0; i < 32; ++i) mxs[i & 7] = fmaxf(mxs[i & 7], __uint_as_float(v[g][i]));
-      const float mx = fmaxf(fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3])),
-                             fmaxf(fmaxf(mxs[4], mxs[5]), fmaxf(mxs[6], mxs[7])));
-      if (j > 0) {
-        mbar_wait(&pv_done[q], (uint32_t)((j - 1) & 1));
+        for (int i = 0; i < 32; ++i) mxs[i & 3] = fmaxf(mxs[i & 3], __uint_as_float(v[g][i]));
+      float mx = fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3]));
+      // combine with the other column half of the same rows (double-buffered slot: one barrier per tile suffices)
+      my_x[(j & 1) * 512] = mx;
+      wg_bar_sync(q);
+      mx = fmaxf(mx, other_x[(j & 1) * 512]);
+      // the P buffer of this tile was last read by P.V of tile j - pbufs
+      uint8_t* pb = pb0 + (j % p.pbufs) * kP;
+      if (j >= p.pbufs) {
+        mbar_wait(&pv_done[2 * q + j % p.pbufs], (uint32_t)((j / p.pbufs - 1) & 1));
         tc_fence_after();
       }
       const float m_new = fmaxf(m_used, mx);
-      const bool need = (m_new - m_used) * c > 8.0f;
+      const bool need = (m_new - m_used) * c > 8.0f;  // identical in both warps of a pair (same rows, same maxima)
       if (__any_sync(0xffffffffu, need)) {
-        const float alpha = (m_used == -INFINITY) ? 0.f : exp2f((m_used - m_new) * c);
+        const float alpha = (m_used == -INFINITY) ? 0.f : ex2_approx((m_used - m_new) * c);
         l *= alpha;
         m_used = m_new;
         if (j > 0) {
-          for (int cb = 0; cb < p.hdp; cb += 16) {
+          // rescale O: needs P.V of tile j-1 complete (rare: only when the running max grew by > 2^8)
+          mbar_wait(&pv_done[2 * q + (j - 1) % p.pbufs], (uint32_t)(((j - 1) / p.pbufs) & 1));
+          tc_fence_after();
+          for (int oc = oc_begin; oc < oc_end; ++oc) {
             uint32_t o[16];
-            tmem_ld16(to + cb, o);
+            tmem_ld16(to + oc * 16, o);
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st16(to + cb, o);
+            tmem_st16(to + oc * 16, o);
           }
           tmem_st_wait();
         }
@@ -442,13 +476,14 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
       const float mc = m_used * c;
       float ls[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
+      for (int g = 0; g < 2; ++g) {
 #pragma unroll
         for (int h = 0; h < 4; ++h) {
           float e[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            e[i] = ex2_approx(fmaf(__uint_as_float(v[g][h * 8 + i]), c, -mc));
+            const float xx = fmaf(__uint_as_float(v[g][h * 8 + i]), c, -mc);
+            e[i] = (i & 1) ? ex2_poly(xx) : ex2_approx(xx);
             ls[i & 3] += e[i];
           }
           *reinterpret_cast<uint4*>(pb + (g * 4 + h) * 2048) =
@@ -460,12 +495,17 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
       tc_fence_before();
       mbar_arrive(&p_ready[q]);
     }
+    // total row sum = the two column halves
+    my_x[1024] = l;
+    wg_bar_sync(q);
+    l += other_x[1024];
     mbar_wait(&o_full[q], 0);
     tc_fence_after();
     const int qrow = q_pair * 256 + q * 128 + row;
     const float inv = 1.f / l;
     __nv_bfloat16* op = p.out + ((long long)bq * p.Nq + qrow) * p.ldo + head * p.hd;
-    for (int cb = 0; cb < p.hdp; cb += 16) {
+    for (int oc = oc_begin; oc < oc_end; ++oc) {
+      const int cb = oc * 16;
       uint32_t o[16];
       tmem_ld16(to + cb, o);
       tmem_ld_wait();
@@ -484,7 +524,7 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 17) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
@@ -578,9 +618,10 @@ extern "C" int vx_flash_attention(const void* q, long long ldq, const void* k, l
     a.q_bytes = 128 * hdp * 2;
     a.kv_bytes = 128 * hdp * 2;
     a.stages = 3;
-    auto need = [&](int st) { return (size_t)2 * a.q_bytes + (size_t)2 * st * a.kv_bytes + 2 * 32768 + 384 + 128; };
-    if (need(3) > 227 * 1024) a.stages = 2;
-    const size_t smem2 = need(a.stages);
+    auto need = [&](int st, int pb) { return (size_t)2 * a.q_bytes + (size_t)2 * st * a.kv_bytes + (size_t)2 * pb * 32768 + 6144 + 384 + 128; };
+    a.pbufs = (need(3, 2) <= 227 * 1024 && !getenv("VX_FA_PBUF1")) ? 2 : 1;
+    if (need(3, a.pbufs) > 227 * 1024) a.stages = 2;
+    const size_t smem2 = need(a.stages, a.pbufs);
     VX_REQUIRE(smem2 <= 227 * 1024, "vx_flash_attention: smem %zu too large (hd=%d)", smem2, hd);
     CUtensorMap mQ, mK, mV;
     const void* ptrs[3] = {q, k, v};
