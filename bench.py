@@ -167,13 +167,13 @@ class Clocks:
 
 
 # --------------------------------------------------------------------------------------------- kernel timing
-def op_table(pipe, host, L, h):
+def op_table(pipe, host, L, h, which="unet"):
     """VX_BENCH_OPS=1: per-op / per-shape device time of one UNet forward.  Every unique (op, shapes) call recorded
     during an eager forward is replayed 8x back-to-back and timed with CUDA events (so host launch overhead overlaps)."""
     from vexpress_b200 import ops
     recs = []
     names = ["gemm", "conv3x3", "flash_attention", "temporal_attention", "smallkv_attention", "groupnorm", "layernorm",
-             "conv_in", "conv_out", "im2col_s2", "upsample2x", "skinny_linear", "timestep_embed"]
+             "conv_in", "conv_out", "im2col_s2", "upsample2x", "skinny_linear", "timestep_embed", "softmax_rows"]
     orig = {n: getattr(ops, n) for n in names}
 
     def wrap(n, fn):
@@ -193,9 +193,14 @@ def op_table(pipe, host, L, h):
         frames = host["lat"].cuda()[0, :, :f].permute(1, 0, 2, 3).repeat(2, 1, 1, 1).contiguous()
         enc = host["audio"].cuda()[:, :f].reshape(2 * f, 5, 768)
         kps = host["kps"].cuda()[:, :, :f].permute(0, 2, 3, 4, 1).reshape(2 * f * h * h, 320).contiguous()
-        eng.forward_frames(frames, 499, enc, kps, None, 2, f)
+        if which == "vae":
+            z = host["lat"].cuda()[0].permute(1, 0, 2, 3)[:16].contiguous()
+            run = lambda: pipe.vae.decode_latents(z)
+        else:
+            run = lambda: eng.forward_frames(frames, 499, enc, kps, None, 2, f)
+        run()
         recs.clear()
-        eng.forward_frames(frames, 499, enc, kps, None, 2, f)
+        run()
         torch.cuda.synchronize()
     finally:
         for n in names:
@@ -217,7 +222,7 @@ def op_table(pipe, host, L, h):
         torch.cuda.synchronize()
         rows.append((e0.elapsed_time(e1) / 8 * count[(n, sig)], count[(n, sig)], n, sig))
     tot = sum(r[0] for r in rows)
-    lines = [f"per-op table of one forward (isolated back-to-back timing): total {tot:.2f} ms"]
+    lines = [f"per-op table of one {which} pass (isolated back-to-back timing): total {tot:.2f} ms"]
     for t, c, n, sig in sorted(rows, reverse=True)[:70]:
         lines.append(f"{t:8.3f} ms  n={c:3d}  avg={t / c * 1e3:8.1f} us  {n} {sig}")
     byop = {}
@@ -434,6 +439,15 @@ def ours(args):
     e1.record()
     torch.cuda.synchronize()
     unet_ms_per_step = e0.elapsed_time(e1) / steps_ddim
+    # VAE decode alone (device events)
+    lat_tmp = lat_dev.clone()
+    pipe_decode_device(pipe, lat_tmp, dist)
+    barrier()
+    e0.record()
+    pipe_decode_device(pipe, lat_tmp, dist)
+    e1.record()
+    torch.cuda.synchronize()
+    vae_ms = e0.elapsed_time(e1)
 
     for _ in range(max(1, min(args.warmup, 1))):
         e2e_pass()
@@ -445,7 +459,8 @@ def ours(args):
         pk = peaks()
         roof_k = kernel_roofline(pipe, host, L, h) if n == 1 else None
         if n == 1 and os.environ.get("VX_BENCH_OPS"):
-            op_table(pipe, host, L, h)
+            op_table(pipe, host, L, h, "unet")
+            op_table(pipe, host, L, h, "vae")
         fps = L * args.steps / sec
         e2e_fps = L * args.steps / e2e_wall
         windows = n
@@ -458,7 +473,7 @@ def ours(args):
                              h2d_bytes_per_step=int(sum(v.numel() * v.element_size() for v in host.values())),
                              d2h_bytes_per_step=int(L * 3 * 512 * 512 * 4)),
                     gpu_launches=int(launches_direct),
-                    unet_ms_per_step=unet_ms_per_step,
+                    unet_ms_per_step=unet_ms_per_step, vae_decode_ms=vae_ms,
                     whole_path=dict(tflop_per_pass=work_tflop, achieved_tflops=work_tflop * args.steps / sec / n,
                                     frac_of_sustained_peak=work_tflop * args.steps / sec / n / pk["tf_sustained"]))
         if roof_k:

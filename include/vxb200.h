@@ -96,6 +96,11 @@ int vx_conv_in(const void* in, long long sn, long long sc, int NB, int H, int W,
 int vx_conv_out(const void* x, long long ldx, int NB, int H, int W, int C, int Cout, const float* w,
                 const float* bias, void* out, long long sn, long long sc, int out_f32, int post, void* stream);
 
+/* ---- tail of the tensor-core conv_out path: x [NB*HW, ldx] bf16 (conv3x3 output with Cout zero-padded to 32)
+ * -> planar (n, co, y, x) with the optional image post-processing. */
+int vx_extract_planar(const void* x, long long ldx, int NB, int HW, int Cout, void* out, long long sn, long long sc,
+                      int out_f32, int post, void* stream);
+
 /* ---- im2col of the stride-2 Downsample3D conv (modules/resnet.py:93-120) and nearest-2x upsample of
  * Upsample3D (:53-82), NHWC. */
 int vx_im2col_s2(const void* x, int NB, int H, int W, int C, void* out, void* stream);

@@ -111,6 +111,12 @@ def test_pipeline_vs_reference_golden(golden_dir, use_graph):
     d = (video - g["video"].float()).abs()
     print(f"graph={use_graph} final latents rel {e_lat:.3e}; video mean abs {d.mean().item():.3e} max {d.max().item():.3e}")
     assert e_lat < 6e-2 and d.mean().item() < 1.5e-2
+    # a second call on the same pipeline object reuses the captured graph / persistent bank buffers
+    video2 = pipe(reference_image=None, kps_images=None, audio_waveform=None, width=g["h"] * 8, height=g["h"] * 8,
+                  video_length=g["L"], num_inference_steps=g["steps"], guidance_scale=g["guidance_scale"],
+                  context_frames=g["S"], context_overlap=g["O"], reference_attention_weight=0.95,
+                  audio_attention_weight=3.0)
+    assert torch.equal(video, video2)
 
 
 def test_pipeline_rejects_non_tiling_length(golden_dir):

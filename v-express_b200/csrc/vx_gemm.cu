@@ -26,7 +26,7 @@ namespace vx {
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
-constexpr int kThreads = 320;
+constexpr int kThreads = 352;   // + warp 10: TMA-store / residual-prefetch warp
 constexpr int kEpiThreads = 256;
 constexpr int kPanelCols = 32;                         // staging panel: 32 bf16 = 64 B rows, 64B swizzle
 constexpr int kPanelBytes = kBlockM * kPanelCols * 2;  // 8 KB
@@ -38,6 +38,7 @@ struct GemmArgs {
   int taps;        // 1 = plain GEMM, 9 = 3x3 conv
   int block_n;     // UMMA N (multiple of 32, <= 256)
   int stages;
+  int nbuf;        // staging tiles (2 when shared memory allows: TMA store/residual latency fully hidden)
   int rows_valid;  // output rows covered by one tile (128 for plain; wbox*hbox*nbox for conv)
   int W, H;        // conv image size
   int tiles_m, tiles_n;
@@ -63,7 +64,23 @@ __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.b
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-__device__ __forceinline__ float gelu_erf(float g) { return 0.5f * g * (1.f + erff(g * 0.70710678118654752f)); }
+// erf-GELU with erf from Abramowitz & Stegun 7.1.28 (|error| < 3e-7, i.e. exact at bf16 precision):
+// erf(x) = 1 - (1 + a1 x + ... + a6 x^6)^-16 for x >= 0.  ~13 FMA-pipe instructions + one MUFU.RCP instead of
+// libdevice erff (the GEGLU epilogue was erf-bound: 128 x 128 erf evaluations per tile).
+__device__ __forceinline__ float gelu_erf(float g) {
+  const float x = fabsf(g) * 0.70710678118654752f;
+  float pl = fmaf(x, 0.0000430638f, 0.0002765672f);
+  pl = fmaf(x, pl, 0.0001520143f);
+  pl = fmaf(x, pl, 0.0092705272f);
+  pl = fmaf(x, pl, 0.0422820123f);
+  pl = fmaf(x, pl, 0.0705230784f);
+  pl = fmaf(x, pl, 1.0f);
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(pl));
+  r *= r; r *= r; r *= r; r *= r;          // ^16
+  const float erf_abs = 1.0f - r;
+  return 0.5f * g * (1.0f + copysignf(erf_abs, g));
+}
 
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapA2,
@@ -78,12 +95,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   uint8_t* sC = smem + p.stages * stage_bytes;  // staging: (block_n or block_n/2)/32 panels of 8 KB
   const int out_cols = p.geglu ? p.block_n / 2 : p.block_n;
   const int npanels = out_cols / kPanelCols;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sC + (p.out_f32 ? 0 : npanels) * kPanelBytes);
+  const int buf_bytes = npanels * kPanelBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sC + (p.out_f32 ? 0 : p.nbuf * buf_bytes));
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tmem_full = empty_bar + p.stages;  // [2]
   uint64_t* tmem_empty = tmem_full + 2;        // [2]
-  uint64_t* res_full = tmem_empty + 2;         // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 1);
+  uint64_t* c_ready = tmem_empty + 2;          // [2] staging tile b free (+ residual landed)
+  uint64_t* staged = c_ready + 2;              // [2] staging tile b fully written by the epilogue warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(staged + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -103,8 +122,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
       mbar_init(&tmem_empty[s], kEpiThreads / 32);
+      mbar_init(&c_ready[s], 1);
+      mbar_init(&staged[s], kEpiThreads);
     }
-    mbar_init(res_full, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -188,23 +208,49 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         umma_commit(&tmem_full[as]);
       }
     }
-  } else {
+  } else if (warp == 10) {
+    // ------------------------------------------------------------ TMA store + residual prefetch (one lane)
+    if (lane == 0 && !p.out_f32) {
+      const uint32_t res_bytes = (uint32_t)(p.rows_valid * out_cols * 2);
+      auto arm = [&](int t, int b) {  // make staging tile b usable for output tile t
+        if (p.has_residual) {
+          const int tn_ = t % p.tiles_n, tm_ = t / p.tiles_n;
+          mbar_expect_tx(&c_ready[b], res_bytes);
+          for (int pn = 0; pn < npanels; ++pn)
+            tma_load_2d(sC + b * buf_bytes + pn * kPanelBytes, &mapR, &c_ready[b], tn_ * out_cols + pn * kPanelCols,
+                        tm_ * p.rows_valid);
+        } else {
+          mbar_arrive(&c_ready[b]);
+        }
+      };
+      for (int b = 0; b < p.nbuf; ++b)
+        if ((int)blockIdx.x + b * (int)gridDim.x < num_tiles) arm(blockIdx.x + b * gridDim.x, b);
+      int it = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+        const int b = it % p.nbuf;
+        const int tile_n = t % p.tiles_n, tile_m = t / p.tiles_n;
+        mbar_wait(&staged[b], (uint32_t)((it / p.nbuf) & 1));
+        for (int pn = 0; pn < npanels; ++pn)
+          tma_store_2d(&mapC, sC + b * buf_bytes + pn * kPanelBytes, tile_n * out_cols + pn * kPanelCols,
+                       tile_m * p.rows_valid);
+        tma_store_commit();
+        const int tnext = t + p.nbuf * gridDim.x;
+        if (tnext < num_tiles) {
+          tma_store_wait_read();  // the store has finished reading tile b
+          arm(tnext, b);
+        }
+      }
+      tma_store_wait_all();
+    }
+  } else if (warp < 10) {
     // ------------------------------------------------------------ epilogue (warps 2..9)
     const int ew = warp - 2;
     const int q = warp & 3;    // TMEM lane quadrant this warp may access
     const int half = ew >> 2;  // which half of the output chunks this warp drains
     const int row = q * 32 + lane;
-    const bool leader = threadIdx.x == 64;
     const int nchunks = out_cols / 16;
     const int c_begin = half ? (nchunks + 1) / 2 : 0;
     const int c_end = half ? nchunks : (nchunks + 1) / 2;
-    const uint32_t res_bytes = (uint32_t)(p.rows_valid * out_cols * 2);
-    if (leader && p.has_residual && (int)blockIdx.x < num_tiles) {
-      const int tile_n = blockIdx.x % p.tiles_n, tile_m = blockIdx.x / p.tiles_n;
-      mbar_expect_tx(res_full, res_bytes);
-      for (int pn = 0; pn < npanels; ++pn)
-        tma_load_2d(sC + pn * kPanelBytes, &mapR, res_full, tile_n * out_cols + pn * kPanelCols, tile_m * p.rows_valid);
-    }
     int it = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       const int tile_n = t % p.tiles_n, tile_m = t / p.tiles_n;
@@ -213,7 +259,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       const bool row_ok = row < p.rows_valid && m < p.M;
       mbar_wait(&tmem_full[as], (uint32_t)((it >> 1) & 1));
       tc_fence_after();
-      if (p.has_residual) mbar_wait(res_full, (uint32_t)(it & 1));
+      const int sb = it % p.nbuf;
+      if (!p.out_f32) mbar_wait(&c_ready[sb], (uint32_t)((it / p.nbuf) & 1));
       const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256);
       const int nbase = tile_n * p.block_n;  // accumulator column base (bias index)
       const float* b2 = p.bias2 ? p.bias2 + (row_ok ? (m / p.bias2_div) : 0) * (long long)p.N : nullptr;
@@ -226,12 +273,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
           tmem_ld16(tacc + (uint32_t)(out_cols + c * 16), g);
           tmem_ld_wait();
           const int nv = nbase + c * 16, ng = nbase + out_cols + c * 16;
+          float bv[16], bg[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float val = __uint_as_float(v[i]) + (p.bias ? p.bias[nv + i] : 0.f);
-            const float gate = __uint_as_float(g[i]) + (p.bias ? p.bias[ng + i] : 0.f);
-            f[i] = val * gelu_erf(gate);
+          for (int i = 0; i < 16; i += 4) {
+            const float4 t0 = p.bias ? *reinterpret_cast<const float4*>(p.bias + nv + i) : make_float4(0, 0, 0, 0);
+            const float4 t1 = p.bias ? *reinterpret_cast<const float4*>(p.bias + ng + i) : make_float4(0, 0, 0, 0);
+            bv[i] = t0.x; bv[i + 1] = t0.y; bv[i + 2] = t0.z; bv[i + 3] = t0.w;
+            bg[i] = t1.x; bg[i + 1] = t1.y; bg[i + 2] = t1.z; bg[i + 3] = t1.w;
           }
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            f[i] = (__uint_as_float(v[i]) + bv[i]) * gelu_erf(__uint_as_float(g[i]) + bg[i]);
         } else {
           tmem_ld_wait();
           const int n = nbase + c * 16;
@@ -269,7 +321,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         }
         // staging tile: panel (c/2), 16-byte chunks (c&1)*2 + {0,1} of the 64-byte row, 64B swizzle:
         // byte offset o = row*64 + chunk*16 is stored at o ^ (((o >> 7) & 3) << 4)
-        uint8_t* panel = sC + (c >> 1) * kPanelBytes;
+        uint8_t* panel = sC + sb * buf_bytes + (c >> 1) * kPanelBytes;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           uint32_t o = (uint32_t)(row * 64 + ((c & 1) * 2 + h) * 16);
@@ -294,26 +346,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[as]);
       if (!p.out_f32) {
-        fence_proxy_async_smem();
-        epi_bar_sync();
-        if (leader) {
-          for (int pn = 0; pn < npanels; ++pn)
-            tma_store_2d(&mapC, sC + pn * kPanelBytes, tile_n * out_cols + pn * kPanelCols, tile_m * p.rows_valid);
-          tma_store_commit();
-          tma_store_wait_read();  // staging tile may be overwritten again
-          const int tn = t + gridDim.x;
-          if (p.has_residual && tn < num_tiles) {
-            const int ntile_n = tn % p.tiles_n, ntile_m = tn / p.tiles_n;
-            mbar_expect_tx(res_full, res_bytes);
-            for (int pn = 0; pn < npanels; ++pn)
-              tma_load_2d(sC + pn * kPanelBytes, &mapR, res_full, ntile_n * out_cols + pn * kPanelCols,
-                          ntile_m * p.rows_valid);
-          }
-        }
-        epi_bar_sync();
+        fence_proxy_async_smem();     // staging writes -> visible to the TMA store (async proxy)
+        mbar_arrive(&staged[sb]);
       }
     }
-    if (leader && !p.out_f32) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
@@ -363,12 +399,18 @@ static int launch(const CUtensorMap& mA, const CUtensorMap& mA2, const CUtensorM
                   const CUtensorMap& mC, GemmArgs& a, cudaStream_t st) {
   const int stage_bytes = kBlockM * kBlockK * 2 + a.block_n * kBlockK * 2;
   const int out_cols = a.geglu ? a.block_n / 2 : a.block_n;
-  const int stage_c = a.out_f32 ? 0 : out_cols / kPanelCols * kPanelBytes;
-  int stages = env_int("VX_GEMM_STAGES", 0);
-  if (stages <= 0) stages = 6;
-  while (stages > 2 && (size_t)stages * stage_bytes + stage_c + 2048 > 227 * 1024) --stages;
+  const int buf_bytes = a.out_f32 ? 0 : out_cols / kPanelCols * kPanelBytes;
+  const int total_kb = a.taps * a.kblocks1 + a.kblocks2;
+  const size_t cap = 227 * 1024 - 2048;
+  // deep TMA rings only pay off for long K loops; short K loops need the second staging tile instead
+  int want_stages = env_int("VX_GEMM_STAGES", 0);
+  if (want_stages <= 0) want_stages = total_kb < 6 ? (total_kb < 3 ? 3 : total_kb) : 6;
+  int nbuf = (!a.out_f32 && (size_t)3 * stage_bytes + 2 * buf_bytes <= cap && !getenv("VX_GEMM_NBUF1")) ? 2 : 1;
+  int stages = want_stages;
+  while (stages > 2 && (size_t)stages * stage_bytes + (size_t)nbuf * buf_bytes > cap) --stages;
   a.stages = stages;
-  const size_t smem = (size_t)stages * stage_bytes + stage_c + 2048;
+  a.nbuf = nbuf;
+  const size_t smem = (size_t)stages * stage_bytes + (size_t)nbuf * buf_bytes + 2048;
   static bool configured = false;
   if (!configured) {
     VX_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

@@ -148,6 +148,37 @@ __global__ void conv_out_kernel(const ConvOutArgs p) {
   }
 }
 
+// ------------------------------------------------------------------ NHWC (first Cout <= 8 channels) -> planar
+// Tail of the tensor-core conv_out path: the 3x3 conv runs on the tcgen05 kernel with Cout zero-padded to 32;
+// this extracts the real channels into (n, co, y, x) planes (+ optional (v/2+0.5).clamp(0,1), fp32 or bf16).
+__global__ void extract_planar_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, long long npix, int HW,
+                                      int Cout, void* __restrict__ out, long long sn, long long sc, int out_f32,
+                                      int post) {
+  for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < npix;
+       pix += (long long)gridDim.x * blockDim.x) {
+    const uint4 u = *reinterpret_cast<const uint4*>(x + pix * ldx);
+    const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+    float f[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 t = unpack_bf16(w4[i]);
+      f[2 * i] = t.x;
+      f[2 * i + 1] = t.y;
+    }
+    const long long n = pix / HW, r = pix % HW;
+#pragma unroll
+    for (int co = 0; co < 8; ++co) {
+      if (co < Cout) {
+        float v = f[co];
+        if (post) v = fminf(fmaxf(v * 0.5f + 0.5f, 0.f), 1.f);
+        const long long off = n * sn + co * sc + r;
+        if (out_f32) reinterpret_cast<float*>(out)[off] = v;
+        else reinterpret_cast<__nv_bfloat16*>(out)[off] = __float2bfloat16(v);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------ im2col (3x3, stride 2, pad 1), NHWC
 __global__ void im2col_s2_kernel(const __nv_bfloat16* __restrict__ x, int NB, int H, int W, int C,
                                  __nv_bfloat16* __restrict__ out) {
@@ -325,6 +356,18 @@ extern "C" int vx_conv_out(const void* x, long long ldx, int NB, int H, int W, i
   ConvOutArgs a{(const __nv_bfloat16*)x, ldx, NB, H, W, C, Cout, w, bias, out, sn, sc, out_f32, post};
   const long long npix = (long long)NB * H * W;
   conv_out_kernel<<<(unsigned)((npix * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a);
+  VX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int vx_extract_planar(const void* x, long long ldx, int NB, int HW, int Cout, void* out, long long sn,
+                                 long long sc, int out_f32, int post, void* stream) {
+  VX_REQUIRE(Cout >= 1 && Cout <= 8 && ldx % 8 == 0, "vx_extract_planar: Cout=%d ldx=%lld", Cout, ldx);
+  const long long npix = (long long)NB * HW;
+  long long blocks = (npix + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  extract_planar_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, ldx, npix, HW, Cout,
+                                                                          out, sn, sc, out_f32, post);
   VX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -248,7 +248,7 @@ __global__ void geglu_kernel(const __nv_bfloat16* __restrict__ x, long long ldx,
     load8(x + r * ldx + c0, h);
     load8(x + r * ldx + inner + c0, g);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) h[i] *= 0.5f * g[i] * (1.f + erff(g[i] * 0.70710678118654752f));
+    for (int i = 0; i < 8; ++i) h[i] *= 0.5f * g[i] * (1.f + erff(g[i] * 0.70710678118654752f));  // stand-alone GEGLU (unfused path)
     store8(out + r * ldo + c0, h);
   }
 }

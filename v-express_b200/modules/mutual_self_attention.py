@@ -85,4 +85,4 @@ class ReferenceAttentionControl:
             for r in self._reader_blocks():
                 r.bank.clear()
             if self.unet._engine is not None:
-                self.unet._engine._bank_cache.clear()
+                self.unet._engine._bank_cache.clear()      # persistent K/V buffers (and graphs) are kept

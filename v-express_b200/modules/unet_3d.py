@@ -359,6 +359,9 @@ class UNetEngine:
         self.W: Dict[str, torch.Tensor] = {}
         self._pack(sd)
         self._bank_cache: Dict[str, tuple] = {}
+        self._bank_buf: Dict[str, torch.Tensor] = {}
+        self._bank_flag: Dict[str, bool] = {}
+        self.bank_epoch = 0
         self.order = attention_block_order(model)
 
     # ---------------------------------------------------------------- packing
@@ -383,7 +386,7 @@ class UNetEngine:
             if p in ("conv_in",):
                 W[k] = self._f32(v).reshape(v.shape[0], -1).t().contiguous()                 # fp32 [Cin*9, Cout]
             elif p == "conv_out":
-                W[k] = self._f32(v).permute(0, 2, 3, 1).reshape(v.shape[0], 9, v.shape[1]).contiguous()
+                W["conv_out.packed_w"], W["conv_out.packed_b"] = ops.pack_conv_out(self._bf(v), self._f32(sd[p + ".bias"]))
             elif p.endswith("time_emb_proj"):
                 self.temb_off[p] = (off, v.shape[0])
                 off += v.shape[0]
@@ -414,7 +417,8 @@ class UNetEngine:
     # ---------------------------------------------------------------- banks
     def _bank_kv(self, name: str, block: TemporalBasicTransformerBlock):
         """K/V of attn1_5 projected once per bank tensor (the reference re-projects f x steps x windows times,
-        modules/mutual_self_attention.py:205-219)."""
+        modules/mutual_self_attention.py:205-219).  The projected buffer is persistent per block and refreshed in
+        place when the bank changes, so CUDA graphs that captured its address stay valid across videos."""
         if not block.bank:
             raise RuntimeError(f"{name}: reference bank is empty -- call ReferenceAttentionControl.update() first")
         bank = block.bank[0]
@@ -423,12 +427,25 @@ class UNetEngine:
         if hit is not None and hit[0] == key:
             return hit[1]
         bflat = bank.to(device=self.dev, dtype=BF16).reshape(-1, bank.shape[-1]).contiguous()
-        kv = ops.gemm(bflat, self.W[name + ".attn1_5.kv"])
+        w = self.W[name + ".attn1_5.kv"]
+        buf = self._bank_buf.get(name)
+        if buf is None or buf.shape != (bflat.shape[0], w.shape[0]):
+            buf = torch.empty((bflat.shape[0], w.shape[0]), device=self.dev, dtype=BF16)
+            self._bank_buf[name] = buf
+            self.bank_epoch += 1
+        ops.gemm(bflat, w, out=buf)
         # CFG: the uncond half of the bank is all zeros (reference mutual_self_attention.py:359) -> K = V = 0 ->
         # softmax-uniform x 0: the attention output of those frames is exactly 0, so it is not computed
         uncond_zero = bool(bank.shape[0] == 2 and torch.count_nonzero(bank[0]).item() == 0)
-        self._bank_cache[name] = (key, (kv, uncond_zero))
-        return kv, uncond_zero
+        if self._bank_flag.get(name) != uncond_zero:
+            self._bank_flag[name] = uncond_zero
+            self.bank_epoch += 1
+        self._bank_cache[name] = (key, (buf, uncond_zero))
+        return buf, uncond_zero
+
+    def graph_signature(self):
+        """Changes whenever a CUDA graph captured from forward_frames would be stale."""
+        return (id(self), self.bank_epoch)
 
     # ---------------------------------------------------------------- blocks
     def _resnet(self, p, x, x2, NB, H, Wd, temb):
@@ -585,5 +602,5 @@ class UNetEngine:
                 tap(f"{p}.upsamplers.0", x, h_, w_)
         x = ops.groupnorm(x, NB, h_ * w_, W["conv_norm_out.weight"], W["conv_norm_out.bias"], self.eps, True, groups=self.groups)
         out = torch.empty((NB, self.model.config["out_channels"], H, Wd), device=self.dev, dtype=BF16)
-        ops.conv_out(x, NB, H, Wd, W["conv_out.weight"], W["conv_out.bias"], out)
+        ops.conv_out_tc(x, NB, H, Wd, W["conv_out.packed_w"], W["conv_out.packed_b"], out)
         return out

@@ -147,7 +147,9 @@ class VaeDecoderEngine:
             elif p == "decoder.conv_in":
                 self.W[k] = v.to(device=dev, dtype=BF16).float().reshape(v.shape[0], -1).t().contiguous()
             elif p == "decoder.conv_out":
-                self.W[k] = v.to(device=dev, dtype=BF16).float().permute(0, 2, 3, 1).reshape(v.shape[0], 9, v.shape[1]).contiguous()
+                bias = model.state_dict()[p + ".bias"].detach().to(device=dev, dtype=BF16).float()
+                self.W["conv_out.packed_w"], self.W["conv_out.packed_b"] = ops.pack_conv_out(
+                    v.to(device=dev, dtype=BF16), bias)
             elif p == "post_quant_conv":
                 self.W[k] = v.to(device=dev, dtype=BF16).float().reshape(v.shape[0], v.shape[1]).contiguous()
             elif v.dim() == 4 and v.shape[-1] == 3:
@@ -210,5 +212,5 @@ class VaeDecoderEngine:
                                 W[f"{d}.up_blocks.{i}.upsamplers.0.conv.bias"])
         x = ops.groupnorm(x, NB, H * Wd, W[d + ".conv_norm_out.weight"], W[d + ".conv_norm_out.bias"], 1e-6, True)
         out = torch.empty((NB, self.model.config["out_channels"], H, Wd), device=self.dev, dtype=out_dtype)
-        ops.conv_out(x, NB, H, Wd, W[d + ".conv_out.weight"], W[d + ".conv_out.bias"], out, post=post)
+        ops.conv_out_tc(x, NB, H, Wd, W["conv_out.packed_w"], W["conv_out.packed_b"], out, post=post)
         return out

@@ -282,3 +282,24 @@ def softmax_rows(x, out=None):
     check(_ffi.lib().vx_softmax_rows(ptr(x), c_ll(x.stride(0)), c_ll(rows), c_int(n), ptr(out), c_ll(out.stride(0)),
                                      stream_ptr()), "vx_softmax_rows")
     return out
+
+
+def pack_conv_out(w, bias, pad_to=32):
+    """(Cout<=8, Cin, 3, 3) conv weight -> zero-padded [pad_to, 9*Cin] bf16 + fp32 bias[pad_to] for the tcgen05 conv."""
+    co = w.shape[0]
+    wp = torch.zeros((pad_to,) + tuple(w.shape[1:]), device=w.device, dtype=BF16)
+    wp[:co] = w.to(BF16)
+    bp = torch.zeros(pad_to, device=w.device, dtype=torch.float32)
+    bp[:co] = bias.float()
+    return pack_conv3x3_weight(wp), bp
+
+
+def conv_out_tc(x, NB, H, W, w_packed, b_packed, out, post=False):
+    """conv_out on the tensor-core conv kernel: x NHWC [NB*H*W, C]; out planar (n, co, h, w) bf16/fp32."""
+    tmp = conv3x3(x.view(NB, H, W, -1), w_packed, b_packed)
+    assert out.stride(3) == 1 and out.stride(2) == W
+    check(_ffi.lib().vx_extract_planar(ptr(tmp), c_ll(tmp.stride(0)), c_int(NB), c_int(H * W), c_int(out.shape[1]),
+                                       ptr(out), c_ll(out.stride(0)), c_ll(out.stride(1)),
+                                       c_int(int(out.dtype == torch.float32)), c_int(int(post)), stream_ptr()),
+          "vx_extract_planar")
+    return out

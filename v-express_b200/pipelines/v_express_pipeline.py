@@ -60,24 +60,30 @@ class _GraphedUNet:
         self.enc = torch.zeros((b * f, enc_tokens, cross_dim), device=dev, dtype=BF16)
         self.kps_idx = torch.zeros((b * f,), device=dev, dtype=torch.int32)
         self.temb = None
-        self.kps = None
+        self.kps = None          # static copy of the channels-last kps features (address baked into the graph)
         self.graph = None
         self.out = None
         self.use_graph = use_graph
+        self.kps_token = None
 
     def _run(self):
         return self.engine.forward_frames(self.frames, None, self.enc, self.kps, self.kps_idx, self.b, self.f,
                                           temb=self.temb)
 
-    def __call__(self, temb, kps):
+    def set_kps(self, kps):
+        """Per video: (re)load the resident channels-last kps features; same shape keeps the captured graph."""
+        if self.kps is None or self.kps.shape != kps.shape:
+            self.kps = torch.empty_like(kps)
+            self.graph = None
+        self.kps.copy_(kps)
+
+    def __call__(self, temb):
         if self.temb is None:
             self.temb = torch.empty_like(temb)
         self.temb.copy_(temb)
         if not self.use_graph:
-            self.kps = kps
             return self._run()
-        if self.graph is None or self.kps is not kps:
-            self.kps = kps
+        if self.graph is None:
             # warm-up on a side stream (allocator + lazy module state), then capture
             s = torch.cuda.Stream()
             s.wait_stream(torch.cuda.current_stream())
@@ -218,16 +224,21 @@ class VExpressPipeline:
         win_dev = [torch.tensor(wn, device=dev, dtype=torch.int32) for wn in windows]
         win_long = [t.long() for t in win_dev]
         lat = latents[0]                                                        # (4, L, h, w) view
-        graphs = {}
+        # refresh the projected reference banks (outside any capture) and reuse graphs across calls while valid
+        for name in eng.order:
+            eng._bank_kv(name, unet.get_submodule(name))
+        graphs = self._graphs
         for i, t in enumerate(timesteps):
             temb = eng.time_embedding(int(t))
             acc.zero_()
             for wi in mine:
                 window = windows[wi]
                 f = len(window)
-                key = (b, f, h, w)
+                key = (b, f, h, w, T, bool(self.use_cuda_graph), eng.graph_signature())
                 g = graphs.get(key)
                 if g is None:
+                    for k_old in [k for k in graphs if k[:4] == key[:4] and k != key]:
+                        del graphs[k_old]                                       # stale capture of the same shape
                     g = graphs[key] = _GraphedUNet(eng, b, f, h, w, T, audio.shape[-1], self.use_cuda_graph)
                 x = lat[:, win_long[wi]].permute(1, 0, 2, 3)                    # (f,4,h,w)
                 g.frames[:f].copy_(x)
@@ -236,7 +247,10 @@ class VExpressPipeline:
                 g.enc.copy_(audio[:, win_long[wi]].reshape(b * f, T, -1))
                 for bi in range(b):
                     g.kps_idx[bi * f:(bi + 1) * f].copy_(win_dev[wi] + bi * L)
-                noise = g(temb, kps_nhwc)                                       # ((b f),4,h,w) bf16
+                if g.kps_token is not kps_nhwc:
+                    g.set_kps(kps_nhwc)
+                    g.kps_token = kps_nhwc
+                noise = g(temb)                                                 # ((b f),4,h,w) bf16
                 ops.cfg_overlap_accumulate(noise, f, hw, L, do_cfg, win_dev[wi], count_dev, float(guidance_scale), acc)
             if world > 1:
                 torch.distributed.all_reduce(acc, op=torch.distributed.ReduceOp.SUM)
