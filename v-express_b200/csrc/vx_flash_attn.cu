@@ -281,7 +281,10 @@ struct Fa2Args {
   __nv_bfloat16* out;
   long long ldo;
   int q_bytes, kv_bytes;  // per 128-row tile
+  long long* trace;       // bring-up only (VX_FA_TRACE): clock64 stamps of CTA (0,0,0)
 };
+
+#define FA_TR(slot) do { if (tr) tr[(j) * 16 + (slot)] = clock64(); } while (0)
 
 __global__ void __launch_bounds__(kFa2Threads, 1)
 flash_attn2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
@@ -363,51 +366,62 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
       }
     }
   } else if (warp >= 17) {
-    // one MMA-issuing warp per query tile: the two tiles advance independently
-    if (lane == 0) {
-      const int q = warp - 17;
-      const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
-      const uint32_t idesc_o = make_idesc_bf16(128, (uint32_t)p.hdp, 0, 1);
-      const uint32_t q_addr = smem_u32(sQ + q * p.q_bytes);
-      const uint32_t p_base = smem_u32(sP + q * p.pbufs * kP);
-      const uint32_t d_s = tmem_base + (uint32_t)(q * 128);
-      const uint32_t d_o = tmem_base + 256u + (uint32_t)(q * 128);
-      auto issue_s = [&](int j) {
-        const uint32_t k_addr = smem_u32(sK + (j % p.stages) * p.kv_bytes);
-        for (int k = 0; k < p.hdp / 16; ++k) {
-          const uint64_t da = make_smem_desc(q_addr + k * 4096, 2048, 128, SWZ_NONE);
-          const uint64_t db = make_smem_desc(k_addr + k * 4096, 2048, 128, SWZ_NONE);
-          umma_ss(d_s, da, db, idesc_s, k ? 1u : 0u);
-        }
+    // one MMA-issuing warp per query tile: the two tiles advance independently.  The whole warp runs the loop so
+    // that all descriptor / barrier values stay warp-uniform; only the elected lane issues (a divergent
+    // `if (lane == 0)` region costs an ELECT + R2UR.BROADCAST loop per UTCHMMA: measured ~150 cycles per MMA,
+    // 4700 instead of ~2000 cycles per KV iteration).
+    const bool leader = elect_one();
+    const int q = warp - 17;
+    const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+    const uint32_t idesc_o = make_idesc_bf16(128, (uint32_t)p.hdp, 0, 1);
+    const uint64_t dq = make_smem_desc(smem_u32(sQ + q * p.q_bytes), 2048, 128, SWZ_NONE);
+    const uint32_t p_base = smem_u32(sP + q * p.pbufs * kP);
+    const uint32_t d_s = tmem_base + (uint32_t)(q * 128);
+    const uint32_t d_o = tmem_base + 256u + (uint32_t)(q * 128);
+    const int ksteps = p.hdp / 16;
+    long long* tr = (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && q == 0 && leader) ? p.trace : nullptr;
+    auto issue_s = [&](int j) {
+      const uint64_t dk = make_smem_desc(smem_u32(sK + (j % p.stages) * p.kv_bytes), 2048, 128, SWZ_NONE);
+      if (leader) {
+        for (int k = 0; k < ksteps; ++k)   // +4096 bytes per K step = +256 in the (addr >> 4) field
+          umma_ss(d_s, dq + (uint64_t)(k * 256), dk + (uint64_t)(k * 256), idesc_s, k ? 1u : 0u);
         umma_commit(&s_full[q]);
-      };
-      mbar_wait(q_full, 0);
-      mbar_wait(&kv_full[0], 0);
-      tc_fence_after();
-      issue_s(0);
-      for (int j = 0; j < T; ++j) {
-        if (j + 1 < T) {
-          mbar_wait(&kv_full[(j + 1) % p.stages], (uint32_t)(((j + 1) / p.stages) & 1));
-          mbar_wait(&s_free[q], (uint32_t)(j & 1));   // S(q, j) is in registers -> overwrite it with S(q, j+1)
-          tc_fence_after();
-          issue_s(j + 1);
-        }
-        const int stage = j % p.stages;
-        const uint32_t v_addr = smem_u32(sV + stage * p.kv_bytes);
-        mbar_wait(&p_ready[q], (uint32_t)(j & 1));
+      }
+      __syncwarp();
+    };
+    mbar_wait(q_full, 0);
+    mbar_wait(&kv_full[0], 0);
+    tc_fence_after();
+    issue_s(0);
+    for (int j = 0; j < T; ++j) {
+      if (j + 1 < T) {
+        mbar_wait(&kv_full[(j + 1) % p.stages], (uint32_t)(((j + 1) / p.stages) & 1));
+        FA_TR(8);
+        mbar_wait(&s_free[q], (uint32_t)(j & 1));   // S(q, j) is in registers -> overwrite it with S(q, j+1)
         tc_fence_after();
-        const int pb_i = j % p.pbufs;
-        const uint32_t p_addr = p_base + (uint32_t)(pb_i * kP);
-        for (int k = 0; k < 8; ++k) {
-          const uint64_t da = make_smem_desc(p_addr + k * 4096, 2048, 128, SWZ_NONE);
-          const uint64_t db = make_smem_desc(v_addr + k * 256, 128, 2048, SWZ_NONE);
-          umma_ss(d_o, da, db, idesc_o, (j | k) ? 1u : 0u);
-        }
+        FA_TR(9);
+        issue_s(j + 1);
+        FA_TR(10);
+      }
+      const int stage = j % p.stages;
+      mbar_wait(&p_ready[q], (uint32_t)(j & 1));
+      tc_fence_after();
+      FA_TR(11);
+      const int pb_i = j % p.pbufs;
+      const uint64_t dp = make_smem_desc(p_base + (uint32_t)(pb_i * kP), 2048, 128, SWZ_NONE);
+      const uint64_t dv = make_smem_desc(smem_u32(sV + stage * p.kv_bytes), 128, 2048, SWZ_NONE);
+      if (leader) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)   // P: +4096 B (= +256) per 16 keys; V: +256 B (= +16) per 16 keys
+          umma_ss(d_o, dp + (uint64_t)(k * 256), dv + (uint64_t)(k * 16), idesc_o, (j | k) ? 1u : 0u);
         umma_commit(&kv_empty[stage]);
         umma_commit(&pv_done[2 * q + pb_i]);
       }
-      umma_commit(&o_full[q]);
+      __syncwarp();
+      FA_TR(12);
     }
+    if (leader) umma_commit(&o_full[q]);
+    __syncwarp();
   } else {
     // ------------------------------------------------------------ softmax: warp = (q, column half, lane quadrant)
     const int q = warp >> 3;
@@ -425,13 +439,16 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
     float m_used = -INFINITY, l = 0.f;
     const float c = p.scale_log2;
     uint8_t* pb0 = sP + q * p.pbufs * kP + row * 16 + half * 8 * 2048;
+    long long* tr = (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && warp == 0 && lane == 0) ? p.trace : nullptr;
     for (int j = 0; j < T; ++j) {
       mbar_wait(&s_full[q], (uint32_t)(j & 1));
       tc_fence_after();
+      FA_TR(0);
       uint32_t v[2][32];
       tmem_ld32(ts, v[0]);
       tmem_ld32(ts + 32, v[1]);
       tmem_ld_wait();
+      FA_TR(1);
       tc_fence_before();
       mbar_arrive(&s_free[q]);
       float mxs[4];
@@ -446,12 +463,14 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
       my_x[(j & 1) * 512] = mx;
       wg_bar_sync(q);
       mx = fmaxf(mx, other_x[(j & 1) * 512]);
+      FA_TR(2);
       // the P buffer of this tile was last read by P.V of tile j - pbufs
       uint8_t* pb = pb0 + (j % p.pbufs) * kP;
       if (j >= p.pbufs) {
         mbar_wait(&pv_done[2 * q + j % p.pbufs], (uint32_t)((j / p.pbufs - 1) & 1));
         tc_fence_after();
       }
+      FA_TR(3);
       const float m_new = fmaxf(m_used, mx);
       const bool need = (m_new - m_used) * c > 8.0f;  // identical in both warps of a pair (same rows, same maxima)
       if (__any_sync(0xffffffffu, need)) {
@@ -491,9 +510,11 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
         }
       }
       l += (ls[0] + ls[1]) + (ls[2] + ls[3]);
+      FA_TR(4);
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(&p_ready[q]);
+      FA_TR(5);
     }
     // total row sum = the two column halves
     my_x[1024] = l;
@@ -618,6 +639,7 @@ extern "C" int vx_flash_attention(const void* q, long long ldq, const void* k, l
     a.q_bytes = 128 * hdp * 2;
     a.kv_bytes = 128 * hdp * 2;
     a.stages = 3;
+    a.trace = getenv("VX_FA_TRACE") ? (long long*)strtoull(getenv("VX_FA_TRACE"), nullptr, 10) : nullptr;
     auto need = [&](int st, int pb) { return (size_t)2 * a.q_bytes + (size_t)2 * st * a.kv_bytes + (size_t)2 * pb * 32768 + 6144 + 384 + 128; };
     a.pbufs = (need(3, 2) <= 227 * 1024 && !getenv("VX_FA_PBUF1")) ? 2 : 1;
     if (need(3, a.pbufs) > 227 * 1024) a.stages = 2;

@@ -138,30 +138,34 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int tile_n = t % p.tiles_n, tile_m = t / p.tiles_n;
-        int n0 = 0, y0 = 0, x0 = 0;
-        const long long m0 = (long long)tile_m * p.rows_valid;
-        if (p.taps == 9) {
-          const long long hw = (long long)p.H * p.W;
-          n0 = (int)(m0 / hw);
-          const int rem = (int)(m0 % hw);
-          y0 = rem / p.W;
-          x0 = rem % p.W;
-        }
-        const uint32_t tx_bytes = (uint32_t)(p.rows_valid * kBlockK * 2 + b_bytes);
-        for (int kb = 0; kb < total_kb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * stage_bytes;
-          uint8_t* sb = sa + a_bytes;
+    // The whole warp runs the loop in lock-step so that tile / coordinate / barrier values stay warp-uniform (they live
+    // in uniform registers); only the elected lane issues.  A divergent `if (lane == 0)` region makes the compiler wrap
+    // every UTMALDG / UTCHMMA in an ELECT + R2UR.BROADCAST loop (~100 cycles per instruction, measured).
+    const bool leader = elect_one();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int tile_n = t % p.tiles_n, tile_m = t / p.tiles_n;
+      int n0 = 0, y0 = 0, x0 = 0;
+      const long long m0 = (long long)tile_m * p.rows_valid;
+      if (p.taps == 9) {
+        const long long hw = (long long)p.H * p.W;
+        n0 = (int)(m0 / hw);
+        const int rem = (int)(m0 % hw);
+        y0 = rem / p.W;
+        x0 = rem % p.W;
+      }
+      const uint32_t tx_bytes = (uint32_t)(p.rows_valid * kBlockK * 2 + b_bytes);
+      for (int kb = 0; kb < total_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * stage_bytes;
+        uint8_t* sb = sa + a_bytes;
+        const int tap = p.taps == 9 ? kb / p.kblocks1 : 0;
+        const int cb = kb - tap * p.kblocks1;
+        const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+        if (leader) {
           mbar_expect_tx(&full_bar[stage], tx_bytes);
           if (p.taps == 9) {
-            const int tap = kb / p.kblocks1;
-            const int cb = kb - tap * p.kblocks1;
-            const int dy = tap / 3 - 1, dx = tap % 3 - 1;
             tma_load_4d(sa, &mapA, &full_bar[stage], cb * kBlockK, x0 + dx, y0 + dy, n0);
           } else if (kb < p.kblocks1) {
             tma_load_2d(sa, &mapA, &full_bar[stage], kb * kBlockK, (int)m0);
@@ -169,48 +173,51 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             tma_load_2d(sa, &mapA2, &full_bar[stage], (kb - p.kblocks1) * kBlockK, (int)m0);
           }
           tma_load_2d(sb, &mapB, &full_bar[stage], kb * kBlockK, tile_n * p.block_n);
-          if (++stage == p.stages) {
-            stage = 0;
-            phase ^= 1;
-          }
+        }
+        __syncwarp();
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1;
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(kBlockM, (uint32_t)p.block_n, 0, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-        const int as = it & 1;
-        mbar_wait(&tmem_empty[as], (uint32_t)(((it >> 1) & 1) ^ 1));
+    // ------------------------------------------------------------ MMA issuer (warp-uniform loop, elected lane issues)
+    const bool leader = elect_one();
+    const uint32_t idesc = make_idesc_bf16(kBlockM, (uint32_t)p.block_n, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int as = it & 1;
+      mbar_wait(&tmem_empty[as], (uint32_t)(((it >> 1) & 1) ^ 1));
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(as * 256);
+      for (int kb = 0; kb < total_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(as * 256);
-        for (int kb = 0; kb < total_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * stage_bytes);
-          const uint32_t sb = sa + a_bytes;
+        const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+        const uint32_t sb = sa + a_bytes;
+        const uint64_t da = make_smem_desc(sa, 16, 1024, SWZ_128B);
+        const uint64_t db = make_smem_desc(sb, 16, 1024, SWZ_128B);
+        if (leader) {
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            const uint64_t da = make_smem_desc(sa + k * 32, 16, 1024, SWZ_128B);
-            const uint64_t db = make_smem_desc(sb + k * 32, 16, 1024, SWZ_128B);
-            umma_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
-          }
+          for (int k = 0; k < kBlockK / 16; ++k)   // +32 bytes per K step = +2 in the (addr >> 4) field
+            umma_ss(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
           umma_commit(&empty_bar[stage]);
-          if (++stage == p.stages) {
-            stage = 0;
-            phase ^= 1;
-          }
         }
-        umma_commit(&tmem_full[as]);
+        __syncwarp();
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1;
+        }
       }
+      if (leader) umma_commit(&tmem_full[as]);
+      __syncwarp();
     }
   } else if (warp == 10) {
     // ------------------------------------------------------------ TMA store + residual prefetch (one lane)
-    if (lane == 0 && !p.out_f32) {
+    if (lane == 0 && !p.out_f32) {   // few TMA ops per tile: the single-lane form is good enough here
       const uint32_t res_bytes = (uint32_t)(p.rows_valid * out_cols * 2);
       auto arm = [&](int t, int b) {  // make staging tile b usable for output tile t
         if (p.has_residual) {
