@@ -124,6 +124,8 @@ int vx_ddim_step(void* latents, const float* acc, long long n, float sqrt_a, flo
 int vx_probe_umma(const void* a_img, int a_bytes, const void* b_img, int b_bytes, unsigned lboA, unsigned sboA,
                   unsigned layA, unsigned lboB, unsigned sboB, unsigned layB, int a_mn, int b_mn, int N, int ksteps,
                   int a_step, int b_step, float* out, void* stream);
+int vx_probe_umma_ts(const void* a_packed, int K, const void* b_img, int b_bytes, unsigned lboB, unsigned sboB,
+                     unsigned layB, int b_mn, int N, int b_step, float* out, void* stream);
 int vx_probe_tma(const void* base, int rank, const unsigned long long* dims, const unsigned long long* strides_bytes,
                  const unsigned* box, int swizzle, const int* coords, int nbytes, void* out, void* stream);
 

@@ -64,3 +64,20 @@ def test_umma_mnmajor_b_noswizzle(ops):
         results[name] = (d - ref).abs().max().item()
     print("mn-major B hypotheses:", results)
     assert results["lbo=128,sbo=keys*16"] < 1e-2, results
+
+
+def test_umma_a_from_tmem(ops):
+    """TS-MMA: A = P [128 queries, keys] in tensor memory (lane = row, 32-bit column = two K-adjacent bf16, low half
+    = even k), B = V [keys, hd] staged [hd/8][keys][8] (MN-major, no swizzle): the P.V product with P kept in TMEM."""
+    g = torch.Generator(device="cuda").manual_seed(4)
+    keys, hd = 128, 48
+    p = torch.randn(128, keys, device="cuda", generator=g).bfloat16()
+    v = torch.randn(keys, hd, device="cuda", generator=g).bfloat16()
+    ref = p.float() @ v.float()
+    a_packed = p.contiguous().view(torch.int32).contiguous()              # [128, keys/2]: (k even | k odd << 16)
+    v_img = v.reshape(keys, hd // 8, 8).permute(1, 0, 2).contiguous()
+    d = ops.probe_umma_ts(a_packed, keys, _bytes(v_img), 128, keys * 16, 0, 1, hd, 16 * 16)
+    torch.cuda.synchronize()
+    err = (d - ref).abs().max().item()
+    print("TS-MMA (A in TMEM) max err", err)
+    assert err < 2e-2

@@ -276,7 +276,8 @@ __device__ __forceinline__ void wg_bar_sync(int q) { asm volatile("bar.sync %0, 
 
 struct Fa2Args {
   int Nq, Nk, hd, hdp, kv_div, stages;
-  int pbufs;              // P tiles per query tile (2 when shared memory allows: softmax never waits for P.V)
+  int pbufs;              // P tiles per query tile in shared memory (smem-P path)
+  int p_tmem;             // 1: P lives in tensor memory and P.V is a TS-MMA (hd <= 64): no smem traffic for P
   float scale_log2;
   __nv_bfloat16* out;
   long long ldo;
@@ -296,12 +297,12 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
   uint8_t* sK = sQ + 2 * p.q_bytes;                 // stages x kv_bytes
   uint8_t* sV = sK + p.stages * p.kv_bytes;         // stages x kv_bytes
   uint8_t* sP = sV + p.stages * p.kv_bytes;         // 2 query tiles x pbufs x 32 KB
-  float* xchg = reinterpret_cast<float*>(sP + 2 * p.pbufs * kP);  // 3 slots x [2 q][2 halves][128 rows]
+  float* xchg = reinterpret_cast<float*>(sP + (p.p_tmem ? 0 : 2 * p.pbufs * kP));  // 3 slots x [2 q][2 halves][128 rows]
   uint64_t* bars = reinterpret_cast<uint64_t*>(xchg + 3 * 512);
   uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;             // [stages <= 3]
-  uint64_t* kv_empty = kv_full + 3;         // [3]
-  uint64_t* s_full = kv_empty + 3;          // [2]
+  uint64_t* kv_full = bars + 1;             // [stages <= 6]
+  uint64_t* kv_empty = kv_full + 6;         // [6]
+  uint64_t* s_full = kv_empty + 6;          // [2]
   uint64_t* p_ready = s_full + 2;           // [2]
   uint64_t* pv_done = p_ready + 2;          // [2 query tiles][2 P buffers]
   uint64_t* o_full = pv_done + 4;           // [2]
@@ -318,7 +319,7 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
   }
   if (threadIdx.x == 0) {
     mbar_init(q_full, 1);
-    for (int s = 0; s < 3; ++s) {
+    for (int s = 0; s < 6; ++s) {
       mbar_init(&kv_full[s], 1);
       mbar_init(&kv_empty[s], 2);
     }
@@ -377,7 +378,8 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
     const uint64_t dq = make_smem_desc(smem_u32(sQ + q * p.q_bytes), 2048, 128, SWZ_NONE);
     const uint32_t p_base = smem_u32(sP + q * p.pbufs * kP);
     const uint32_t d_s = tmem_base + (uint32_t)(q * 128);
-    const uint32_t d_o = tmem_base + 256u + (uint32_t)(q * 128);
+    const uint32_t d_o = tmem_base + 256u + (uint32_t)(q * (p.p_tmem ? 64 : 128));
+    const uint32_t t_p = tmem_base + 384u + (uint32_t)(q * 64);   // P tile in TMEM (p_tmem mode): 64 packed columns
     const int ksteps = p.hdp / 16;
     long long* tr = (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && q == 0 && leader) ? p.trace : nullptr;
     auto issue_s = [&](int j) {
@@ -411,9 +413,15 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
       const uint64_t dp = make_smem_desc(p_base + (uint32_t)(pb_i * kP), 2048, 128, SWZ_NONE);
       const uint64_t dv = make_smem_desc(smem_u32(sV + stage * p.kv_bytes), 128, 2048, SWZ_NONE);
       if (leader) {
+        if (p.p_tmem) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k)   // P: +4096 B (= +256) per 16 keys; V: +256 B (= +16) per 16 keys
-          umma_ss(d_o, dp + (uint64_t)(k * 256), dv + (uint64_t)(k * 16), idesc_o, (j | k) ? 1u : 0u);
+          for (int k = 0; k < 8; ++k)   // A = P from tensor memory (8 packed columns per 16 keys), B = V from smem
+            umma_ts(d_o, t_p + (uint32_t)(k * 8), dv + (uint64_t)(k * 16), idesc_o, (j | k) ? 1u : 0u);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 8; ++k)   // P: +4096 B (= +256) per 16 keys; V: +256 B (= +16) per 16 keys
+            umma_ss(d_o, dp + (uint64_t)(k * 256), dv + (uint64_t)(k * 16), idesc_o, (j | k) ? 1u : 0u);
+        }
         umma_commit(&kv_empty[stage]);
         umma_commit(&pv_done[2 * q + pb_i]);
       }
@@ -430,7 +438,8 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
     const int row = qd * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
     const uint32_t ts = tmem_base + lane_addr + (uint32_t)(q * 128 + half * 64);
-    const uint32_t to = tmem_base + lane_addr + 256u + (uint32_t)(q * 128);
+    const uint32_t to = tmem_base + lane_addr + 256u + (uint32_t)(q * (p.p_tmem ? 64 : 128));
+    const uint32_t tp = tmem_base + lane_addr + 384u + (uint32_t)(q * 64 + half * 32);
     float* my_x = xchg + (q * 2 + half) * 128 + row;
     const float* other_x = xchg + (q * 2 + (half ^ 1)) * 128 + row;
     // O columns (16-wide chunks) this warp owns for the rescale and the epilogue
@@ -494,24 +503,45 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
       }
       const float mc = m_used * c;
       float ls[4] = {0.f, 0.f, 0.f, 0.f};
+      if (p.p_tmem) {
+        uint32_t pk[32];
 #pragma unroll
-      for (int g = 0; g < 2; ++g) {
+        for (int g = 0; g < 2; ++g) {
 #pragma unroll
-        for (int h = 0; h < 4; ++h) {
-          float e[8];
+          for (int h = 0; h < 4; ++h) {
+            float e[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float xx = fmaf(__uint_as_float(v[g][h * 8 + i]), c, -mc);
-            e[i] = (i & 1) ? ex2_poly(xx) : ex2_approx(xx);
-            ls[i & 3] += e[i];
+            for (int i = 0; i < 8; ++i) {
+              const float xx = fmaf(__uint_as_float(v[g][h * 8 + i]), c, -mc);
+              e[i] = ((i & 3) == 3) ? ex2_poly(xx) : ex2_approx(xx);
+              ls[i & 3] += e[i];
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) pk[g * 16 + h * 4 + i] = pack_bf16(e[2 * i], e[2 * i + 1]);
           }
-          *reinterpret_cast<uint4*>(pb + (g * 4 + h) * 2048) =
-              make_uint4(pack_bf16(e[0], e[1]), pack_bf16(e[2], e[3]), pack_bf16(e[4], e[5]), pack_bf16(e[6], e[7]));
         }
+        tmem_st32(tp, pk);       // this warp's 64 keys = 32 packed columns of P(q)
+        tmem_st_wait();
+      } else {
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            float e[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float xx = fmaf(__uint_as_float(v[g][h * 8 + i]), c, -mc);
+              e[i] = ((i & 3) == 3) ? ex2_poly(xx) : ex2_approx(xx);
+              ls[i & 3] += e[i];
+            }
+            *reinterpret_cast<uint4*>(pb + (g * 4 + h) * 2048) =
+                make_uint4(pack_bf16(e[0], e[1]), pack_bf16(e[2], e[3]), pack_bf16(e[4], e[5]), pack_bf16(e[6], e[7]));
+          }
+        }
+        fence_proxy_async_smem();
       }
       l += (ls[0] + ls[1]) + (ls[2] + ls[3]);
       FA_TR(4);
-      fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(&p_ready[q]);
       FA_TR(5);
@@ -640,10 +670,15 @@ extern "C" int vx_flash_attention(const void* q, long long ldq, const void* k, l
     a.kv_bytes = 128 * hdp * 2;
     a.stages = 3;
     a.trace = getenv("VX_FA_TRACE") ? (long long*)strtoull(getenv("VX_FA_TRACE"), nullptr, 10) : nullptr;
-    auto need = [&](int st, int pb) { return (size_t)2 * a.q_bytes + (size_t)2 * st * a.kv_bytes + (size_t)2 * pb * 32768 + 6144 + 384 + 128; };
-    a.pbufs = (need(3, 2) <= 227 * 1024 && !getenv("VX_FA_PBUF1")) ? 2 : 1;
-    if (need(3, a.pbufs) > 227 * 1024) a.stages = 2;
-    const size_t smem2 = need(a.stages, a.pbufs);
+    auto need = [&](int st, int pb) { return (size_t)2 * a.q_bytes + (size_t)2 * st * a.kv_bytes + (size_t)2 * pb * 32768 + 6144 + 512 + 128; };
+    // P in tensor memory whenever O (2 x hdp) + S (2 x 128) + P (2 x 64) columns fit the 512-column TMEM
+    a.p_tmem = (hdp <= 64 && !getenv("VX_FA_PSMEM")) ? 1 : 0;
+    a.pbufs = 1;
+    a.stages = 6;
+    const int psm = a.p_tmem ? 0 : 1;
+    while (a.stages > 2 && need(a.stages, psm) > 227 * 1024) --a.stages;
+    if (getenv("VX_FA_STAGES")) a.stages = atoi(getenv("VX_FA_STAGES"));
+    const size_t smem2 = need(a.stages, psm);
     VX_REQUIRE(smem2 <= 227 * 1024, "vx_flash_attention: smem %zu too large (hd=%d)", smem2, hd);
     CUtensorMap mQ, mK, mV;
     const void* ptrs[3] = {q, k, v};

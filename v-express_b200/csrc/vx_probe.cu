@@ -55,6 +55,62 @@ __global__ void __launch_bounds__(128, 1) umma_probe_kernel(const ProbeArgs p) {
   if (warp == 0) { tc_fence_after(); tmem_dealloc(tb, 256); }
 }
 
+// TS-MMA probe: A (128 x K bf16) comes from TENSOR MEMORY (written with tcgen05.st, row r in lane r, two K-adjacent
+// bf16 per 32-bit column), B from shared memory.  Pins the layout the flash kernel uses to keep P in TMEM.
+struct ProbeTsArgs {
+  const uint32_t* a_packed;  // [128][K/2] 32-bit words: (a[r][2c] | a[r][2c+1] << 16)
+  const uint8_t* b_img; int b_bytes;
+  uint32_t lboB, sboB, layB;
+  uint32_t idesc;
+  int ksteps, b_step, K, N;
+  float* out;  // [128, N]
+};
+
+__global__ void __launch_bounds__(128, 1) umma_ts_probe_kernel(const ProbeTsArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sb = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  for (int i = threadIdx.x; i < p.b_bytes / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(sb)[i] = reinterpret_cast<const uint32_t*>(p.b_img)[i];
+  fence_proxy_async_smem();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  if (warp == 0) { tmem_alloc(&tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = tmem_slot;
+  const uint32_t a_tmem = tb + 256;  // A at columns [256, 256 + K/2)
+  const int row = warp * 32 + lane;
+  for (int c = 0; c < p.K / 2; c += 16) {
+    uint32_t v[16];
+    for (int i = 0; i < 16; ++i) v[i] = p.a_packed[row * (p.K / 2) + c + i];
+    tmem_st16(a_tmem + ((uint32_t)(warp * 32) << 16) + c, v);
+  }
+  tmem_st_wait();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < p.ksteps; ++k) {
+      const uint64_t db = make_smem_desc(smem_u32(sb) + k * p.b_step, p.lboB, p.sboB, p.layB);
+      umma_ts(tb, a_tmem + (uint32_t)(k * 8), db, p.idesc, k ? 1u : 0u);   // 16 K elements = 8 columns per step
+    }
+    umma_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  tc_fence_after();
+  for (int c = 0; c < p.N; c += 16) {
+    uint32_t v[16];
+    tmem_ld16(tb + ((uint32_t)(warp * 32) << 16) + c, v);
+    tmem_ld_wait();
+    for (int i = 0; i < 16; ++i) p.out[row * p.N + c + i] = __uint_as_float(v[i]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tb, 512); }
+}
+
 __global__ void tma_probe_kernel(const __grid_constant__ CUtensorMap map, int rank, int c0, int c1, int c2, int c3,
                                  int nbytes, uint8_t* out) {
   extern __shared__ uint8_t smem_raw[];
@@ -87,6 +143,17 @@ extern "C" int vx_probe_umma(const void* a_img, int a_bytes, const void* b_img, 
   const size_t smem = ((a_bytes + 1023) & ~1023) + ((b_bytes + 1023) & ~1023) + 2048;
   VX_CHECK_CUDA(cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   umma_probe_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(p);
+  VX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int vx_probe_umma_ts(const void* a_packed, int K, const void* b_img, int b_bytes, unsigned lboB,
+                                unsigned sboB, unsigned layB, int b_mn, int N, int b_step, float* out, void* stream) {
+  VX_REQUIRE(N % 16 == 0 && N <= 256 && K % 32 == 0 && K <= 256 && b_bytes % 4 == 0, "vx_probe_umma_ts: bad args");
+  ProbeTsArgs p{(const uint32_t*)a_packed, (const uint8_t*)b_img, b_bytes, lboB, sboB, layB,
+                make_idesc_bf16(128, N, 0, b_mn), K / 16, b_step, K, N, out};
+  VX_CHECK_CUDA(cudaFuncSetAttribute(umma_ts_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  umma_ts_probe_kernel<<<1, 128, ((b_bytes + 1023) & ~1023) + 2048, (cudaStream_t)stream>>>(p);
   VX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -94,6 +94,14 @@ def probe_umma(a_img, b_img, lboA, sboA, layA, lboB, sboB, layB, a_mn, b_mn, N, 
     return out
 
 
+def probe_umma_ts(a_packed, K, b_img, lboB, sboB, layB, b_mn, N, b_step):
+    out = torch.empty((128, N), device=b_img.device, dtype=torch.float32)
+    check(_ffi.lib().vx_probe_umma_ts(ptr(a_packed), c_int(K), ptr(b_img), c_int(b_img.numel()), ctypes.c_uint(lboB),
+                                      ctypes.c_uint(sboB), ctypes.c_uint(layB), c_int(b_mn), c_int(N), c_int(b_step),
+                                      ptr(out), stream_ptr()), "vx_probe_umma_ts")
+    return out
+
+
 def probe_tma(base, dims, strides_bytes, box, swizzle, coords, nbytes):
     rank = len(dims)
     out = torch.empty(nbytes, device=base.device, dtype=torch.uint8)
