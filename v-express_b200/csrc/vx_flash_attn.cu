@@ -287,6 +287,10 @@ struct Fa2Args {
 
 #define FA_TR(slot) do { if (tr) tr[(j) * 16 + (slot)] = clock64(); } while (0)
 
+// ONES: the head dim is padded (hd 40 -> 48) and column `hd` of every V tile is set to 1.0, so the P.V product also
+// accumulates the softmax row sum in O[:, hd] (with exactly the bf16-rounded P it multiplies V with); the 64
+// per-element FADDs of the row sum disappear from the issue-bound softmax loop.
+template <bool ONES>
 __global__ void __launch_bounds__(kFa2Threads, 1)
 flash_attn2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                    const __grid_constant__ CUtensorMap mapV, const Fa2Args p) {
@@ -316,6 +320,14 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
     const int total16 = (2 * p.q_bytes + 2 * p.stages * p.kv_bytes) / 16;
     uint4* z = reinterpret_cast<uint4*>(sQ);
     for (int i = threadIdx.x; i < total16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+  }
+  if (ONES) {
+    __syncthreads();
+    // V tiles are [hdp/8 chunks][128 keys][8]: element (key, col hd) = chunk hd/8, slot hd%8; TMA never touches it
+    for (int i = threadIdx.x; i < p.stages * 128; i += blockDim.x) {
+      const int st = i / 128, key = i % 128;
+      reinterpret_cast<__nv_bfloat16*>(sV + st * p.kv_bytes + (p.hd / 8) * 2048 + key * 16)[p.hd % 8] = __float2bfloat16(1.0f);
+    }
   }
   if (threadIdx.x == 0) {
     mbar_init(q_full, 1);
@@ -513,8 +525,8 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const float xx = fmaf(__uint_as_float(v[g][h * 8 + i]), c, -mc);
-              e[i] = ((i & 3) == 3) ? ex2_poly(xx) : ex2_approx(xx);
-              ls[i & 3] += e[i];
+              e[i] = (i == 7) ? ex2_poly(xx) : ex2_approx(xx);   // 1/8 on the FMA pipe balances issue vs MUFU
+              if (!ONES) ls[i & 3] += e[i];
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) pk[g * 16 + h * 4 + i] = pack_bf16(e[2 * i], e[2 * i + 1]);
@@ -532,7 +544,7 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
             for (int i = 0; i < 8; ++i) {
               const float xx = fmaf(__uint_as_float(v[g][h * 8 + i]), c, -mc);
               e[i] = ((i & 3) == 3) ? ex2_poly(xx) : ex2_approx(xx);
-              ls[i & 3] += e[i];
+              if (!ONES) ls[i & 3] += e[i];
             }
             *reinterpret_cast<uint4*>(pb + (g * 4 + h) * 2048) =
                 make_uint4(pack_bf16(e[0], e[1]), pack_bf16(e[2], e[3]), pack_bf16(e[4], e[5]), pack_bf16(e[6], e[7]));
@@ -546,12 +558,30 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
       mbar_arrive(&p_ready[q]);
       FA_TR(5);
     }
-    // total row sum = the two column halves
-    my_x[1024] = l;
-    wg_bar_sync(q);
-    l += other_x[1024];
     mbar_wait(&o_full[q], 0);
     tc_fence_after();
+    if (ONES) {
+      // the row sum sits in O[:, hd]; the warp owning that chunk publishes it to its partner
+      const int lc = p.hd / 16;
+      if (lc >= oc_begin && lc < oc_end) {
+        uint32_t o[16];
+        tmem_ld16(to + lc * 16, o);
+        tmem_ld_wait();
+        float lv = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (i == (p.hd & 15)) lv = __uint_as_float(o[i]);
+        l = lv;
+        my_x[1024] = l;
+      }
+      wg_bar_sync(q);
+      if (!(lc >= oc_begin && lc < oc_end)) l = other_x[1024];
+    } else {
+      // total row sum = the two column halves
+      my_x[1024] = l;
+      wg_bar_sync(q);
+      l += other_x[1024];
+    }
     const int qrow = q_pair * 256 + q * 128 + row;
     const float inv = 1.f / l;
     __nv_bfloat16* op = p.out + ((long long)bq * p.Nq + qrow) * p.ldo + head * p.hd;
@@ -693,11 +723,15 @@ extern "C" int vx_flash_attention(const void* q, long long ldq, const void* k, l
     }
     static bool cfg2 = false;
     if (!cfg2) {
-      VX_CHECK_CUDA(cudaFuncSetAttribute(flash_attn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      VX_CHECK_CUDA(cudaFuncSetAttribute(flash_attn2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      VX_CHECK_CUDA(cudaFuncSetAttribute(flash_attn2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       cfg2 = true;
     }
     dim3 grid2(Nq / 256, heads, Bq);
-    flash_attn2_kernel<<<grid2, kFa2Threads, smem2, (cudaStream_t)stream>>>(mQ, mK, mV, a);
+    if (hdp > hd && !getenv("VX_FA_NOONES"))
+      flash_attn2_kernel<true><<<grid2, kFa2Threads, smem2, (cudaStream_t)stream>>>(mQ, mK, mV, a);
+    else
+      flash_attn2_kernel<false><<<grid2, kFa2Threads, smem2, (cudaStream_t)stream>>>(mQ, mK, mV, a);
     VX_CHECK_CUDA(cudaGetLastError());
     return 0;
   }
