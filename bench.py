@@ -291,7 +291,7 @@ def cpu_sample(threads=None):
     at (b=2, f=1, 64x64) = the per-frame cost of one CFG denoise step, and one 1-frame VAE decode at 512x512.
     frames/s of the 25-step workload = 1 / (25 * t_unet + t_vae)."""
     from oracle import vx_oracle as O
-    threads = threads or os.cpu_count()
+    threads = threads or min(os.cpu_count(), 32)   # beyond ~32 threads the small per-frame convs/GEMMs scale negatively
     torch.set_num_threads(threads)
     cfg, vcfg = O.DEFAULT_CFG, O.VAE_CFG
     g = torch.Generator().manual_seed(0)
