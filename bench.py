@@ -288,10 +288,10 @@ def kernel_roofline(pipe, host, L, h):
 # --------------------------------------------------------------------------------------------- CPU arms
 def cpu_sample(threads=None):
     """Bounded sample of the reference algorithm (oracle port, fp32) on the host cores: one full-width UNet forward
-    at (b=2, f=1, 64x64) = the per-frame cost of one CFG denoise step, and one 1-frame VAE decode at 512x512.
-    frames/s of the 25-step workload = 1 / (25 * t_unet + t_vae)."""
+    at (b=2, f=4, 64x64) (BASELINE configs[0] shape; per-frame cost of one CFG denoise step = t_unet / 4) and one
+    1-frame VAE decode at 512x512.  frames/s of the 25-step workload = 1 / (25 * t_unet / 4 + t_vae)."""
     from oracle import vx_oracle as O
-    threads = threads or min(os.cpu_count(), 32)   # beyond ~32 threads the small per-frame convs/GEMMs scale negatively
+    threads = threads or int(os.environ.get("VX_CPU_THREADS", 0)) or min(os.cpu_count(), 32)   # >32 threads scale negatively here
     torch.set_num_threads(threads)
     cfg, vcfg = O.DEFAULT_CFG, O.VAE_CFG
     g = torch.Generator().manual_seed(0)
@@ -308,7 +308,8 @@ def cpu_sample(threads=None):
         return sd
     sd = synth(O.unet_param_shapes(cfg))
     vsd = synth(O.vae_param_shapes(vcfg))
-    lat, kps, audio, banks = O.synth_inputs(cfg, 1, 64, 64, True, 42)
+    F_SAMPLE = 4   # frames in the CPU sample window (BASELINE configs[0] shape)
+    lat, kps, audio, banks = O.synth_inputs(cfg, F_SAMPLE, 64, 64, True, 42)
     x = lat.repeat(2, 1, 1, 1, 1)
     enc = audio.reshape(-1, 5, 768)
     z = torch.randn(1, 4, 64, 64, generator=g)
@@ -340,16 +341,16 @@ def reference_arm(args):
     wall = time.perf_counter() - t0
     tu /= args.steps
     tv /= args.steps
-    fps = 1.0 / (25 * tu + tv)
-    sample = (f"per step: 1 full-width UNet forward (b=2 CFG, f=1, 64x64 latents, fp32) = {tu:.2f}s and 1 VAE decode of one "
-              f"512x512 frame = {tv:.2f}s; frames/s = 1/(25*t_unet + t_vae)")
+    fps = 1.0 / (25 * tu / 4 + tv)
+    sample = (f"per step: 1 full-width UNet forward (b=2 CFG, f=4, 64x64 latents, fp32) = {tu:.2f}s and 1 VAE decode of one "
+              f"512x512 frame = {tv:.2f}s; frames/s = 1/(25*t_unet/4 + t_vae)")
     line = dict(metric="frames_per_sec_512x512_25step", value=fps, unit="frames/s", n_gpus=args.gpus, steps=args.steps,
                 warmup=args.warmup, ms_per_step=wall / args.steps * 1e3, higher_is_better=True, scaling="weak",
                 vs_baseline=None, dtype="f32", data="synthetic", impl="reference",
                 config=workload_config(args.gpus),
                 cpu_baseline=dict(value=fps, unit="frames/s", cores=threads, kind="port", sample=sample),
                 e2e=dict(value=fps, unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
-                unet_ms_per_step=tu * 16 * 1e3)
+                unet_ms_per_step=tu * 4 * 1e3)
     print(json.dumps(line))
 
 
