@@ -354,8 +354,17 @@ def reference_arm(args):
     print(json.dumps(line))
 
 
+FRAMES_OVERRIDE = 0   # --frames L: other BASELINE configs on one GPU (e.g. 96 = configs[2]); not the headline line
+
+
 def workload_config(n):
     L = 16 if n == 1 else 8 * n + 8
+    if FRAMES_OVERRIDE and n == 1:
+        L = FRAMES_OVERRIDE
+        nw = (L - 16) // 8 + 1
+        return dict(workload=f"512x512, {L} frames via context scheduler (window 16, overlap 8 -> {nw} windows), 25 DDIM steps, "
+                             f"CFG 3.5, bf16, 1 GPU", video_length=L, context_frames=16, context_overlap=8,
+                    num_inference_steps=25, guidance_scale=3.5, l2="working set >> 126 MB L2", parallelism="windows-dp1")
     return dict(workload=("BASELINE configs[1]: 512x512, single 16-frame context window, 25 DDIM steps, CFG 3.5, bf16"
                           if n == 1 else
                           f"512x512, {L} frames = {n} context windows (window 16, overlap 8), one window per rank, 25 DDIM "
@@ -464,7 +473,7 @@ def ours(args):
             op_table(pipe, host, L, h, "vae")
         fps = L * args.steps / sec
         e2e_fps = L * args.steps / e2e_wall
-        windows = n
+        windows = n if not (FRAMES_OVERRIDE and n == 1) else (L - 16) // 8 + 1
         work_tflop = steps_ddim * windows * 32 * UNET_TFLOP_PER_FRAME_EVAL + L * VAE_TFLOP_PER_FRAME
         line = dict(metric="frames_per_sec_512x512_25step", value=fps, unit="frames/s", n_gpus=n, steps=args.steps,
                     warmup=args.warmup, ms_per_step=sec / args.steps * 1e3, higher_is_better=True, scaling="weak",
@@ -520,7 +529,10 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=0, help="video length override for N=1 (multiple of 8, >= 16)")
     args = ap.parse_args()
+    global FRAMES_OVERRIDE
+    FRAMES_OVERRIDE = args.frames
     if args.impl == "reference":
         reference_arm(args)
         return

@@ -91,19 +91,29 @@ __global__ void __launch_bounds__(128) temporal_attn_kernel(const TemporalArgs p
     __syncwarp();
     const float* kh = reinterpret_cast<const float*>(base) + hs * p.f * HD;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
+    for (int j = 0; j < 32; j += 2) {   // two keys per step: four independent FMA chains per thread
       if (j >= p.f) break;
-      float a0 = 0.f, a1 = 0.f;
+      const bool two = j + 1 < p.f;
+      float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
 #pragma unroll
       for (int i = 0; i < HD / 4; ++i) {
         const float4 kk = *reinterpret_cast<const float4*>(kh + j * HD + i * 4);
+        const float4 k2 = *reinterpret_cast<const float4*>(kh + (two ? j + 1 : j) * HD + i * 4);
         a0 = fmaf(qf[4 * i], kk.x, a0);
+        b0 = fmaf(qf[4 * i], k2.x, b0);
         a1 = fmaf(qf[4 * i + 1], kk.y, a1);
+        b1 = fmaf(qf[4 * i + 1], k2.y, b1);
         a0 = fmaf(qf[4 * i + 2], kk.z, a0);
+        b0 = fmaf(qf[4 * i + 2], k2.z, b0);
         a1 = fmaf(qf[4 * i + 3], kk.w, a1);
+        b1 = fmaf(qf[4 * i + 3], k2.w, b1);
       }
       s[j] = a0 + a1;
       mx = fmaxf(mx, s[j]);
+      if (two) {
+        s[j + 1] = b0 + b1;
+        mx = fmaxf(mx, s[j + 1]);
+      }
     }
   } else {
     uint4 qreg[VEC];

@@ -56,6 +56,7 @@ __global__ void gn_stats_kernel(const GnStatsArgs p) {
   const __nv_bfloat16* base = second ? p.x2 + (long long)n * p.HW * p.ld2 + (c0 - p.C1)
                                      : p.x1 + (long long)n * p.HW * p.ld1 + c0;
   const long long ld = second ? p.ld2 : p.ld1;
+#pragma unroll 4
   for (int px = p0 + r; px < p1; px += p.R) {
     float f[8];
     load8(base + px * ld, f);
@@ -155,6 +156,7 @@ __global__ void gn_apply_kernel(const GnApplyArgs p) {
                                     : p.x1 + (long long)n * p.HW * p.ld1 + c0;
   const long long lds = second ? p.ld2 : p.ld1;
   __nv_bfloat16* dst = p.out + (long long)n * p.HW * p.ldo + c0;
+#pragma unroll 4
   for (int px = p0 + r; px < p1; px += R) {
     float f[8];
     load8(src + px * lds, f);
