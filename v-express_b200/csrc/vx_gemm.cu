@@ -67,6 +67,58 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;"
 // erf-GELU with erf from Abramowitz & Stegun 7.1.28 (|error| < 3e-7, i.e. exact at bf16 precision):
 // erf(x) = 1 - (1 + a1 x + ... + a6 x^6)^-16 for x >= 0.  ~13 FMA-pipe instructions + one MUFU.RCP instead of
 // libdevice erff (the GEGLU epilogue was erf-bound: 128 x 128 erf evaluations per tile).
+// ---- cta_group::2 (CTA pair on one 256-row tile) helpers
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void tma_load_2d_cg2(void* dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
+          "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_cg2(void* dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0, int c1,
+                                                int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::
+          "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void umma_ss_cg2(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// completion of all prior MMAs of this thread -> arrive on the barrier at the same smem offset in both CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_cg2(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_cg2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
 __device__ __forceinline__ float gelu_erf(float g) {
   const float x = fabsf(g) * 0.70710678118654752f;
   float pl = fmaf(x, 0.0000430638f, 0.0002765672f);
@@ -82,6 +134,11 @@ __device__ __forceinline__ float gelu_erf(float g) {
   return 0.5f * g * (1.0f + copysignf(erf_abs, g));
 }
 
+// CG = 1: one CTA per 128-row tile.  CG = 2: a CTA pair (cluster of 2) owns a 256-row tile: each CTA loads its own
+// 128 rows of A and HALF of the W tile, the leader issues tcgen05.mma.cta_group::2 (M = 256) and every SM feeds only
+// half of B from its shared memory -- the 1-CTA kernel is bound by the SS-MMA operand fetch (A 4 KB + B 8 KB per
+// 128x256x16 MMA at ~64 B/clk = 192 clk vs 128 clk of math, profiles/r01e_final_ncu.md).
+template <int CG>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapA2,
                     const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapR,
@@ -90,8 +147,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   // 1024-byte alignment required by the 128B swizzle atom
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int a_bytes = kBlockM * kBlockK * 2;
-  const int b_bytes = p.block_n * kBlockK * 2;
+  const int b_bytes = (p.block_n / CG) * kBlockK * 2;   // this CTA's share of the W tile
   const int stage_bytes = a_bytes + b_bytes;
+  const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
+  const bool pair_leader = cta_rank == 0;
   uint8_t* sC = smem + p.stages * stage_bytes;  // staging: (block_n or block_n/2)/32 panels of 8 KB
   const int out_cols = p.geglu ? p.block_n / 2 : p.block_n;
   const int npanels = out_cols / kPanelCols;
@@ -107,7 +166,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int total_kb = p.taps * p.kblocks1 + p.kblocks2;
-  const int num_tiles = p.tiles_m * p.tiles_n;
+  // work items are (row-tile group of CG tiles, column tile); every CTA of a pair walks the same sequence
+  const int num_tiles = ((p.tiles_m + CG - 1) / CG) * p.tiles_n;
+  const int first_item = blockIdx.x / CG, item_stride = gridDim.x / CG;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA);
@@ -121,18 +182,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], kEpiThreads / 32);
+      mbar_init(&tmem_empty[s], CG * kEpiThreads / 32);
       mbar_init(&c_ready[s], 1);
       mbar_init(&staged[s], kEpiThreads);
     }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
+    if (CG == 2) {
+      tmem_alloc_cg2(tmem_slot, 512);
+    } else {
+      tmem_alloc(tmem_slot, 512);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -144,8 +209,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     const bool leader = elect_one();
     int stage = 0;
     uint32_t phase = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const int tile_n = t % p.tiles_n, tile_m = t / p.tiles_n;
+    for (int t = first_item; t < num_tiles; t += item_stride) {
+      const int tile_n = t % p.tiles_n, tile_m = (t / p.tiles_n) * CG + (int)cta_rank;
       int n0 = 0, y0 = 0, x0 = 0;
       const long long m0 = (long long)tile_m * p.rows_valid;
       if (p.taps == 9) {
@@ -155,7 +220,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         y0 = rem / p.W;
         x0 = rem % p.W;
       }
-      const uint32_t tx_bytes = (uint32_t)(p.rows_valid * kBlockK * 2 + b_bytes);
+      // the pair's loads all complete on the LEADER's full barrier (it alone waits for the operands)
+      const uint32_t tx_bytes = (uint32_t)(CG * (p.rows_valid * kBlockK * 2 + b_bytes));
+      const int b_row = tile_n * p.block_n + (int)cta_rank * (p.block_n / CG);
       for (int kb = 0; kb < total_kb; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * stage_bytes;
@@ -164,15 +231,28 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         const int cb = kb - tap * p.kblocks1;
         const int dy = tap / 3 - 1, dx = tap % 3 - 1;
         if (leader) {
-          mbar_expect_tx(&full_bar[stage], tx_bytes);
-          if (p.taps == 9) {
-            tma_load_4d(sa, &mapA, &full_bar[stage], cb * kBlockK, x0 + dx, y0 + dy, n0);
-          } else if (kb < p.kblocks1) {
-            tma_load_2d(sa, &mapA, &full_bar[stage], kb * kBlockK, (int)m0);
+          if (CG == 2) {
+            const uint32_t fb = mapa_rank(smem_u32(&full_bar[stage]), 0);
+            if (pair_leader) mbar_expect_tx(&full_bar[stage], tx_bytes);
+            if (p.taps == 9) {
+              tma_load_4d_cg2(sa, &mapA, fb, cb * kBlockK, x0 + dx, y0 + dy, n0);
+            } else if (kb < p.kblocks1) {
+              tma_load_2d_cg2(sa, &mapA, fb, kb * kBlockK, (int)m0);
+            } else {
+              tma_load_2d_cg2(sa, &mapA2, fb, (kb - p.kblocks1) * kBlockK, (int)m0);
+            }
+            tma_load_2d_cg2(sb, &mapB, fb, kb * kBlockK, b_row);
           } else {
-            tma_load_2d(sa, &mapA2, &full_bar[stage], (kb - p.kblocks1) * kBlockK, (int)m0);
+            mbar_expect_tx(&full_bar[stage], tx_bytes);
+            if (p.taps == 9) {
+              tma_load_4d(sa, &mapA, &full_bar[stage], cb * kBlockK, x0 + dx, y0 + dy, n0);
+            } else if (kb < p.kblocks1) {
+              tma_load_2d(sa, &mapA, &full_bar[stage], kb * kBlockK, (int)m0);
+            } else {
+              tma_load_2d(sa, &mapA2, &full_bar[stage], (kb - p.kblocks1) * kBlockK, (int)m0);
+            }
+            tma_load_2d(sb, &mapB, &full_bar[stage], kb * kBlockK, b_row);
           }
-          tma_load_2d(sb, &mapB, &full_bar[stage], kb * kBlockK, tile_n * p.block_n);
         }
         __syncwarp();
         if (++stage == p.stages) {
@@ -183,12 +263,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (warp-uniform loop, elected lane issues)
-    const bool leader = elect_one();
-    const uint32_t idesc = make_idesc_bf16(kBlockM, (uint32_t)p.block_n, 0, 0);
+    const bool leader = elect_one() && pair_leader;   // with CG = 2 only the pair leader issues MMAs
+    const uint32_t idesc = make_idesc_bf16(kBlockM * CG, (uint32_t)p.block_n, 0, 0);
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+    if (pair_leader)
+    for (int t = first_item; t < num_tiles; t += item_stride, ++it) {
       const int as = it & 1;
       mbar_wait(&tmem_empty[as], (uint32_t)(((it >> 1) & 1) ^ 1));
       tc_fence_after();
@@ -202,9 +283,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         const uint64_t db = make_smem_desc(sb, 16, 1024, SWZ_128B);
         if (leader) {
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k)   // +32 bytes per K step = +2 in the (addr >> 4) field
-            umma_ss(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_commit(&empty_bar[stage]);
+          for (int k = 0; k < kBlockK / 16; ++k) {  // +32 bytes per K step = +2 in the (addr >> 4) field
+            if (CG == 2) umma_ss_cg2(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_ss(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          if (CG == 2) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
         }
         __syncwarp();
         if (++stage == p.stages) {
@@ -212,7 +295,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
           phase ^= 1;
         }
       }
-      if (leader) umma_commit(&tmem_full[as]);
+      if (leader) {
+        if (CG == 2) umma_commit_pair(&tmem_full[as]); else umma_commit(&tmem_full[as]);
+      }
       __syncwarp();
     }
   } else if (warp == 10) {
@@ -221,7 +306,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       const uint32_t res_bytes = (uint32_t)(p.rows_valid * out_cols * 2);
       auto arm = [&](int t, int b) {  // make staging tile b usable for output tile t
         if (p.has_residual) {
-          const int tn_ = t % p.tiles_n, tm_ = t / p.tiles_n;
+          const int tn_ = t % p.tiles_n, tm_ = (t / p.tiles_n) * CG + (int)cta_rank;
           mbar_expect_tx(&c_ready[b], res_bytes);
           for (int pn = 0; pn < npanels; ++pn)
             tma_load_2d(sC + b * buf_bytes + pn * kPanelBytes, &mapR, &c_ready[b], tn_ * out_cols + pn * kPanelCols,
@@ -231,17 +316,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         }
       };
       for (int b = 0; b < p.nbuf; ++b)
-        if ((int)blockIdx.x + b * (int)gridDim.x < num_tiles) arm(blockIdx.x + b * gridDim.x, b);
+        if (first_item + b * item_stride < num_tiles) arm(first_item + b * item_stride, b);
       int it = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      for (int t = first_item; t < num_tiles; t += item_stride, ++it) {
         const int b = it % p.nbuf;
-        const int tile_n = t % p.tiles_n, tile_m = t / p.tiles_n;
+        const int tile_n = t % p.tiles_n, tile_m = (t / p.tiles_n) * CG + (int)cta_rank;
         mbar_wait(&staged[b], (uint32_t)((it / p.nbuf) & 1));
         for (int pn = 0; pn < npanels; ++pn)
           tma_store_2d(&mapC, sC + b * buf_bytes + pn * kPanelBytes, tile_n * out_cols + pn * kPanelCols,
                        tile_m * p.rows_valid);
         tma_store_commit();
-        const int tnext = t + p.nbuf * gridDim.x;
+        const int tnext = t + p.nbuf * item_stride;
         if (tnext < num_tiles) {
           tma_store_wait_read();  // the store has finished reading tile b
           arm(tnext, b);
@@ -259,8 +344,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     const int c_begin = half ? (nchunks + 1) / 2 : 0;
     const int c_end = half ? nchunks : (nchunks + 1) / 2;
     int it = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-      const int tile_n = t % p.tiles_n, tile_m = t / p.tiles_n;
+    const uint32_t te_leader0 = CG == 2 ? mapa_rank(smem_u32(&tmem_empty[0]), 0) : 0u;
+    const uint32_t te_leader1 = CG == 2 ? mapa_rank(smem_u32(&tmem_empty[1]), 0) : 0u;
+    for (int t = first_item; t < num_tiles; t += item_stride, ++it) {
+      const int tile_n = t % p.tiles_n, tile_m = (t / p.tiles_n) * CG + (int)cta_rank;
       const int as = it & 1;
       const long long m = (long long)tile_m * p.rows_valid + row;
       const bool row_ok = row < p.rows_valid && m < p.M;
@@ -351,7 +438,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       // accumulator stage drained: hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[as]);
+      if (lane == 0) {
+        if (CG == 2) mbar_arrive_cluster(as ? te_leader1 : te_leader0);   // the pair leader's MMA warp owns both halves
+        else mbar_arrive(&tmem_empty[as]);
+      }
       if (!p.out_f32) {
         fence_proxy_async_smem();     // staging writes -> visible to the TMA store (async proxy)
         mbar_arrive(&staged[sb]);
@@ -359,10 +449,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (CG == 2) tmem_dealloc_cg2(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -382,17 +472,35 @@ static int num_sms() {
   return n;
 }
 
+static int env_int(const char* name, int dflt);
+
+static bool pair_ok(int out_f32, int block_n, long long tiles_m, int total_kb) {
+  // CTA pairs need an even split of the W tile into 8-row swizzle groups and at least two row tiles.  They pay off
+  // once the K loop is long enough to be MMA/operand bound; short K loops (K <= 640) are bound by the epilogue and
+  // the output stores, where two independent CTAs overlap better (profiles/tools/gemm_sweep.py).
+  const int mode = env_int("VX_GEMM_CG", 0);   // 0 = auto, 1 = never, 2 = whenever legal
+  if (out_f32 || block_n % 32 != 0 || tiles_m < 2 || mode == 1) return false;
+  return mode == 2 || total_kb >= 12;
+}
+
+// resident CTA pairs of the persistent cta_group::2 kernel (GPCs with an odd SM count strand one SM)
+static int num_pairs();
+
 // Pick the UMMA N: among the multiples of `gran` that divide N, minimise
-//   waves(tiles) x cycles per k-block, with cycles = max(MMA issue 2*bn, smem feed 128 + bn).
-static int pick_block_n(long long tiles_m, int N, int gran) {
+//   waves(work items) x cycles per k-block, with cycles = max(MMA issue 2*bn, smem feed 128 + bn) for one CTA per
+//   tile and max(2*bn, 128 + bn/2) for a CTA pair (each SM feeds only half of W).
+static int pick_block_n(long long tiles_m, int N, int gran, int out_f32, int total_kb) {
   const int sms = num_sms();
   int best = 0;
   double best_cost = 1e30;
   for (int bn = 256; bn >= gran; bn -= gran) {
     if (N % bn) continue;
-    const long long tiles = tiles_m * (N / bn);
-    const double waves = (double)((tiles + sms - 1) / sms);
-    const double cyc = (2.0 * bn > 128.0 + bn) ? 2.0 * bn : 128.0 + bn;
+    const bool pair = pair_ok(out_f32, bn, tiles_m, total_kb);
+    const long long items = (pair ? (tiles_m + 1) / 2 : tiles_m) * (N / bn);
+    const int slots = pair ? num_pairs() : sms;
+    const double waves = (double)((items + slots - 1) / slots);
+    const double feed = pair ? 128.0 + bn / 2 : 128.0 + bn;
+    const double cyc = (2.0 * bn > feed) ? 2.0 * bn : feed;
     const double cost = waves * (cyc + 40.0);  // + per-k-block issue overhead
     if (cost < best_cost * 0.999) {
       best_cost = cost;
@@ -402,9 +510,40 @@ static int pick_block_n(long long tiles_m, int N, int gran) {
   return best;
 }
 
+static bool use_pair(const GemmArgs& a) {
+  return pair_ok(a.out_f32, a.block_n, a.tiles_m, a.taps * a.kblocks1 + a.kblocks2);
+}
+
+static int num_pairs() {
+  static int n = 0;
+  if (n <= 0) {
+    cudaFuncSetAttribute(gemm_tcgen05_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * num_sms());
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = 227 * 1024;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int c = 0;
+    if (cudaOccupancyMaxActiveClusters(&c, gemm_tcgen05_kernel<2>, &cfg) != cudaSuccess || c <= 0) {
+      cudaGetLastError();
+      c = num_sms() / 2;
+    }
+    n = env_int("VX_GEMM_PAIRS", c);
+    if (getenv("VX_GEMM_VERBOSE")) fprintf(stderr, "[vx_gemm] resident CTA pairs: %d (occupancy query %d)\n", n, c);
+  }
+  return n;
+}
+
 static int launch(const CUtensorMap& mA, const CUtensorMap& mA2, const CUtensorMap& mB, const CUtensorMap& mR,
                   const CUtensorMap& mC, GemmArgs& a, cudaStream_t st) {
-  const int stage_bytes = kBlockM * kBlockK * 2 + a.block_n * kBlockK * 2;
+  const int cg = use_pair(a) ? 2 : 1;
+  const int stage_bytes = kBlockM * kBlockK * 2 + (a.block_n / cg) * kBlockK * 2;
   const int out_cols = a.geglu ? a.block_n / 2 : a.block_n;
   const int buf_bytes = a.out_f32 ? 0 : out_cols / kPanelCols * kPanelBytes;
   const int total_kb = a.taps * a.kblocks1 + a.kblocks2;
@@ -412,20 +551,50 @@ static int launch(const CUtensorMap& mA, const CUtensorMap& mA2, const CUtensorM
   // deep TMA rings only pay off for long K loops; short K loops need the second staging tile instead
   int want_stages = env_int("VX_GEMM_STAGES", 0);
   if (want_stages <= 0) want_stages = total_kb < 6 ? (total_kb < 3 ? 3 : total_kb) : 6;
-  int nbuf = (!a.out_f32 && (size_t)3 * stage_bytes + 2 * buf_bytes <= cap && !getenv("VX_GEMM_NBUF1")) ? 2 : 1;
+  int nbuf = (!a.out_f32 && (size_t)3 * stage_bytes + 2 * buf_bytes <= cap) ? 2 : 1;
+  if (cg == 2 && nbuf == 2) {
+    // a pair at full MMA rate pulls 64 B/clk/SM through the TMA ring: it needs >= 5 stages in flight.  Give up the
+    // second staging tile for them unless a residual prefetch shares the staging tile and K is too short to hide it.
+    const int st2 = (int)((cap - 2 * (size_t)buf_bytes) / stage_bytes);
+    if (st2 < 5 && (!a.has_residual || total_kb >= 40)) nbuf = 1;
+  }
+  const int force_nbuf = env_int("VX_GEMM_NBUF", 0);
+  if (force_nbuf == 1 || (force_nbuf == 2 && (size_t)2 * stage_bytes + 2 * buf_bytes <= cap)) nbuf = force_nbuf;
   int stages = want_stages;
   while (stages > 2 && (size_t)stages * stage_bytes + (size_t)nbuf * buf_bytes > cap) --stages;
   a.stages = stages;
   a.nbuf = nbuf;
   const size_t smem = (size_t)stages * stage_bytes + (size_t)nbuf * buf_bytes + 2048;
+  if (getenv("VX_GEMM_VERBOSE"))
+    fprintf(stderr, "[vx_gemm] M=%d N=%d kb=%d taps=%d cg=%d bn=%d stages=%d nbuf=%d tiles=%dx%d\n", a.M, a.N, total_kb,
+            a.taps, cg, a.block_n, stages, nbuf, a.tiles_m, a.tiles_n);
   static bool configured = false;
   if (!configured) {
-    VX_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    VX_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    VX_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
-  const int tiles = a.tiles_m * a.tiles_n;
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_tcgen05_kernel<<<grid, kThreads, smem, st>>>(mA, mA2, mB, mR, mC, a);
+  if (cg == 1) {
+    const int tiles = a.tiles_m * a.tiles_n;
+    const int grid = tiles < num_sms() ? tiles : num_sms();
+    gemm_tcgen05_kernel<1><<<grid, kThreads, smem, st>>>(mA, mA2, mB, mR, mC, a);
+  } else {
+    const int items = ((a.tiles_m + 1) / 2) * a.tiles_n;
+    const int pairs = items < num_pairs() ? items : num_pairs();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    VX_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<2>, mA, mA2, mB, mR, mC, a));
+  }
   VX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -468,8 +637,9 @@ extern "C" int vx_gemm_bf16(const void* A, long long lda, int K1, const void* A2
   VX_REQUIRE(!residual || (ldr % 8 == 0 && !out_f32 && !geglu), "vx_gemm_bf16: residual needs bf16 linear epilogue, ldr %%8");
   VX_REQUIRE(!geglu || (!bias2 && scale == 1.0f), "vx_gemm_bf16: GEGLU epilogue takes only the packed bias");
   const int tiles_m = (M + kBlockM - 1) / kBlockM;
+  const int total_kb = (K1 + kBlockK - 1) / kBlockK + (K2 + kBlockK - 1) / kBlockK;
   if (block_n <= 0) block_n = env_int("VX_GEMM_BN", 0);
-  if (block_n <= 0) block_n = pick_block_n(tiles_m, N, gran);
+  if (block_n <= 0) block_n = pick_block_n(tiles_m, N, gran, out_f32, total_kb);
   VX_REQUIRE(block_n >= gran && block_n % gran == 0 && block_n <= 256 && N % block_n == 0,
              "vx_gemm_bf16: block_n=%d invalid for N=%d", block_n, N);
   CUtensorMap mA, mA2, mB, mR, mC;
@@ -490,7 +660,7 @@ extern "C" int vx_gemm_bf16(const void* A, long long lda, int K1, const void* A2
   {
     uint64_t dims[2] = {(uint64_t)(K1 + K2), (uint64_t)N};
     uint64_t str[1] = {(uint64_t)ldw * 2};
-    uint32_t box[2] = {kBlockK, (uint32_t)block_n};
+    uint32_t box[2] = {kBlockK, (uint32_t)(pair_ok(out_f32, block_n, tiles_m, total_kb) ? block_n / 2 : block_n)};
     if (make_tmap_bf16(&mB, Wt, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
   }
   if (!out_f32) {
@@ -546,8 +716,9 @@ extern "C" int vx_conv3x3_bf16(const void* X, int NB, int H, int W, int C, const
   const long long M = (long long)NB * H * W;
   VX_REQUIRE(M % rows_valid == 0, "vx_conv3x3_bf16: NB*H*W=%lld not tileable by %d", M, rows_valid);
   const long long tiles_m = M / rows_valid;
+  const int total_kb = 9 * (C / kBlockK);
   if (block_n <= 0) block_n = env_int("VX_GEMM_BN", 0);
-  if (block_n <= 0) block_n = pick_block_n(tiles_m, Cout, 32);
+  if (block_n <= 0) block_n = pick_block_n(tiles_m, Cout, 32, 0, total_kb);
   VX_REQUIRE(block_n % 32 == 0 && block_n >= 32 && block_n <= 256 && Cout % block_n == 0,
              "vx_conv3x3_bf16: block_n=%d invalid for Cout=%d", block_n, Cout);
   CUtensorMap mA, mB, mR, mC;
@@ -560,7 +731,7 @@ extern "C" int vx_conv3x3_bf16(const void* X, int NB, int H, int W, int C, const
   {
     uint64_t dims[2] = {(uint64_t)9 * C, (uint64_t)Cout};
     uint64_t str[1] = {(uint64_t)9 * C * 2};
-    uint32_t box[2] = {kBlockK, (uint32_t)block_n};
+    uint32_t box[2] = {kBlockK, (uint32_t)(pair_ok(0, block_n, tiles_m, total_kb) ? block_n / 2 : block_n)};
     if (make_tmap_bf16(&mB, Wt, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
   }
   if (make_out_maps(&mR, &mC, residual, ldr, out, ldc, M, Cout, rows_valid)) return 1;
