@@ -190,6 +190,113 @@ __global__ void __launch_bounds__(128) temporal_attn_kernel(const TemporalArgs p
   }
 }
 
+
+// ---- tensor-core version for f <= 16: one warp per (b, pixel, head), everything in mma.sync fragments.
+// S (16 queries x 16 keys) = Q K^T with m16n8k16 bf16 MMAs whose A / B fragments are read straight from global
+// memory (row = frame, 4 lanes x 4 bytes = one 16-byte piece of the head's row; the second load of a pair takes the
+// other half of the same 32-byte sector from L1), softmax across the 4 lanes of a quad, P packed to bf16 in place
+// (the S accumulator layout is the A layout of the next MMA) and O = P V with V^T fragments produced by
+// movmatrix.trans -- no shared memory, no transposing copies, ~11 MMAs instead of ~1300 FMAs per lane and head.
+__device__ __forceinline__ uint32_t ldg_nc_b32(const __nv_bfloat16* p) {
+  uint32_t r;
+  asm volatile("ld.global.nc.b32 %0, [%1];" : "=r"(r) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint32_t movmatrix_trans(uint32_t a) {
+  uint32_t d;
+  asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(d) : "r"(a));
+  return d;
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                               uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// One 16 x 16 attention in fragments.  q0/q1, k0/k1, v0/v1, o0/o1 point at (row g | row g + 8, column 2t) of the
+// head's slice; okq* / okk* say whether those query / key rows exist, nk = number of valid keys (<= 16).
+template <int HD>
+__device__ __forceinline__ void attn16_mma(const __nv_bfloat16* q0, const __nv_bfloat16* q1, const __nv_bfloat16* k0,
+                                           const __nv_bfloat16* k1, const __nv_bfloat16* v0, const __nv_bfloat16* v1,
+                                           __nv_bfloat16* o0, __nv_bfloat16* o1, bool okq0, bool okq1, bool okk0,
+                                           bool okk1, int nk, float scale, int t) {
+  constexpr int NB = HD / 8;          // 8-column blocks of the head
+  constexpr int KS = (NB + 1) / 2;    // k-steps of 16 (the last one half empty when NB is odd)
+  uint32_t qa[2 * KS][2], kb[2 * KS][2];
+#pragma unroll
+  for (int j = 0; j < 2 * KS; ++j) {
+    const bool in = j < NB;
+    qa[j][0] = (in && okq0) ? ldg_nc_b32(q0 + 8 * j) : 0u;
+    qa[j][1] = (in && okq1) ? ldg_nc_b32(q1 + 8 * j) : 0u;
+    kb[j][0] = (in && okk0) ? ldg_nc_b32(k0 + 8 * j) : 0u;
+    kb[j][1] = (in && okk1) ? ldg_nc_b32(k1 + 8 * j) : 0u;
+  }
+  uint32_t vr[NB][2];
+#pragma unroll
+  for (int j = 0; j < NB; ++j) {
+    vr[j][0] = okk0 ? ldg_nc_b32(v0 + 8 * j) : 0u;
+    vr[j][1] = okk1 ? ldg_nc_b32(v1 + 8 * j) : 0u;
+  }
+  float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};   // keys 0..7 / 8..15
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) {
+    mma_bf16_16816(s0, qa[2 * ks][0], qa[2 * ks][1], qa[2 * ks + 1][0], qa[2 * ks + 1][1], kb[2 * ks][0], kb[2 * ks + 1][0]);
+    mma_bf16_16816(s1, qa[2 * ks][0], qa[2 * ks][1], qa[2 * ks + 1][0], qa[2 * ks + 1][1], kb[2 * ks][1], kb[2 * ks + 1][1]);
+  }
+  // accumulator element i of s0/s1: row g (i < 2) or g + 8, key 2t + (i & 1) (+ 8 for s1)
+  const float sl = scale * 1.4426950408889634f;
+  const bool kv00 = 2 * t < nk, kv01 = 2 * t + 1 < nk, kv10 = 2 * t + 8 < nk, kv11 = 2 * t + 9 < nk;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    s0[i] = ((i & 1) ? kv01 : kv00) ? s0[i] * sl : -INFINITY;
+    s1[i] = ((i & 1) ? kv11 : kv10) ? s1[i] * sl : -INFINITY;
+  }
+  float m0 = fmaxf(fmaxf(s0[0], s0[1]), fmaxf(s1[0], s1[1]));
+  float m1 = fmaxf(fmaxf(s0[2], s0[3]), fmaxf(s1[2], s1[3]));
+  m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+  m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    s0[i] = exp2f(s0[i] - (i < 2 ? m0 : m1));    // key 0 is always valid, so the maxima are finite
+    s1[i] = exp2f(s1[i] - (i < 2 ? m0 : m1));
+  }
+  float sum0 = s0[0] + s0[1] + s1[0] + s1[1], sum1 = s0[2] + s0[3] + s1[2] + s1[3];
+  sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1); sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+  sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1); sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+  const float inv0 = 1.f / sum0, inv1 = 1.f / sum1;
+  const uint32_t pa0 = pack_bf16(s0[0], s0[1]), pa1 = pack_bf16(s0[2], s0[3]);
+  const uint32_t pa2 = pack_bf16(s1[0], s1[1]), pa3 = pack_bf16(s1[2], s1[3]);
+#pragma unroll
+  for (int j = 0; j < NB; ++j) {
+    float o[4] = {0.f, 0.f, 0.f, 0.f};
+    const uint32_t b0 = movmatrix_trans(vr[j][0]);   // (keys 2t, 2t+1; d = 8j + g)
+    const uint32_t b1 = movmatrix_trans(vr[j][1]);   // (keys 2t+8, 2t+9)
+    mma_bf16_16816(o, pa0, pa1, pa2, pa3, b0, b1);
+    if (okq0) *reinterpret_cast<uint32_t*>(o0 + 8 * j) = pack_bf16(o[0] * inv0, o[1] * inv0);
+    if (okq1) *reinterpret_cast<uint32_t*>(o1 + 8 * j) = pack_bf16(o[2] * inv1, o[3] * inv1);
+  }
+}
+
+template <int HD>
+__global__ void __launch_bounds__(128) temporal_attn_mma_kernel(const TemporalArgs p) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const long long item = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);   // (b, pixel, head), head fastest
+  if (item >= (long long)p.b * p.HW * p.heads) return;
+  const int head = (int)(item % p.heads);
+  const long long bp = item / p.heads;
+  const int px = (int)(bp % p.HW);
+  const int bb = (int)(bp / p.HW);
+  const long long row0 = (long long)bb * p.f * p.HW + px;
+  const bool ok0 = g < p.f, ok1 = g + 8 < p.f;           // frames g and g + 8 of this lane's fragment rows
+  const long long r0 = row0 + (long long)(ok0 ? g : 0) * p.HW, r1 = row0 + (long long)(ok1 ? g + 8 : 0) * p.HW;
+  const int col = head * HD + 2 * t;
+  attn16_mma<HD>(p.q + r0 * p.ld + col, p.q + r1 * p.ld + col, p.k + r0 * p.ld + col, p.k + r1 * p.ld + col,
+                 p.v + r0 * p.ld + col, p.v + r1 * p.ld + col, p.out + r0 * p.ldo + col, p.out + r1 * p.ldo + col,
+                 ok0, ok1, ok0, ok1, p.f, p.scale, t);
+}
+
 // one thread per (query row, head); K/V of the frame ([Lk, C], Lk <= 8) stay cache resident
 struct SmallKvArgs {
   const __nv_bfloat16* q; long long ldq;
@@ -263,6 +370,24 @@ __global__ void smallkv_attn_kernel(const SmallKvArgs p) {
   }
 }
 
+// tensor-core version: one warp per (16 consecutive query rows of one frame, head); the frame's Lk tokens are the
+// key rows 0..Lk-1 of the 16-key tile (the rest masked), read once per 16 queries instead of once per query.
+template <int HD>
+__global__ void __launch_bounds__(128) smallkv_attn_mma_kernel(const SmallKvArgs p) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const long long item = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);   // (row tile, head), head fastest
+  if (item >= (p.rows / 16) * p.heads) return;
+  const int head = (int)(item % p.heads);
+  const long long r0 = (item / p.heads) * 16 + g, r1 = r0 + 8;
+  const long long frame = r0 / p.rows_per_frame;
+  const int col = head * HD + 2 * t;
+  const bool okk = g < p.Lk;
+  const long long kr = frame * p.Lk + (okk ? g : 0);
+  attn16_mma<HD>(p.q + r0 * p.ldq + col, p.q + r1 * p.ldq + col, p.k + kr * p.ldkv + col, p.k + kr * p.ldkv + col,
+                 p.v + kr * p.ldkv + col, p.v + kr * p.ldkv + col, p.out + r0 * p.ldo + col, p.out + r1 * p.ldo + col,
+                 true, true, okk, false, p.Lk, p.scale, t);
+}
+
 }  // namespace vx
 
 using namespace vx;
@@ -273,13 +398,28 @@ extern "C" int vx_temporal_attention(const void* q, const void* k, const void* v
   VX_REQUIRE(f >= 1 && f <= 32 && ld % 8 == 0 && ldo % 8 == 0, "vx_temporal_attention: bad f=%d", f);
   TemporalArgs a{(const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, ld, (__nv_bfloat16*)out,
                  ldo, b, f, HW, heads, hd, 1.0f / sqrtf((float)hd)};
+  auto st = (cudaStream_t)stream;
+  if (f <= 16 && !getenv("VX_TEMPORAL_V1")) {
+    const long long warps = (long long)b * HW * heads;
+    const unsigned grid_m = (unsigned)((warps + 3) / 4);
+    switch (hd) {
+      case 8: temporal_attn_mma_kernel<8><<<grid_m, 128, 0, st>>>(a); break;
+      case 16: temporal_attn_mma_kernel<16><<<grid_m, 128, 0, st>>>(a); break;
+      case 32: temporal_attn_mma_kernel<32><<<grid_m, 128, 0, st>>>(a); break;
+      case 40: temporal_attn_mma_kernel<40><<<grid_m, 128, 0, st>>>(a); break;
+      case 80: temporal_attn_mma_kernel<80><<<grid_m, 128, 0, st>>>(a); break;
+      case 160: temporal_attn_mma_kernel<160><<<grid_m, 128, 0, st>>>(a); break;
+      default: return fail("vx_temporal_attention: head dim %d not instantiated (8,16,32,40,80,160)", hd);
+    }
+    VX_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   const int G = f <= 16 ? 2 : 1;
   VX_REQUIRE(heads % G == 0, "vx_temporal_attention: heads=%d must be even", heads);
   const size_t smem = (size_t)4 * 2 * G * f * hd * (hd <= 80 ? 4 : 2);
   VX_REQUIRE(smem <= 200 * 1024, "vx_temporal_attention: smem %zu", smem);
   const long long items = (long long)b * HW * (heads / G);
   const unsigned grid = (unsigned)((items + 3) / 4);
-  auto st = (cudaStream_t)stream;
 #define TA_LAUNCH(HD)                                                                                               \
   do {                                                                                                              \
     static bool cfg = false;                                                                                        \
@@ -311,6 +451,20 @@ extern "C" int vx_smallkv_attention(const void* q, long long ldq, const void* k,
   VX_REQUIRE(hd % 8 == 0 && Lk >= 1 && Lk <= 8, "vx_smallkv_attention: hd=%d Lk=%d", hd, Lk);
   SmallKvArgs a{(const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, ldkv,
                 (__nv_bfloat16*)out, ldo, rows, rows_per_frame, heads, hd, Lk, 1.0f / sqrtf((float)hd)};
+  auto st = (cudaStream_t)stream;
+  if (rows_per_frame % 16 == 0 && rows % 16 == 0 && !getenv("VX_SMALLKV_V1") &&
+      (hd == 8 || hd == 40 || hd == 80 || hd == 160)) {
+    const long long warps = rows / 16 * heads;
+    const unsigned grid_m = (unsigned)((warps + 3) / 4);
+    switch (hd) {
+      case 8: smallkv_attn_mma_kernel<8><<<grid_m, 128, 0, st>>>(a); break;
+      case 40: smallkv_attn_mma_kernel<40><<<grid_m, 128, 0, st>>>(a); break;
+      case 80: smallkv_attn_mma_kernel<80><<<grid_m, 128, 0, st>>>(a); break;
+      default: smallkv_attn_mma_kernel<160><<<grid_m, 128, 0, st>>>(a); break;
+    }
+    VX_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   const long long n = rows * heads;
   smallkv_attn_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(a);
   VX_CHECK_CUDA(cudaGetLastError());

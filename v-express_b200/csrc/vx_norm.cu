@@ -291,6 +291,99 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restri
   }
 }
 
+
+// ---- LayerNorm for C = 40 * LPR (320 / 640 / 1280, the three transformer widths): LPR lanes per row and exactly
+// five 16-byte vectors per lane (no idle lanes, 128-byte coalesced segments), 32 / LPR rows per warp pass.  gamma and
+// beta live in registers for the whole grid-stride loop: the per-row version above spends four parameter loads per
+// data load on them.
+template <int LPR>
+__global__ void __launch_bounds__(256) layernorm5_kernel(const __nv_bfloat16* __restrict__ x, long long ldx,
+                                                         long long rows, const float* __restrict__ gamma,
+                                                         const float* __restrict__ beta, float eps,
+                                                         const float* __restrict__ pe, int pe_rows_per_frame,
+                                                         int pe_frames, __nv_bfloat16* __restrict__ out, long long ldo) {
+  constexpr int RPW = 32 / LPR;
+  constexpr int C = LPR * 40;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LPR, l = lane % LPR;
+  const long long nwarps = (long long)gridDim.x * 8;
+  const long long ngroups = (rows + RPW - 1) / RPW;
+  float g[5][8], b[5][8];
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    const int c = (l + i * LPR) * 8;
+    const float4 g0 = *reinterpret_cast<const float4*>(gamma + c), g1 = *reinterpret_cast<const float4*>(gamma + c + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(beta + c), b1 = *reinterpret_cast<const float4*>(beta + c + 4);
+    g[i][0] = g0.x; g[i][1] = g0.y; g[i][2] = g0.z; g[i][3] = g0.w; g[i][4] = g1.x; g[i][5] = g1.y; g[i][6] = g1.z; g[i][7] = g1.w;
+    b[i][0] = b0.x; b[i][1] = b0.y; b[i][2] = b0.z; b[i][3] = b0.w; b[i][4] = b1.x; b[i][5] = b1.y; b[i][6] = b1.z; b[i][7] = b1.w;
+  }
+  // two row sets per iteration (rows r and r + RPW): twice the bytes in flight for the same parameter registers
+  const long long npairs = (ngroups + 1) / 2;
+  for (long long grp = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); grp < npairs; grp += nwarps) {
+    long long row[2];
+    bool ok[2];
+    uint4 u[2][5];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      row[r] = (grp * 2 + r) * RPW + sub;
+      ok[r] = row[r] < rows;
+      const __nv_bfloat16* xp = x + (ok[r] ? row[r] : 0) * ldx + l * 8;
+#pragma unroll
+      for (int i = 0; i < 5; ++i) u[r][i] = *reinterpret_cast<const uint4*>(xp + i * LPR * 8);
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        const uint32_t w4[4] = {u[r][i].x, u[r][i].y, u[r][i].z, u[r][i].w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float2 v = unpack_bf16(w4[t]);
+          s += v.x + v.y;
+        }
+      }
+#pragma unroll
+      for (int o = LPR / 2; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      const float mean = s * (1.0f / C);
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        const uint32_t w4[4] = {u[r][i].x, u[r][i].y, u[r][i].z, u[r][i].w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float2 v = unpack_bf16(w4[t]);
+          const float d0 = v.x - mean, d1 = v.y - mean;
+          q = fmaf(d0, d0, q);
+          q = fmaf(d1, d1, q);
+        }
+      }
+#pragma unroll
+      for (int o = LPR / 2; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+      const float rstd = rsqrtf(q * (1.0f / C) + eps);
+      const float* perow = pe ? pe + (long long)((row[r] / pe_rows_per_frame) % pe_frames) * C + l * 8 : nullptr;
+      __nv_bfloat16* op = out + (ok[r] ? row[r] : 0) * ldo + l * 8;
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        const uint32_t w4[4] = {u[r][i].x, u[r][i].y, u[r][i].z, u[r][i].w};
+        float y[8];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float2 v = unpack_bf16(w4[t]);
+          y[2 * t] = (v.x - mean) * rstd * g[i][2 * t] + b[i][2 * t];
+          y[2 * t + 1] = (v.y - mean) * rstd * g[i][2 * t + 1] + b[i][2 * t + 1];
+        }
+        if (perow) {
+          const float4 p0 = *reinterpret_cast<const float4*>(perow + i * LPR * 8);
+          const float4 p1 = *reinterpret_cast<const float4*>(perow + i * LPR * 8 + 4);
+          y[0] += p0.x; y[1] += p0.y; y[2] += p0.z; y[3] += p0.w; y[4] += p1.x; y[5] += p1.y; y[6] += p1.z; y[7] += p1.w;
+        }
+        if (ok[r]) store8(op + i * LPR * 8, y);
+      }
+    }
+  }
+}
+
 }  // namespace vx
 
 using namespace vx;
@@ -361,6 +454,22 @@ extern "C" int vx_layernorm(const void* x, long long ldx, long long rows, int C,
   const int V = C / 8;
   auto st = (cudaStream_t)stream;
   if (pe && (rows_per_frame <= 0 || pe_frames <= 0)) return fail("vx_layernorm: bad pe args");
+  if ((C == 320 || C == 640 || C == 1280) && ldx % 8 == 0 && ldo % 8 == 0 && !getenv("VX_LN_V1")) {
+    const int lpr = C / 40;
+    const long long groups = (rows + 32 / lpr - 1) / (32 / lpr);
+    long long nb = ((groups + 1) / 2 + 7) / 8;
+    if (nb > 148 * 4) nb = 148 * 4;   // one 256-thread block is resident per SM (parameter registers); 4 waves balance the tail
+    if (nb < 1) nb = 1;
+#define LN5_LAUNCH(LPR)                                                                                            \
+  layernorm5_kernel<LPR><<<(unsigned)nb, 256, 0, st>>>((const __nv_bfloat16*)x, ldx, rows, gamma, beta, eps, pe,  \
+                                                       rows_per_frame, pe_frames, (__nv_bfloat16*)out, ldo)
+    if (lpr == 8) LN5_LAUNCH(8);
+    else if (lpr == 16) LN5_LAUNCH(16);
+    else LN5_LAUNCH(32);
+#undef LN5_LAUNCH
+    VX_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
 #define LN_LAUNCH(MV)                                                                                            \
   layernorm_kernel<MV><<<(unsigned)blocks, threads, 0, st>>>((const __nv_bfloat16*)x, ldx, (int)rows, C, gamma, \
                                                              beta, eps, pe, rows_per_frame, pe_frames,          \
