@@ -52,3 +52,13 @@ for HW, C, heads in ((4096, 320, 8), (1024, 640, 8), (256, 1280, 8)):
     kv = torch.randn(b * f * 5, 2 * C, device=dev).bfloat16()
     row(f"smallkv_attention rows={rows} C={C}", rows * C * 2 * 2,
         lambda: ops.smallkv_attention(q, kv[:, :C], kv[:, C:], HW, heads, 5, out=out))
+
+# conv_in (4 -> 320 channels, 64x64 latents, 32 frames) with the kps-feature addend, as the UNet calls it
+xin = torch.randn(32, 4, 64, 64, device=dev).bfloat16()
+w = torch.randn(36, 320, device=dev)
+bias = torch.randn(320, device=dev)
+add = torch.randn(16 * 4096, 320, device=dev).bfloat16()
+af = (torch.arange(32, device=dev, dtype=torch.int32) % 16).contiguous()
+outc = torch.empty(32 * 4096, 320, device=dev, dtype=torch.bfloat16)
+row("conv_in NB=32 64x64 4->320 (+kps addend)", (32 * 4096 * 320 * 2) * 2,
+    lambda: ops.conv_in(xin, w, bias, 320, addend=add, add_frame=af, out=outc))

@@ -273,6 +273,8 @@ __device__ __forceinline__ float ex2_poly(float x) {
   return __uint_as_float(__float_as_uint(pl) + (__float_as_uint(t) << 23));   // scale by 2^round(x)
 }
 __device__ __forceinline__ void wg_bar_sync(int q) { asm volatile("bar.sync %0, 256;" ::"r"(q + 1) : "memory"); }
+// named barrier of the two warps (column halves) that share the rows of one TMEM lane quadrant: ids 3..10
+__device__ __forceinline__ void pair_bar_sync(int q, int qd) { asm volatile("bar.sync %0, 64;" ::"r"(3 + q * 4 + qd) : "memory"); }
 
 struct Fa2Args {
   int Nq, Nk, hd, hdp, kv_div, stages;
@@ -283,6 +285,9 @@ struct Fa2Args {
   long long ldo;
   int q_bytes, kv_bytes;  // per 128-row tile
   long long* trace;       // bring-up only (VX_FA_TRACE): clock64 stamps of CTA (0,0,0)
+  int stagger;            // clocks by which the softmax warps of query tile 1 start late (see the softmax loop)
+  int pair_sync;          // exchange the half-row maxima under a 64-thread pair barrier instead of the 256-thread tile barrier
+  int late_wait;          // p_tmem: wait for P.V(j-1) only right before P(j) is stored, not before the exponentials
 };
 
 #define FA_TR(slot) do { if (tr) tr[(j) * 16 + (slot)] = clock64(); } while (0)
@@ -461,6 +466,16 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
     const float c = p.scale_log2;
     uint8_t* pb0 = sP + q * p.pbufs * kP + row * 16 + half * 8 * 2048;
     long long* tr = (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && warp == 0 && lane == 0) ? p.trace : nullptr;
+    // The four softmax warps of an SM sub-partition (two per query tile) share one MUFU unit.  Started together, the
+    // two query tiles run in lock-step: all four warps sit in their exponential phase at the same time and the unit
+    // idles during everybody's load / max / barrier phases (clock64 timeline, profiles/tools/fa_trace.py).  Starting
+    // tile 1 half a period late makes the exponential phase of one tile overlap the other phases of the other tile.
+    if (q == 1 && p.stagger > 0) {
+      const long long t0 = clock64();
+      while (clock64() - t0 < p.stagger) {
+      }
+    }
+    const bool late_wait = p.p_tmem && p.late_wait;
     for (int j = 0; j < T; ++j) {
       mbar_wait(&s_full[q], (uint32_t)(j & 1));
       tc_fence_after();
@@ -482,12 +497,12 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
       float mx = fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3]));
       // combine with the other column half of the same rows (double-buffered slot: one barrier per tile suffices)
       my_x[(j & 1) * 512] = mx;
-      wg_bar_sync(q);
+      if (p.pair_sync) pair_bar_sync(q, qd); else wg_bar_sync(q);
       mx = fmaxf(mx, other_x[(j & 1) * 512]);
       FA_TR(2);
       // the P buffer of this tile was last read by P.V of tile j - pbufs
       uint8_t* pb = pb0 + (j % p.pbufs) * kP;
-      if (j >= p.pbufs) {
+      if (j >= p.pbufs && !late_wait) {
         mbar_wait(&pv_done[2 * q + j % p.pbufs], (uint32_t)((j / p.pbufs - 1) & 1));
         tc_fence_after();
       }
@@ -532,6 +547,12 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
             for (int i = 0; i < 4; ++i) pk[g * 16 + h * 4 + i] = pack_bf16(e[2 * i], e[2 * i + 1]);
           }
         }
+        FA_TR(6);
+        if (j >= p.pbufs && late_wait) {   // P(j) overwrites the tile P.V(j - pbufs) reads: wait only now
+          mbar_wait(&pv_done[2 * q + j % p.pbufs], (uint32_t)((j / p.pbufs - 1) & 1));
+          tc_fence_after();
+        }
+        FA_TR(7);
         tmem_st32(tp, pk);       // this warp's 64 keys = 32 packed columns of P(q)
         tmem_st_wait();
       } else {
@@ -574,12 +595,12 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
         l = lv;
         my_x[1024] = l;
       }
-      wg_bar_sync(q);
+      if (p.pair_sync) pair_bar_sync(q, qd); else wg_bar_sync(q);
       if (!(lc >= oc_begin && lc < oc_end)) l = other_x[1024];
     } else {
       // total row sum = the two column halves
       my_x[1024] = l;
-      wg_bar_sync(q);
+      if (p.pair_sync) pair_bar_sync(q, qd); else wg_bar_sync(q);
       l += other_x[1024];
     }
     const int qrow = q_pair * 256 + q * 128 + row;
@@ -699,6 +720,9 @@ extern "C" int vx_flash_attention(const void* q, long long ldq, const void* k, l
     a.q_bytes = 128 * hdp * 2;
     a.kv_bytes = 128 * hdp * 2;
     a.stages = 3;
+    a.stagger = getenv("VX_FA_STAGGER") ? atoi(getenv("VX_FA_STAGGER")) : 0;
+    a.pair_sync = getenv("VX_FA_PAIRSYNC") ? atoi(getenv("VX_FA_PAIRSYNC")) : 1;
+    a.late_wait = getenv("VX_FA_LATEWAIT") ? atoi(getenv("VX_FA_LATEWAIT")) : 0;
     a.trace = getenv("VX_FA_TRACE") ? (long long*)strtoull(getenv("VX_FA_TRACE"), nullptr, 10) : nullptr;
     auto need = [&](int st, int pb) { return (size_t)2 * a.q_bytes + (size_t)2 * st * a.kv_bytes + (size_t)2 * pb * 32768 + 6144 + 512 + 128; };
     // P in tensor memory whenever O (2 x hdp) + S (2 x 128) + P (2 x 64) columns fit the 512-column TMEM

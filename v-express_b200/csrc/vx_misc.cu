@@ -28,62 +28,98 @@ struct ConvInArgs {
 __device__ __forceinline__ float rbf16(float v) { return __bfloat162float(__float2bfloat16(v)); }
 
 template <int CIN>
-__global__ void conv_in_kernel(const ConvInArgs p) {
-  extern __shared__ float sw[];  // [Cin*9][Cout]: p.w is pre-transposed on the host side of the ABI (wt)
+__global__ void __launch_bounds__(256) conv_in_kernel(const ConvInArgs p) {
+  // Every thread owns 8 output channels of 4 horizontally adjacent pixels, so each weight read from shared memory
+  // feeds 4 FMAs (one pixel per thread left the kernel bound by shared-memory bandwidth, 1 LDS word per FMA).
+  // Weights sit in two planes [K][Cout/2] (channels 8v..8v+3 | 8v+4..8v+7 of vector v) so that consecutive lanes
+  // read consecutive 16-byte words.  p.w is pre-transposed on the host side of the ABI ([Cin*9][Cout]).
+  extern __shared__ float sw[];
   constexpr int K = CIN * 9;
-  for (int i = threadIdx.x; i < K * p.Cout; i += blockDim.x) sw[i] = p.wt[i];
+  const int half = p.Cout / 2;
+  for (int i = threadIdx.x; i < K * p.Cout; i += blockDim.x) {
+    const int k = i / p.Cout, c = i % p.Cout;
+    sw[((c & 4) ? K * half : 0) + k * half + (c >> 3) * 4 + (c & 3)] = p.wt[i];
+  }
   __syncthreads();
   const int vecs = p.Cout / 8;
-  const long long total = (long long)p.NB * p.H * p.W * vecs;
+  const int WQ = (p.W + 3) / 4;
+  const long long total = (long long)p.NB * p.H * WQ * vecs;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
     const int cv = (int)(idx % vecs);
-    const long long pix = idx / vecs;
-    const int x = (int)(pix % p.W);
-    const int y = (int)((pix / p.W) % p.H);
-    const int n = (int)(pix / ((long long)p.W * p.H));
-    float acc[8];
+    const long long quad = idx / vecs;
+    const int x0 = (int)(quad % WQ) * 4;
+    const int y = (int)((quad / WQ) % p.H);
+    const int n = (int)(quad / ((long long)WQ * p.H));
+    float acc[4][8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = p.bias ? p.bias[cv * 8 + i] : 0.f;
+    for (int i = 0; i < 8; ++i) {
+      const float bv = p.bias ? p.bias[cv * 8 + i] : 0.f;
 #pragma unroll
-    for (int t = 0; t < 9; ++t) {
-      const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
-      if (yy < 0 || yy >= p.H || xx < 0 || xx >= p.W) continue;
-      float vin[CIN];
+      for (int px = 0; px < 4; ++px) acc[px][i] = bv;
+    }
 #pragma unroll
-      for (int c = 0; c < CIN; ++c) vin[c] = __bfloat162float(p.in[n * p.sn + c * p.sc + yy * p.W + xx]);
-      if (p.pre_w) {
-        float tmp[CIN];
+    for (int dy = 0; dy < 3; ++dy) {
+      const int yy = y + dy - 1;
+      if (yy < 0 || yy >= p.H) continue;
+      float vin[6][CIN];   // columns x0-1 .. x0+4 of input row yy; zero outside the image (conv padding)
 #pragma unroll
-        for (int c = 0; c < CIN; ++c) tmp[c] = rbf16(p.pre_scale * vin[c]);
+      for (int cx = 0; cx < 6; ++cx) {
+        const int xx = x0 + cx - 1;
+        const bool valid = xx >= 0 && xx < p.W;
 #pragma unroll
-        for (int c = 0; c < CIN; ++c) {
-          float a = p.pre_b ? p.pre_b[c] : 0.f;
+        for (int c = 0; c < CIN; ++c)
+          vin[cx][c] = valid ? __bfloat162float(p.in[n * p.sn + c * p.sc + yy * p.W + xx]) : 0.f;
+        if (p.pre_w && valid) {
+          float tmp[CIN];
 #pragma unroll
-          for (int k = 0; k < CIN; ++k) a += p.pre_w[c * CIN + k] * tmp[k];
-          vin[c] = rbf16(a);
+          for (int c = 0; c < CIN; ++c) tmp[c] = rbf16(p.pre_scale * vin[cx][c]);
+#pragma unroll
+          for (int c = 0; c < CIN; ++c) {
+            float a = p.pre_b ? p.pre_b[c] : 0.f;
+#pragma unroll
+            for (int k = 0; k < CIN; ++k) a += p.pre_w[c * CIN + k] * tmp[k];
+            vin[cx][c] = rbf16(a);
+          }
         }
       }
 #pragma unroll
-      for (int c = 0; c < CIN; ++c) {
-        const float* wr = sw + (c * 9 + t) * p.Cout + cv * 8;
+      for (int dx = 0; dx < 3; ++dx) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] += vin[c] * wr[i];
+        for (int c = 0; c < CIN; ++c) {
+          const int k = c * 9 + dy * 3 + dx;
+          const float4 w0 = *reinterpret_cast<const float4*>(sw + k * half + cv * 4);
+          const float4 w1 = *reinterpret_cast<const float4*>(sw + K * half + k * half + cv * 4);
+          const float wr[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+          for (int px = 0; px < 4; ++px) {
+            const float v = vin[px + dx][c];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[px][i] += v * wr[i];
+          }
+        }
       }
     }
-    if (p.addend) {
-      const long long arow = (p.add_frame ? (long long)p.add_frame[n] : (long long)n) * p.H * p.W + (long long)y * p.W + x;
-      const uint4 u = *reinterpret_cast<const uint4*>(p.addend + arow * p.add_ld + cv * 8);
-      const uint32_t ww[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float2 t = unpack_bf16(ww[i]);
-        acc[2 * i] += t.x;
-        acc[2 * i + 1] += t.y;
+    for (int px = 0; px < 4; ++px) {
+      const int x = x0 + px;
+      if (x >= p.W) continue;
+      const long long pix = ((long long)n * p.H + y) * p.W + x;
+      if (p.addend) {
+        const long long arow = (p.add_frame ? (long long)p.add_frame[n] : (long long)n) * p.H * p.W + (long long)y * p.W + x;
+        const uint4 u = *reinterpret_cast<const uint4*>(p.addend + arow * p.add_ld + cv * 8);
+        const uint32_t ww[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 t = unpack_bf16(ww[i]);
+          acc[px][2 * i] += t.x;
+          acc[px][2 * i + 1] += t.y;
+        }
       }
+      *reinterpret_cast<uint4*>(p.out + pix * p.ldo + cv * 8) =
+          make_uint4(pack_bf16(acc[px][0], acc[px][1]), pack_bf16(acc[px][2], acc[px][3]),
+                     pack_bf16(acc[px][4], acc[px][5]), pack_bf16(acc[px][6], acc[px][7]));
     }
-    *reinterpret_cast<uint4*>(p.out + pix * p.ldo + cv * 8) = make_uint4(
-        pack_bf16(acc[0], acc[1]), pack_bf16(acc[2], acc[3]), pack_bf16(acc[4], acc[5]), pack_bf16(acc[6], acc[7]));
   }
 }
 
@@ -341,9 +377,9 @@ extern "C" int vx_conv_in(const void* in, long long sn, long long sc, int NB, in
     VX_CHECK_CUDA(cudaFuncSetAttribute(conv_in_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     cfg = true;
   }
-  const long long total = (long long)NB * H * W * (Cout / 8);
+  const long long total = (long long)NB * H * ((W + 3) / 4) * (Cout / 8);
   long long blocks = (total + 255) / 256;
-  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks > 148 * 4) blocks = 148 * 4;
   conv_in_kernel<4><<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(a);
   VX_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -112,21 +112,41 @@ __global__ void gn_apply_kernel(const GnApplyArgs p) {
   float* gmean = sm + 2 * C;
   float* grstd = gmean + p.G;
   const int n = blockIdx.y;
-  for (int g = threadIdx.x; g < p.G; g += blockDim.x) {
-    // Chan et al. parallel-variance merge of the S partials, always in the same order (deterministic)
-    float cnt = 0.f, mean = 0.f, m2 = 0.f;
-    for (int s = 0; s < p.S; ++s) {
-      const float* q = p.partial + ((long long)(n * p.S + s) * p.G + g) * 3;
-      const float cb = q[0];
-      if (cb <= 0.f) continue;
-      const float tot = cnt + cb;
-      const float delta = q[1] - mean;
-      mean += delta * (cb / tot);
-      m2 += q[2] + delta * delta * (cnt * cb / tot);
-      cnt = tot;
+  {
+    // Chan et al. parallel-variance merge of the S partials of every group: one warp per group, lane s holds partial
+    // s (and s + 32), then a fixed shuffle-down tree -- the same order in every CTA and every run (deterministic).
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nfull = blockDim.x >> 5;
+    if (warp < nfull) {
+      for (int g = warp; g < p.G; g += nfull) {
+        float cnt = 0.f, mean = 0.f, m2 = 0.f;
+        for (int s = lane; s < p.S; s += 32) {
+          const float* q = p.partial + ((long long)(n * p.S + s) * p.G + g) * 3;
+          const float cb = q[0], mb = q[1], qb = q[2];
+          if (cb > 0.f) {
+            const float tot = cnt + cb, delta = mb - mean;
+            mean += delta * (cb / tot);
+            m2 += qb + delta * delta * (cnt * cb / tot);
+            cnt = tot;
+          }
+        }
+#pragma unroll
+        for (int off = 16; off; off >>= 1) {
+          const float cb = __shfl_down_sync(0xffffffffu, cnt, off);
+          const float mb = __shfl_down_sync(0xffffffffu, mean, off);
+          const float qb = __shfl_down_sync(0xffffffffu, m2, off);
+          if (cb > 0.f) {
+            const float tot = cnt + cb, delta = mb - mean;
+            mean += delta * (cb / tot);
+            m2 += qb + delta * delta * (cnt * cb / tot);
+            cnt = tot;
+          }
+        }
+        if (lane == 0) {
+          gmean[g] = mean;
+          grstd[g] = rsqrtf(m2 / cnt + p.eps);
+        }
+      }
     }
-    gmean[g] = mean;
-    grstd[g] = rsqrtf(m2 / cnt + p.eps);
   }
   __syncthreads();
   const int cpg = C / p.G;
@@ -431,10 +451,11 @@ extern "C" int vx_groupnorm_apply(const void* x1, long long ld1, int C1, const v
   VX_REQUIRE(C1 % 8 == 0 && C2 % 8 == 0 && C % G == 0, "vx_groupnorm_apply: bad C1=%d C2=%d G=%d", C1, C2, G);
   GnApplyArgs a{(const __nv_bfloat16*)x1, ld1, C1, (const __nv_bfloat16*)x2, ld2, C2, HW, G, S, partial, gamma, beta,
                 eps, silu, (__nv_bfloat16*)out, ldo, 0};
-  // ~64 KB of activations per CTA
-  int chunk = (32768 / C);
+  VX_REQUIRE(S >= 1, "vx_groupnorm_apply: S=%d", S);
+  // same partition as the statistics pass: S chunks per frame, sized by the caller so that NB * S CTAs fill the
+  // SMs evenly in one wave (a fixed 64 KB chunk left a 10 % second wave at the 64x64 level)
+  int chunk = (HW + S - 1) / S;
   if (chunk < 1) chunk = 1;
-  if (chunk > HW) chunk = HW;
   a.chunk = chunk;
   const size_t smem = (size_t)(2 * C + 2 * G) * sizeof(float);
   int Rr;
@@ -454,7 +475,8 @@ extern "C" int vx_layernorm(const void* x, long long ldx, long long rows, int C,
   const int V = C / 8;
   auto st = (cudaStream_t)stream;
   if (pe && (rows_per_frame <= 0 || pe_frames <= 0)) return fail("vx_layernorm: bad pe args");
-  if ((C == 320 || C == 640 || C == 1280) && ldx % 8 == 0 && ldo % 8 == 0 && !getenv("VX_LN_V1")) {
+  // (with a positional-encoding row to fetch per row the one-warp-per-row kernel, with its 8x occupancy, is as fast)
+  if ((C == 320 || C == 640 || C == 1280) && !pe && ldx % 8 == 0 && ldo % 8 == 0 && !getenv("VX_LN_V1")) {
     const int lpr = C / 40;
     const long long groups = (rows + 32 / lpr - 1) / (32 / lpr);
     long long nb = ((groups + 1) / 2 + 7) / 8;

@@ -160,7 +160,8 @@ def smallkv_attention(q, k, v, rows_per_frame, heads, Lk, out=None):
 
 # ----------------------------------------------------------------------------- norms / activations
 def _gn_S(NB, HW):
-    s = max(1, min(HW // 32, (148 * 6) // max(NB, 1)))
+    # NB * S CTAs = 8 per SM in one balanced wave (both GroupNorm kernels use the same partition)
+    s = max(1, min(HW // 32, (148 * 8) // max(NB, 1)))
     return max(1, min(s, 64))
 
 
