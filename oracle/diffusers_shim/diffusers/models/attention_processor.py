@@ -55,6 +55,14 @@ class AttnProcessor:
 AttentionProcessor = AttnProcessor2_0
 
 
+class AttnAddedKVProcessor:  # name only (unet_2d_condition.py:11-17 imports it; SD-1.5 never selects it)
+    pass
+
+
+ADDED_KV_ATTENTION_PROCESSORS = (AttnAddedKVProcessor,)
+CROSS_ATTENTION_PROCESSORS = (AttnProcessor, AttnProcessor2_0)
+
+
 class Attention(nn.Module):
     def __init__(self, query_dim, cross_attention_dim=None, heads=8, dim_head=64, dropout=0.0, bias=False,
                  upcast_attention=False, upcast_softmax=False, norm_num_groups=None, eps=1e-5,

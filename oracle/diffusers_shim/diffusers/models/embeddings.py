@@ -35,3 +35,25 @@ class TimestepEmbedding(nn.Module):
 class SinusoidalPositionalEmbedding(nn.Module):
     def __init__(self, *a, **k):
         raise NotImplementedError
+
+
+def _unused(name):
+    class _U(nn.Module):
+        def __init__(self, *a, **k):
+            raise NotImplementedError(name + ": not used by the SD-1.5 ReferenceNet")
+    _U.__name__ = name
+    return _U
+
+
+# names imported by modules/unet_2d_condition.py:18-33 and transformer_2d.py:7-10 but never constructed for SD-1.5
+GaussianFourierProjection = _unused("GaussianFourierProjection")
+ImageHintTimeEmbedding = _unused("ImageHintTimeEmbedding")
+ImageProjection = _unused("ImageProjection")
+ImageTimeEmbedding = _unused("ImageTimeEmbedding")
+TextImageProjection = _unused("TextImageProjection")
+TextImageTimeEmbedding = _unused("TextImageTimeEmbedding")
+TextTimeEmbedding = _unused("TextTimeEmbedding")
+PositionNet = _unused("PositionNet")
+CaptionProjection = _unused("CaptionProjection")
+ImagePositionalEmbeddings = _unused("ImagePositionalEmbeddings")
+PatchEmbed = _unused("PatchEmbed")

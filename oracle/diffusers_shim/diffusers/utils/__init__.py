@@ -30,3 +30,26 @@ class BaseOutput(OrderedDict):
 
 def is_accelerate_available():
     return False
+
+
+USE_PEFT_BACKEND = False
+
+
+def deprecate(*a, **k):
+    pass
+
+
+def scale_lora_layers(model, weight):
+    pass
+
+
+def unscale_lora_layers(model, weight=None):
+    pass
+
+
+def is_torch_version(op, version):
+    import operator
+    import torch
+    from packaging import version as V
+    ops = {">": operator.gt, ">=": operator.ge, "==": operator.eq, "<": operator.lt, "<=": operator.le, "!=": operator.ne}
+    return ops[op](V.parse(torch.__version__.split("+")[0]), V.parse(version))

@@ -7,9 +7,11 @@ box never runs this.  The reference's files are imported verbatim from where the
   * ``modules/{unet_3d,unet_3d_blocks,transformer_3d,attention,motion_module,resnet,
      mutual_self_attention}.py``           (over oracle/diffusers_shim)        -> unet_small.pt
   * ``pipelines/v_express_pipeline.py``    (over the shim; DDIM + VAE decoder restated) -> pipeline_small.pt
+  * ``modules/{unet_2d_condition,unet_2d_blocks,transformer_2d,attention}.py`` + the write-mode hooks of
+     ``mutual_self_attention.py``          (ReferenceNet)        -> refnet_small.pt
 
 Inputs/weights are NOT stored: they are regenerated from seeds by ``oracle.vx_oracle.synth_*``.
-Usage:  python oracle/gen_golden.py
+Usage:  python oracle/gen_golden.py [context ddim unet pipeline refnet]   (default: all)
 """
 import importlib
 import importlib.util
@@ -211,6 +213,55 @@ def gen_pipeline(msa, unet3d, pipe):
     print("pipeline_small.pt: video", tuple(video.shape), "latents absmean", captured["latents"].abs().mean().item())
 
 
+def gen_refnet(msa, unet3d):
+    """ReferenceNet write pass exactly as the pipeline drives it (v_express_pipeline.py:451-457,501-509): the
+    reference's UNet2DConditionModel under a write-mode ReferenceAttentionControl at timestep 0 with a zero text
+    token, then the reference's own ``reader.update(writer, do_cfg)`` into a reference UNet3D."""
+    u2 = importlib.import_module("modules.unet_2d_condition")
+    cfg = O.small_cfg()
+    sd = O.synth_state_dict(O.refnet_param_shapes(cfg), seed=4321)
+    net = u2.UNet2DConditionModel(
+        sample_size=64, in_channels=4, out_channels=4,
+        down_block_types=("CrossAttnDownBlock2D", "CrossAttnDownBlock2D", "CrossAttnDownBlock2D", "DownBlock2D"),
+        up_block_types=("UpBlock2D", "CrossAttnUpBlock2D", "CrossAttnUpBlock2D", "CrossAttnUpBlock2D"),
+        block_out_channels=cfg["block_out_channels"], layers_per_block=2, cross_attention_dim=cfg["cross_attention_dim"],
+        attention_head_dim=8, norm_num_groups=32, norm_eps=1e-5)
+    ref_sd = net.state_dict()
+    assert set(ref_sd) == set(sd), sorted(set(ref_sd) ^ set(sd))[:10]
+    for k in ref_sd:
+        assert tuple(ref_sd[k].shape) == tuple(sd[k].shape), k
+    net.load_state_dict(sd, strict=True)
+    net.eval()
+    h = 16
+    ref_latents = torch.randn(1, 4, h, h, generator=torch.Generator().manual_seed(77))
+    writer = msa.ReferenceAttentionControl(net, do_classifier_free_guidance=True, mode="write", batch_size=1,
+                                           fusion_blocks="full")
+    with torch.no_grad():
+        out = net(ref_latents, timestep=0, encoder_hidden_states=torch.zeros(1, 1, cfg["cross_attention_dim"]),
+                  return_dict=False)[0]
+    # hand the banks to a reference UNet3D reader with the reference's own update()
+    unet = build_reference_unet(unet3d, cfg, O.synth_state_dict(O.unet_param_shapes(cfg), seed=1234))
+    reader = msa.ReferenceAttentionControl(unet, do_classifier_free_guidance=True, mode="read", batch_size=1,
+                                           fusion_blocks="full")
+    reader.update(writer, True, dtype=torch.float32)
+    from modules.attention import TemporalBasicTransformerBlock
+    mods = [m for m in msa.torch_dfs(unet) if isinstance(m, TemporalBasicTransformerBlock)]
+    mods = sorted(mods, key=lambda x: -x.norm1.normalized_shape[0])
+    names = {id(m): n for n, m in unet.named_modules()}
+    order = [names[id(m)].replace(".transformer_blocks.0", "") for m in mods]
+    assert order == O.bank_order(cfg), (order, O.bank_order(cfg))
+    banks = []
+    for m in mods:
+        assert len(m.bank) == 1
+        bk = m.bank[0]
+        assert bk.shape[0] == 2 and torch.count_nonzero(bk[0]).item() == 0   # CFG: [zeros | bank] (:357-359)
+        banks.append(bk[1:].clone())
+    torch.save(dict(cfg=cfg, seed_weights=4321, seed_latents=77, h=h, bank_order=order, banks=banks, out=out),
+               os.path.join(GOLD, "refnet_small.pt"))
+    print("refnet_small.pt:", len(banks), "banks,", [tuple(b.shape) for b in banks[:1] + banks[-1:]],
+          "out absmean", out.abs().mean().item())
+
+
 def gen_ddim():
     """Known-answer values of the restated DDIM -- self-pins, cross-checked
     against the constants quoted in the survey."""
@@ -232,7 +283,14 @@ if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
     msa, unet3d, ctx, pipe = import_reference()
-    gen_context(ctx)
-    gen_ddim()
-    gen_unet(msa, unet3d)
-    gen_pipeline(msa, unet3d, pipe)
+    which = set(sys.argv[1:]) or {"context", "ddim", "unet", "pipeline", "refnet"}
+    if "context" in which:
+        gen_context(ctx)
+    if "ddim" in which:
+        gen_ddim()
+    if "unet" in which:
+        gen_unet(msa, unet3d)
+    if "pipeline" in which:
+        gen_pipeline(msa, unet3d, pipe)
+    if "refnet" in which:
+        gen_refnet(msa, unet3d)

@@ -423,6 +423,178 @@ def unet_forward(sd: Dict[str, Tensor], cfg, sample: Tensor, timestep, enc: Tens
 
 
 # --------------------------------------------------------------------------------------
+# ReferenceNet write pass: SD-1.5 UNet2DConditionModel at t = 0 with a zero text token,
+# every BasicTransformerBlock appending norm2(h) to its bank
+# --------------------------------------------------------------------------------------
+
+def transformer_2d_write(sd, p, x, enc, heads, groups):
+    """modules/transformer_2d.py:216-399 (continuous input, conv projections) around the write branch of the
+    hacked BasicTransformerBlock forward (modules/mutual_self_attention.py:127-130,145-174, feed-forward tail
+    :270-283).  x (B,C,h,w), enc (B,1,cross) -> (output (B,C,h,w), bank (B,N,C) = norm2(h + attn1(norm1(h))))."""
+    B, C, H, W = x.shape
+    res = x
+    h = group_norm(sd, p + ".norm", x, groups, 1e-6)
+    h = conv(sd, p + ".proj_in", h, padding=0)
+    h = h.permute(0, 2, 3, 1).reshape(B, H * W, C)
+    tb = p + ".transformer_blocks.0"
+    n = layer_norm(sd, tb + ".norm1", h)
+    h = attention(sd, tb + ".attn1", n, n, heads) + h
+    n = layer_norm(sd, tb + ".norm2", h)
+    bank = n.clone()
+    h = attention(sd, tb + ".attn2", n, enc, heads) + h
+    h = feed_forward(sd, tb + ".ff", layer_norm(sd, tb + ".norm3", h)) + h
+    h = h.reshape(B, H, W, C).permute(0, 3, 1, 2)
+    h = conv(sd, p + ".proj_out", h, padding=0)
+    return h + res, bank
+
+
+def refnet_forward(sd: Dict[str, Tensor], cfg, ref_latents: Tensor, taps: Optional[dict] = None):
+    """The reference's ReferenceNet call (pipelines/v_express_pipeline.py:502-508):
+    ``reference_net(ref_latents, timestep=0, encoder_hidden_states=zeros(1,1,cross))`` with the write-mode hooks
+    installed -- modules/unet_2d_condition.py:877-1313 (forward), unet_2d_blocks.py (CrossAttnDownBlock2D :630-676,
+    DownBlock2D :745-775, UNetMidBlock2DCrossAttn :470-507, UpBlock2D :1027-1073, CrossAttnUpBlock2D :890-961).
+
+    ref_latents (1,4,h,w) -> (banks, out): ``banks`` is the list of the 16 (1,N,C) bank tensors in PAIRING order
+    (``bank_order``: stable sort of the writer's dfs order by -dim, mutual_self_attention.py:349-351 -- the writer
+    registers down_blocks, up_blocks, mid_block in the same order as the reader), ``out`` the (unused) UNet output."""
+    B, cin, H, W = ref_latents.shape
+    boc = cfg["block_out_channels"]
+    heads, groups, eps = cfg["heads"], cfg["norm_num_groups"], cfg["norm_eps"]
+    enc = torch.zeros(B, 1, cfg["cross_attention_dim"], dtype=ref_latents.dtype)
+    bank_of: Dict[str, Tensor] = {}
+
+    def tap(name, t):
+        if taps is not None:
+            taps[name] = t.detach().clone()
+
+    t = torch.zeros(B, dtype=torch.long)                       # timestep=0 (unet_2d_condition.py:1010-1030)
+    t_emb = timestep_embedding(t, boc[0]).to(ref_latents.dtype)
+    emb = _lin(sd, "time_embedding.linear_2", F.silu(_lin(sd, "time_embedding.linear_1", t_emb)))
+
+    def attn(p, x):
+        x, bank_of[p] = transformer_2d_write(sd, p, x, enc, heads, groups)
+        return x
+
+    x = conv(sd, "conv_in", ref_latents)
+    tap("conv_in", x)
+    skips = [x]
+    for i in range(4):
+        p = f"down_blocks.{i}"
+        for j in range(cfg["layers_per_block"]):
+            x = resnet_block(sd, f"{p}.resnets.{j}", x, emb, groups, eps)
+            if i < 3:
+                x = attn(f"{p}.attentions.{j}", x)
+            skips.append(x)
+        if i < 3:
+            x = conv(sd, f"{p}.downsamplers.0.conv", x, stride=2, padding=1)
+            skips.append(x)
+        tap(p, x)
+    x = resnet_block(sd, "mid_block.resnets.0", x, emb, groups, eps)
+    x = attn("mid_block.attentions.0", x)
+    x = resnet_block(sd, "mid_block.resnets.1", x, emb, groups, eps)
+    tap("mid_block", x)
+    for i in range(4):
+        p = f"up_blocks.{i}"
+        for j in range(cfg["layers_per_block"] + 1):
+            x = torch.cat([x, skips.pop()], dim=1)
+            x = resnet_block(sd, f"{p}.resnets.{j}", x, emb, groups, eps)
+            if i > 0:
+                x = attn(f"{p}.attentions.{j}", x)
+        if i < 3:
+            x = F.interpolate(x, scale_factor=2.0, mode="nearest")
+            x = conv(sd, f"{p}.upsamplers.0.conv", x)
+        tap(p, x)
+    # the reference resets ``self.conv_norm_out = None`` after building it (unet_2d_condition.py:650), so its
+    # state_dict has no conv_norm_out and forward (:1301-1304) applies conv_out directly
+    x = conv(sd, "conv_out", x)
+    return [bank_of[n] for n in bank_order(cfg)], x
+
+
+def refnet_param_shapes(cfg) -> Dict[str, tuple]:
+    """state_dict key -> shape of the reference's UNet2DConditionModel in the SD-1.5 configuration
+    (modules/unet_2d_condition.py:69-660; 684 tensors, 859.5 M parameters at full width)."""
+    boc = cfg["block_out_channels"]
+    ted = boc[0] * 4
+    cross = cfg["cross_attention_dim"]
+    S: Dict[str, tuple] = {}
+
+    def conv_(p, co, ci, k):
+        S[p + ".weight"] = (co, ci, k, k)
+        S[p + ".bias"] = (co,)
+
+    def lin_(p, co, ci, bias=True):
+        S[p + ".weight"] = (co, ci)
+        if bias:
+            S[p + ".bias"] = (co,)
+
+    def norm_(p, c):
+        S[p + ".weight"] = (c,)
+        S[p + ".bias"] = (c,)
+
+    def resnet_(p, ci, co):
+        norm_(p + ".norm1", ci)
+        conv_(p + ".conv1", co, ci, 3)
+        lin_(p + ".time_emb_proj", co, ted)
+        norm_(p + ".norm2", co)
+        conv_(p + ".conv2", co, co, 3)
+        if ci != co:
+            conv_(p + ".conv_shortcut", co, ci, 1)
+
+    def attn_(p, c, kv):
+        lin_(p + ".to_q", c, c, False)
+        lin_(p + ".to_k", c, kv, False)
+        lin_(p + ".to_v", c, kv, False)
+        lin_(p + ".to_out.0", c, c)
+
+    def t2d_(p, c):
+        norm_(p + ".norm", c)
+        conv_(p + ".proj_in", c, c, 1)
+        tb = p + ".transformer_blocks.0"
+        norm_(tb + ".norm1", c)
+        attn_(tb + ".attn1", c, c)
+        norm_(tb + ".norm2", c)
+        attn_(tb + ".attn2", c, cross)
+        norm_(tb + ".norm3", c)
+        lin_(tb + ".ff.net.0.proj", 8 * c, c)
+        lin_(tb + ".ff.net.2", c, 4 * c)
+        conv_(p + ".proj_out", c, c, 1)
+
+    conv_("conv_in", boc[0], cfg["in_channels"], 3)
+    lin_("time_embedding.linear_1", ted, boc[0])
+    lin_("time_embedding.linear_2", ted, ted)
+    out_c = boc[0]
+    for i in range(4):
+        in_c, out_c = out_c, boc[i]
+        for j in range(cfg["layers_per_block"]):
+            resnet_(f"down_blocks.{i}.resnets.{j}", in_c if j == 0 else out_c, out_c)
+            if i < 3:
+                t2d_(f"down_blocks.{i}.attentions.{j}", out_c)
+        if i < 3:
+            conv_(f"down_blocks.{i}.downsamplers.0.conv", out_c, out_c, 3)
+    c = boc[-1]
+    resnet_("mid_block.resnets.0", c, c)
+    t2d_("mid_block.attentions.0", c)
+    resnet_("mid_block.resnets.1", c, c)
+    rev = list(reversed(boc))
+    out_c = rev[0]
+    for i in range(4):
+        prev_out = out_c
+        out_c = rev[i]
+        in_c = rev[min(i + 1, 3)]
+        n = cfg["layers_per_block"] + 1
+        for j in range(n):
+            skip_c = in_c if j == n - 1 else out_c
+            res_in = prev_out if j == 0 else out_c
+            resnet_(f"up_blocks.{i}.resnets.{j}", res_in + skip_c, out_c)
+            if i > 0:
+                t2d_(f"up_blocks.{i}.attentions.{j}", out_c)
+        if i < 3:
+            conv_(f"up_blocks.{i}.upsamplers.0.conv", out_c, out_c, 3)
+    conv_("conv_out", cfg["out_channels"], boc[0], 3)     # no conv_norm_out: see refnet_forward
+    return S
+
+
+# --------------------------------------------------------------------------------------
 # AutoencoderKL decoder (diffusers 0.29.2, sd-vae-ft-mse config; SURVEY Appendix B.6)
 # --------------------------------------------------------------------------------------
 

@@ -91,3 +91,29 @@ def test_pipeline_matches_reference(golden_dir):
         video = O.decode_latents(vsd, vcfg, final)
     assert video.shape == g["video"].shape and video.dtype == torch.float32
     torch.testing.assert_close(video, g["video"].float(), atol=2e-3, rtol=0)
+
+
+def test_refnet_param_layout_full_width():
+    S = O.refnet_param_shapes(O.DEFAULT_CFG)          # SD-1.5 UNet2D minus the conv_norm_out the reference drops
+    assert len(S) == 684
+    assert sum(int(np.prod(v)) for v in S.values()) == 859520964 - 640
+    assert "conv_norm_out.weight" not in S           # modules/unet_2d_condition.py:650
+    assert S["up_blocks.1.resnets.2.conv1.weight"] == (1280, 1920, 3, 3)
+    assert S["down_blocks.0.attentions.0.transformer_blocks.0.attn2.to_k.weight"] == (320, 768)
+
+
+def test_refnet_write_pass_matches_reference(golden_dir):
+    """the 16 banks the hot path consumes, produced by the reference's own UNet2D + write hooks
+    + ``update`` (oracle/gen_golden.py:gen_refnet), against the restated write pass."""
+    g = torch.load(os.path.join(golden_dir, "refnet_small.pt"), weights_only=False)
+    cfg = g["cfg"]
+    sd = O.synth_state_dict(O.refnet_param_shapes(cfg), g["seed_weights"])
+    x = torch.randn(1, 4, g["h"], g["h"], generator=torch.Generator().manual_seed(g["seed_latents"]))
+    assert g["bank_order"] == O.bank_order(cfg)
+    with torch.no_grad():
+        banks, out = O.refnet_forward(sd, cfg, x)
+    assert len(banks) == len(g["banks"]) == 16
+    for name, a, b in zip(g["bank_order"], banks, g["banks"]):
+        assert a.shape == b.shape, name
+        torch.testing.assert_close(a, b, atol=2e-4, rtol=1e-4, msg=lambda m: f"{name}: {m}")
+    torch.testing.assert_close(out, g["out"], atol=2e-4, rtol=1e-4)
