@@ -139,3 +139,48 @@ def test_overlap_allreduce_bit_identical_two_ranks():
         p.join(120)
         assert p.exitcode == 0
     assert ret.get(timeout=5) is True
+
+
+def test_refnet_layout_and_writer_pairing_cpu():
+    """ReferenceNet mirror: reference state_dict layout, registration order (down, up, mid) and writer -> reader pairing
+    of ``ReferenceAttentionControl.update`` (reference modules/mutual_self_attention.py:321-363) without any compute."""
+    import torch
+    from oracle import vx_oracle as O
+    from vexpress_b200.modules import ReferenceAttentionControl, UNet2DConditionModel, UNet3DConditionModel
+    from vexpress_b200.modules.unet_3d import attention_block_order
+    cfg = O.small_cfg()
+    net = UNet2DConditionModel(block_out_channels=cfg["block_out_channels"], cross_attention_dim=cfg["cross_attention_dim"])
+    S = O.refnet_param_shapes(cfg)
+    sd = net.state_dict()
+    assert set(sd) == set(S) and all(tuple(sd[k].shape) == tuple(S[k]) for k in S)
+    tops = [k.split(".")[0] for k in sd]
+    assert tops.index("up_blocks") < tops.index("mid_block")          # the reference registers mid_block last
+    with __import__("pytest").raises(ValueError):
+        UNet2DConditionModel(use_linear_projection=True)
+    writer = ReferenceAttentionControl(net, mode="write", fusion_blocks="full", do_classifier_free_guidance=True)
+    assert net.write_banks
+    blocks = net.writer_blocks()
+    for i, b in enumerate(blocks):       # tag every bank with its dfs index
+        c = b.norm1.normalized_shape[0]
+        b.bank.append(torch.full((1, 4, c), float(i + 1)))
+    unet = UNet3DConditionModel(
+        block_out_channels=cfg["block_out_channels"], cross_attention_dim=cfg["cross_attention_dim"],
+        use_inflated_groupnorm=True, use_motion_module=True, motion_module_mid_block=True, motion_module_type="Vanilla",
+        motion_module_kwargs=dict(num_attention_heads=8, num_transformer_block=1,
+                                  attention_block_types=["Temporal_Self", "Temporal_Self"],
+                                  temporal_position_encoding=True, temporal_position_encoding_max_len=32,
+                                  temporal_attention_dim_div=1))
+    reader = ReferenceAttentionControl(unet, mode="read", fusion_blocks="full", do_classifier_free_guidance=True)
+    reader.update(writer, True, dtype=torch.float32)
+    mods = dict(unet.named_modules())
+    names = attention_block_order(unet)
+    assert [n.replace(".transformer_blocks.0", "") for n in names] == O.bank_order(cfg)
+    # same-named blocks pair up: writer dfs index i -> reader block with the same module path
+    from vexpress_b200.modules.unet_2d_condition import writer_block_names
+    wnames = writer_block_names()
+    for n in names:
+        bank = mods[n].bank[0]
+        assert bank.shape[0] == 2 and torch.count_nonzero(bank[0]).item() == 0
+        assert bank[1, 0, 0].item() == float(wnames.index(n) + 1), n
+    writer.clear()
+    assert all(len(b.bank) == 0 for b in blocks)

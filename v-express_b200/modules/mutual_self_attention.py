@@ -1,4 +1,4 @@
-"""``ReferenceAttentionControl`` for the B200 UNet: same constructor / ``update`` / ``clear`` API as the
+"""``ReferenceAttentionControl`` for the B200 UNets: same constructor / ``update`` / ``clear`` API as the
 reference (modules/mutual_self_attention.py:18-55, 321-387), without monkey-patching ``forward``.
 
 The reference installs a closure on every transformer block and keeps the reference features in
@@ -12,6 +12,7 @@ from typing import List
 
 import torch
 
+from .unet_2d_condition import UNet2DConditionModel
 from .unet_3d import TemporalBasicTransformerBlock, UNet3DConditionModel, attention_block_order
 
 
@@ -48,6 +49,14 @@ class ReferenceAttentionControl:
             unet.audio_attention_weight = float(audio_attention_weight)
             for blk in self._reader_blocks():
                 blk.bank = []
+        elif isinstance(unet, UNet2DConditionModel):
+            if mode != "write":
+                raise ValueError("the B200 ReferenceNet only implements the write side of the reference control")
+            if fusion_blocks != "full":
+                raise ValueError("the V-Express pipeline pairs all 16 blocks (fusion_blocks='full')")
+            unet.write_banks = True
+            for blk in unet.writer_blocks():
+                blk.bank = []
 
     # ------------------------------------------------------------------
     def _reader_blocks(self) -> List[TemporalBasicTransformerBlock]:
@@ -81,6 +90,9 @@ class ReferenceAttentionControl:
                 r.bank = [v.clone().to(dtype) for v in bank]
 
     def clear(self):
+        if self.reference_attn and isinstance(self.unet, UNet2DConditionModel):
+            for w in self.unet.writer_blocks():
+                w.bank.clear()
         if self.reference_attn and isinstance(self.unet, UNet3DConditionModel):
             for r in self._reader_blocks():
                 r.bank.clear()
