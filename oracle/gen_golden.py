@@ -11,7 +11,11 @@ box never runs this.  The reference's files are imported verbatim from where the
      ``mutual_self_attention.py``          (ReferenceNet)        -> refnet_small.pt
 
 Inputs/weights are NOT stored: they are regenerated from seeds by ``oracle.vx_oracle.synth_*``.
-Usage:  python oracle/gen_golden.py [context ddim unet pipeline refnet]   (default: all)
+  * ``modules/v_kps_guider.py``, ``modules/audio_projection.py``, the audio windowing of
+     ``VExpressPipeline.prepare_audio_embeddings`` and ``median_filter_3d`` of ``pipelines/utils.py`` (SURVEY 8f-f2/f3;
+     the latter executed from its source because the module imports cv2 / ffmpeg)      -> prologue_small.pt
+
+Usage:  python oracle/gen_golden.py [context ddim unet pipeline refnet prologue]   (default: all)
 """
 import importlib
 import importlib.util
@@ -262,6 +266,61 @@ def gen_refnet(msa, unet3d):
           "out absmean", out.abs().mean().item())
 
 
+def gen_prologue(pipe):
+    import ast
+    import torch.nn.functional as func
+    import tqdm
+    kg = importlib.import_module("modules.v_kps_guider")
+    ap = importlib.import_module("modules.audio_projection")
+    out = {}
+    # VKpsGuider (inference.py:100): 64x64 keypoint images, 2 frames
+    kcfg = O.KPS_CFG
+    ksd = O.synth_state_dict(O.kps_guider_param_shapes(kcfg), 21)
+    m = kg.VKpsGuider(kcfg["conditioning_embedding_channels"], block_out_channels=kcfg["block_out_channels"])
+    assert set(m.state_dict()) == set(ksd)
+    m.load_state_dict(ksd)
+    kps_in = torch.rand(1, 3, 2, 64, 64, generator=torch.Generator().manual_seed(3))
+    with torch.no_grad():
+        out["kps"] = dict(seed_weights=21, seed_input=3, shape=tuple(kps_in.shape), feature=m.eval()(kps_in))
+    # AudioProjection (inference.py:116-126,192-201)
+    acfg = O.AUDIO_PROJ_CFG
+    asd = O.synth_state_dict(O.audio_projection_param_shapes(acfg), 22)
+    m2 = ap.AudioProjection(dim=acfg["dim"], depth=acfg["depth"], dim_head=acfg["dim_head"], heads=acfg["heads"],
+                            num_queries=acfg["num_queries"], embedding_dim=acfg["embedding_dim"],
+                            output_dim=acfg["output_dim"], ff_mult=acfg["ff_mult"], max_seq_len=acfg["max_seq_len"])
+    assert set(m2.state_dict()) == set(asd)
+    m2.load_state_dict(asd)
+    xa = torch.randn(6, 10, 768, generator=torch.Generator().manual_seed(4))
+    with torch.no_grad():
+        out["audio_projection"] = dict(seed_weights=22, seed_input=4, shape=tuple(xa.shape), tokens=m2.eval()(xa))
+
+    # audio windowing: the reference method itself with stub encoder / identity projection (:374-407)
+    class _Enc:
+        def __call__(self, w):
+            return type("R", (), {"last_hidden_state": w})()
+
+    class _Self:
+        device, dtype = torch.device("cpu"), torch.float32
+        audio_processor = staticmethod(lambda w, return_tensors=None, sampling_rate=None: {"input_values": w})
+        audio_encoder = _Enc()
+        audio_projection = staticmethod(lambda x: x)
+    emb = torch.randn(1, 37, 32, generator=torch.Generator().manual_seed(6))
+    win = pipe.VExpressPipeline.prepare_audio_embeddings(_Self(), emb, 8, 2, True)
+    assert win.shape[0] == 2 and torch.count_nonzero(win[0]).item() == 0
+    out["audio_windows"] = dict(seed_input=6, shape=tuple(emb.shape), video_length=8, num_pad=2, windows=win[1])
+    # median filter: the function's own source (pipelines/utils.py:46-63)
+    src = open(os.path.join(REF, "pipelines", "utils.py")).read()
+    fn = [n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "median_filter_3d"][0]
+    ns = dict(torch=torch, func=func, tqdm=tqdm)
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "pipelines/utils.py", "exec"), ns)
+    v = torch.rand(3, 5, 12, 10, generator=torch.Generator().manual_seed(5))
+    filt = ns["median_filter_3d"](v, 3, "cpu")
+    out["median"] = dict(seed_input=5, shape=tuple(v.shape), filtered=filt,
+                         uint8=torch.from_numpy((filt.permute(1, 2, 3, 0) * 255).numpy().astype("uint8")))
+    torch.save(out, os.path.join(GOLD, "prologue_small.pt"))
+    print("prologue_small.pt:", {k: tuple(next(t for t in v.values() if torch.is_tensor(t)).shape) for k, v in out.items()})
+
+
 def gen_ddim():
     """Known-answer values of the restated DDIM -- self-pins, cross-checked
     against the constants quoted in the survey."""
@@ -283,7 +342,7 @@ if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
     msa, unet3d, ctx, pipe = import_reference()
-    which = set(sys.argv[1:]) or {"context", "ddim", "unet", "pipeline", "refnet"}
+    which = set(sys.argv[1:]) or {"context", "ddim", "unet", "pipeline", "refnet", "prologue"}
     if "context" in which:
         gen_context(ctx)
     if "ddim" in which:
@@ -294,3 +353,5 @@ if __name__ == "__main__":
         gen_pipeline(msa, unet3d, pipe)
     if "refnet" in which:
         gen_refnet(msa, unet3d)
+    if "prologue" in which:
+        gen_prologue(pipe)

@@ -595,6 +595,120 @@ def refnet_param_shapes(cfg) -> Dict[str, tuple]:
 
 
 # --------------------------------------------------------------------------------------
+# Conditioning prologue and post-processing (row f3)
+# --------------------------------------------------------------------------------------
+
+KPS_CFG = dict(conditioning_embedding_channels=320, conditioning_channels=3, block_out_channels=(16, 32, 96, 256))
+AUDIO_PROJ_CFG = dict(dim=768, depth=4, dim_head=64, heads=12, num_queries=5, embedding_dim=768, output_dim=768,
+                      ff_mult=4, max_seq_len=10)          # inference.py:116-126,192-201 with num_pad_audio_frames=2
+
+
+def kps_guider_param_shapes(cfg=KPS_CFG) -> Dict[str, tuple]:
+    """modules/v_kps_guider.py:10-33: conv_in, (same-width conv, stride-2 conv) per level, conv_out."""
+    boc = cfg["block_out_channels"]
+    S: Dict[str, tuple] = {}
+
+    def conv_(p, co, ci):
+        S[p + ".weight"] = (co, ci, 3, 3)
+        S[p + ".bias"] = (co,)
+
+    conv_("conv_in", boc[0], cfg["conditioning_channels"])
+    for i in range(len(boc) - 1):
+        conv_(f"blocks.{2 * i}", boc[i], boc[i])
+        conv_(f"blocks.{2 * i + 1}", boc[i + 1], boc[i])
+    conv_("conv_out", cfg["conditioning_embedding_channels"], boc[-1])
+    return S
+
+
+def kps_guider_forward(sd, cfg, images: Tensor) -> Tensor:
+    """modules/v_kps_guider.py:35-45 on (b,3,t,H,W) keypoint images in [0,1]: every conv is an InflatedConv3d, i.e. a
+    per-frame 2-D conv (modules/resnet.py:9-17); SiLU after every conv but the last.  -> (b,C0,t,H/8,W/8)."""
+    b, c, t, H, W = images.shape
+    x = images.permute(0, 2, 1, 3, 4).reshape(b * t, c, H, W)
+    x = F.silu(conv(sd, "conv_in", x))
+    for i in range(2 * (len(cfg["block_out_channels"]) - 1)):
+        x = F.silu(conv(sd, f"blocks.{i}", x, stride=1 + (i & 1)))
+    x = conv(sd, "conv_out", x)
+    return x.view(b, t, x.shape[1], x.shape[2], x.shape[3]).permute(0, 2, 1, 3, 4).contiguous()
+
+
+def audio_frame_windows(emb: Tensor, video_length: int, num_pad_audio_frames: int = 2) -> Tensor:
+    """pipelines/v_express_pipeline.py:380-401: wav2vec2 states (1,T,d) -> linear interpolation (fp32) to 2*L steps,
+    2*num_pad zero rows on both sides, and the (L, 2*(2*num_pad+1), d) sliding windows of the frames."""
+    dt = emb.dtype
+    x = F.interpolate(emb.float().permute(0, 2, 1), size=2 * video_length, mode="linear")[0].permute(1, 0).to(dt)
+    pad = torch.zeros(2 * num_pad_audio_frames, x.shape[1], dtype=dt)
+    x = torch.cat([pad, x, pad], 0)
+    return torch.stack([x[2 * i:2 * (i + 2 * num_pad_audio_frames + 1)] for i in range(video_length)], 0)
+
+
+def audio_projection_param_shapes(cfg=AUDIO_PROJ_CFG) -> Dict[str, tuple]:
+    """modules/audio_projection.py:88-126 (num_latents_mean_pooled = 0)."""
+    d, inner = cfg["dim"], cfg["dim_head"] * cfg["heads"]
+    S: Dict[str, tuple] = {"pos_emb.weight": (cfg["max_seq_len"], cfg["embedding_dim"]), "latents": (1, cfg["num_queries"], d),
+                           "proj_in.weight": (d, cfg["embedding_dim"]), "proj_in.bias": (d,),
+                           "proj_out.weight": (cfg["output_dim"], d), "proj_out.bias": (cfg["output_dim"],),
+                           "norm_out.weight": (cfg["output_dim"],), "norm_out.bias": (cfg["output_dim"],)}
+    for i in range(cfg["depth"]):
+        a, f = f"layers.{i}.0", f"layers.{i}.1"
+        for n in ("norm1", "norm2"):
+            S[f"{a}.{n}.weight"] = (d,)
+            S[f"{a}.{n}.bias"] = (d,)
+        S[a + ".to_q.weight"] = (inner, d)
+        S[a + ".to_kv.weight"] = (2 * inner, d)
+        S[a + ".to_out.weight"] = (d, inner)
+        S[f + ".0.weight"] = (d,)
+        S[f + ".0.bias"] = (d,)
+        S[f + ".1.weight"] = (cfg["ff_mult"] * d, d)
+        S[f + ".3.weight"] = (d, cfg["ff_mult"] * d)
+    return S
+
+
+def audio_projection_forward(sd, cfg, x: Tensor) -> Tensor:
+    """modules/audio_projection.py:128-150 (perceiver resampler): x (L, 10, 768) -> (L, 5, 768).
+    PerceiverAttention :44-75: q from the latents, k/v from [x | latents], both pre-normalised; softmax in fp32."""
+    heads = cfg["heads"]
+    n = x.shape[1]
+    x = x + sd["pos_emb.weight"][:n]
+    lat = sd["latents"].repeat(x.shape[0], 1, 1)
+    x = _lin(sd, "proj_in", x)
+
+    def split(t):
+        return t.view(t.shape[0], t.shape[1], heads, -1).transpose(1, 2)
+
+    for i in range(cfg["depth"]):
+        a, f = f"layers.{i}.0", f"layers.{i}.1"
+        xn = layer_norm(sd, a + ".norm1", x)
+        ln = layer_norm(sd, a + ".norm2", lat)
+        q = split(_lin(sd, a + ".to_q", ln))
+        k, v = _lin(sd, a + ".to_kv", torch.cat([xn, ln], dim=-2)).chunk(2, dim=-1)
+        k, v = split(k), split(v)
+        sc = 1 / math.sqrt(math.sqrt(cfg["dim_head"]))
+        w = torch.softmax(((q * sc) @ (k * sc).transpose(-2, -1)).float(), dim=-1).to(q.dtype)
+        o = (w @ v).permute(0, 2, 1, 3).reshape(lat.shape[0], lat.shape[1], -1)
+        lat = _lin(sd, a + ".to_out", o) + lat
+        h = layer_norm(sd, f + ".0", lat)
+        lat = _lin(sd, f + ".3", F.gelu(_lin(sd, f + ".1", h))) + lat
+    return layer_norm(sd, "norm_out", _lin(sd, "proj_out", lat))
+
+
+def median_filter_3d(video: Tensor, kernel_size: int = 3) -> Tensor:
+    """pipelines/utils.py:46-63: (3,T,H,W) -> (3,T,H,W), median over the k x k x k neighbourhood (t,h,w) with reflect
+    padding on all three axes.  k^3 is odd, so torch.median's lower-median rule coincides with the true median."""
+    p = kernel_size // 2
+    x = F.pad(video, (p, p, p, p, p, p), mode="reflect")
+    _, T, H, W = video.shape
+    views = [x[:, dt:dt + T, dy:dy + H, dx:dx + W] for dt in range(kernel_size) for dy in range(kernel_size)
+             for dx in range(kernel_size)]
+    return torch.stack(views, dim=-1).median(dim=-1)[0]
+
+
+def video_to_uint8(video: Tensor) -> np.ndarray:
+    """pipelines/utils.py:72-73: (3,T,H,W) in [0,1] -> (T,H,W,3) uint8 by truncation of v*255."""
+    return (video.permute(1, 2, 3, 0) * 255).numpy().astype(np.uint8)
+
+
+# --------------------------------------------------------------------------------------
 # AutoencoderKL decoder (diffusers 0.29.2, sd-vae-ft-mse config; SURVEY Appendix B.6)
 # --------------------------------------------------------------------------------------
 
@@ -876,7 +990,7 @@ def synth_state_dict(shapes: Dict[str, tuple], seed: int) -> Dict[str, Tensor]:
         g = torch.Generator().manual_seed((seed * 1000003 + zlib.crc32(k.encode())) % (2 ** 31))
         if k.endswith("pos_encoder.pe"):
             sd[k] = positional_encoding(shp[2], shp[1])
-        elif "norm" in k.split(".")[-2] or (len(k.split(".")) > 2 and k.split(".")[-3] == "norms"):
+        elif (len(k.split(".")) >= 2 and "norm" in k.split(".")[-2]) or (len(k.split(".")) > 2 and k.split(".")[-3] == "norms"):
             if k.endswith(".weight"):
                 sd[k] = 1 + 0.02 * torch.randn(shp, generator=g)
             else:

@@ -117,3 +117,27 @@ def test_refnet_write_pass_matches_reference(golden_dir):
         assert a.shape == b.shape, name
         torch.testing.assert_close(a, b, atol=2e-4, rtol=1e-4, msg=lambda m: f"{name}: {m}")
     torch.testing.assert_close(out, g["out"], atol=2e-4, rtol=1e-4)
+
+
+def test_prologue_and_postprocessing_match_reference(golden_dir):
+    """VKpsGuider, AudioProjection, the audio windowing of prepare_audio_embeddings and the
+    3x3x3 median filter, against outputs of the reference's own code (oracle/gen_golden.py:gen_prologue)."""
+    g = torch.load(os.path.join(golden_dir, "prologue_small.pt"), weights_only=False)
+    k = g["kps"]
+    sd = O.synth_state_dict(O.kps_guider_param_shapes(O.KPS_CFG), k["seed_weights"])
+    x = torch.rand(*k["shape"], generator=torch.Generator().manual_seed(k["seed_input"]))
+    with torch.no_grad():
+        torch.testing.assert_close(O.kps_guider_forward(sd, O.KPS_CFG, x), k["feature"], atol=1e-5, rtol=1e-5)
+    a = g["audio_projection"]
+    sd = O.synth_state_dict(O.audio_projection_param_shapes(O.AUDIO_PROJ_CFG), a["seed_weights"])
+    x = torch.randn(*a["shape"], generator=torch.Generator().manual_seed(a["seed_input"]))
+    with torch.no_grad():
+        torch.testing.assert_close(O.audio_projection_forward(sd, O.AUDIO_PROJ_CFG, x), a["tokens"], atol=1e-5, rtol=1e-5)
+    w = g["audio_windows"]
+    emb = torch.randn(*w["shape"], generator=torch.Generator().manual_seed(w["seed_input"]))
+    assert torch.equal(O.audio_frame_windows(emb, w["video_length"], w["num_pad"]), w["windows"])
+    m = g["median"]
+    v = torch.rand(*m["shape"], generator=torch.Generator().manual_seed(m["seed_input"]))
+    filt = O.median_filter_3d(v, 3)
+    assert torch.equal(filt, m["filtered"])                         # order statistics: bit-exact
+    assert np.array_equal(O.video_to_uint8(filt), m["uint8"].numpy())
