@@ -120,6 +120,12 @@ int vx_cfg_overlap_accumulate(const void* noise, int f, int hw, int L, int do_cf
 int vx_ddim_step(void* latents, const float* acc, long long n, float sqrt_a, float sqrt_1ma, float sqrt_aprev,
                  float sqrt_1maprev, void* stream);
 
+/* ---- post-processing of the decoded video: 3x3x3 median over (t, y, x) with reflect padding
+ * (pipelines/utils.py:46-63) and the uint8 frames save_video hands to the encoder (:70-73, truncation of v*255).
+ * video [C,T,H,W] fp32 (device); filtered (nullable) same layout; frames (nullable) [T,H,W,C] uint8.
+ * Written at the end of round 1 without GPU budget left: not yet run on hardware. */
+int vx_median3d_u8(const float* video, int C, int T, int H, int W, float* filtered, unsigned char* frames, void* stream);
+
 /* ---- bring-up probes used by tests/test_probe_gpu.py (descriptor / TMA layout conventions) */
 int vx_probe_umma(const void* a_img, int a_bytes, const void* b_img, int b_bytes, unsigned lboA, unsigned sboA,
                   unsigned layA, unsigned lboB, unsigned sboB, unsigned layB, int a_mn, int b_mn, int N, int ksteps,

@@ -324,3 +324,15 @@ def conv_out_tc(x, NB, H, W, w_packed, b_packed, out, post=False):
                                        c_int(int(out.dtype == torch.float32)), c_int(int(post)), stream_ptr()),
           "vx_extract_planar")
     return out
+
+
+def median3d_u8(video, want_filtered=False):
+    """video (C,T,H,W) fp32 on the device -> uint8 frames (T,H,W,C) [, filtered (C,T,H,W) fp32]: the reference's
+    ``median_filter_3d(kernel_size=3)`` + ``(v * 255).astype(uint8)`` (pipelines/utils.py:46-63,70-73)."""
+    assert video.dtype == torch.float32 and video.is_contiguous() and video.dim() == 4
+    C, T, H, W = video.shape
+    frames = torch.empty((T, H, W, C), device=video.device, dtype=torch.uint8)
+    filt = torch.empty_like(video) if want_filtered else None
+    check(_ffi.lib().vx_median3d_u8(ptr(video), c_int(C), c_int(T), c_int(H), c_int(W), ptr(filt), ptr(frames),
+                                    stream_ptr()), "vx_median3d_u8")
+    return (frames, filt) if want_filtered else frames
