@@ -33,6 +33,17 @@ int vx_gemm_bf16(const void* A, long long lda, int K1, const void* A2, long long
                  const void* residual, long long ldr, void* out, long long ldc, int out_f32, int block_n,
                  void* stream);
 
+/* ---- LayerNorm folded into the consumer GEMM (experiment, default off in the engine: VX_LN_FOLD=1; written at the
+ * end of round 1 without GPU budget left -- not yet run on hardware).  vx_row_stats writes (mean, rstd) per row of the
+ * un-normalised activations; vx_gemm_lnfold_bf16 computes rstd[m] * (A @ Wt^T - mean[m] * colsum) + bias with
+ * Wt = W * gamma, colsum[n] = sum_k Wt[n,k], bias[n] = sum_k beta[k] W[n,k] + b[n]: the nn.LayerNorm + nn.Linear pairs
+ * of modules/attention.py:329-375 and modules/motion_module.py:228-234 without writing LayerNorm(x) to HBM. */
+int vx_row_stats(const void* x, long long ldx, long long rows, int C, float eps, float* stats, void* stream);
+int vx_gemm_lnfold_bf16(const void* A, long long lda, int K, const void* Wt, long long ldw, int M, int N,
+                        const float* stats, const float* colsum, const float* bias, const float* bias2, int bias2_div,
+                        float scale, const void* residual, long long ldr, void* out, long long ldc, int geglu,
+                        int block_n, void* stream);
+
 /* ---- tcgen05 implicit-GEMM 3x3 convolution, stride 1, pad 1, NHWC.  X [NB,H,W,C]; W [Cout, 9*C].
  * Replaces InflatedConv3d / nn.Conv2d 3x3 (modules/resnet.py:9-17,165-167,194-196; Upsample3D conv :51) and the
  * VAE decoder convs (diffusers AutoencoderKL).  bias2 = per-sample bias (time embedding,

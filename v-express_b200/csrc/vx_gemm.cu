@@ -51,6 +51,10 @@ struct GemmArgs {
   float scale;
   float* out32;
   long long ldc;
+  // LayerNorm folded into the epilogue (LNF instantiations only): out = rstd[m] * (acc - mean[m] * colsum[n]) + bias[n]
+  // with W pre-multiplied by gamma, colsum[n] = sum_k W'[n,k], bias[n] = sum_k beta[k] W[n,k] + b[n]
+  const float* ln_stats;    // [M][2] = (mean, rstd) of the un-normalised rows of A
+  const float* ln_colsum;   // [N]
 };
 
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
@@ -138,7 +142,7 @@ __device__ __forceinline__ float gelu_erf(float g) {
 // 128 rows of A and HALF of the W tile, the leader issues tcgen05.mma.cta_group::2 (M = 256) and every SM feeds only
 // half of B from its shared memory -- the 1-CTA kernel is bound by the SS-MMA operand fetch (A 4 KB + B 8 KB per
 // 128x256x16 MMA at ~64 B/clk = 192 clk vs 128 clk of math, profiles/r01e_final_ncu.md).
-template <int CG>
+template <int CG, bool LNF>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapA2,
                     const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapR,
@@ -358,6 +362,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256);
       const int nbase = tile_n * p.block_n;  // accumulator column base (bias index)
       const float* b2 = p.bias2 ? p.bias2 + (row_ok ? (m / p.bias2_div) : 0) * (long long)p.N : nullptr;
+      float ln_mean = 0.f, ln_rstd = 1.f;
+      if constexpr (LNF) {
+        if (row_ok) {
+          const float2 st = *reinterpret_cast<const float2*>(p.ln_stats + 2 * m);
+          ln_mean = st.x;
+          ln_rstd = st.y;
+        }
+      }
       for (int c = c_begin; c < c_end; ++c) {
         uint32_t v[16];
         float f[16];
@@ -375,6 +387,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             bv[i] = t0.x; bv[i + 1] = t0.y; bv[i + 2] = t0.z; bv[i + 3] = t0.w;
             bg[i] = t1.x; bg[i + 1] = t1.y; bg[i + 2] = t1.z; bg[i + 3] = t1.w;
           }
+          if constexpr (LNF) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              const float4 s0 = *reinterpret_cast<const float4*>(p.ln_colsum + nv + i);
+              const float4 s1 = *reinterpret_cast<const float4*>(p.ln_colsum + ng + i);
+              const float sv[4] = {s0.x, s0.y, s0.z, s0.w}, sg[4] = {s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                v[i + j] = __float_as_uint(ln_rstd * (__uint_as_float(v[i + j]) - ln_mean * sv[j]));
+                g[i + j] = __float_as_uint(ln_rstd * (__uint_as_float(g[i + j]) - ln_mean * sg[j]));
+              }
+            }
+          }
 #pragma unroll
           for (int i = 0; i < 16; ++i)
             f[i] = (__uint_as_float(v[i]) + bv[i]) * gelu_erf(__uint_as_float(g[i]) + bg[i]);
@@ -383,6 +408,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
           const int n = nbase + c * 16;
 #pragma unroll
           for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+          if constexpr (LNF) {
+            if (n < p.N) {
+#pragma unroll
+              for (int i = 0; i < 16; i += 4) {
+                const float4 s0 = *reinterpret_cast<const float4*>(p.ln_colsum + n + i);
+                f[i] = ln_rstd * (f[i] - ln_mean * s0.x);
+                f[i + 1] = ln_rstd * (f[i + 1] - ln_mean * s0.y);
+                f[i + 2] = ln_rstd * (f[i + 2] - ln_mean * s0.z);
+                f[i + 3] = ln_rstd * (f[i + 3] - ln_mean * s0.w);
+              }
+            }
+          }
           if (n < p.N) {
             if (p.bias) {
 #pragma unroll
@@ -517,7 +554,7 @@ static bool use_pair(const GemmArgs& a) {
 static int num_pairs() {
   static int n = 0;
   if (n <= 0) {
-    cudaFuncSetAttribute(gemm_tcgen05_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(gemm_tcgen05_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(2 * num_sms());
     cfg.blockDim = dim3(kThreads);
@@ -530,7 +567,7 @@ static int num_pairs() {
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     int c = 0;
-    if (cudaOccupancyMaxActiveClusters(&c, gemm_tcgen05_kernel<2>, &cfg) != cudaSuccess || c <= 0) {
+    if (cudaOccupancyMaxActiveClusters(&c, gemm_tcgen05_kernel<2, false>, &cfg) != cudaSuccess || c <= 0) {
       cudaGetLastError();
       c = num_sms() / 2;
     }
@@ -570,14 +607,17 @@ static int launch(const CUtensorMap& mA, const CUtensorMap& mA2, const CUtensorM
             a.taps, cg, a.block_n, stages, nbuf, a.tiles_m, a.tiles_n);
   static bool configured = false;
   if (!configured) {
-    VX_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    VX_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    VX_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    VX_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    VX_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    VX_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
   if (cg == 1) {
     const int tiles = a.tiles_m * a.tiles_n;
     const int grid = tiles < num_sms() ? tiles : num_sms();
-    gemm_tcgen05_kernel<1><<<grid, kThreads, smem, st>>>(mA, mA2, mB, mR, mC, a);
+    if (a.ln_stats) gemm_tcgen05_kernel<1, true><<<grid, kThreads, smem, st>>>(mA, mA2, mB, mR, mC, a);
+    else gemm_tcgen05_kernel<1, false><<<grid, kThreads, smem, st>>>(mA, mA2, mB, mR, mC, a);
   } else {
     const int items = ((a.tiles_m + 1) / 2) * a.tiles_n;
     const int pairs = items < num_pairs() ? items : num_pairs();
@@ -593,7 +633,8 @@ static int launch(const CUtensorMap& mA, const CUtensorMap& mA2, const CUtensorM
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    VX_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<2>, mA, mA2, mB, mR, mC, a));
+    if (a.ln_stats) VX_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<2, true>, mA, mA2, mB, mR, mC, a));
+    else VX_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<2, false>, mA, mA2, mB, mR, mC, a));
   }
   VX_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -622,10 +663,10 @@ using namespace vx;
 
 // epilogue: 0 = linear (bias, bias2, scale, residual); 1 = GEGLU (W / bias packed per tile as value|gate halves,
 // see vx_geglu_pack_rows; out has N/2 columns)
-extern "C" int vx_gemm_bf16(const void* A, long long lda, int K1, const void* A2, long long lda2, int K2,
-                            const void* Wt, long long ldw, int M, int N, const float* bias, const float* bias2,
-                            int bias2_div, float scale, const void* residual, long long ldr, void* out,
-                            long long ldc, int out_f32, int block_n, void* stream) {
+static int gemm_entry(const void* A, long long lda, int K1, const void* A2, long long lda2, int K2, const void* Wt,
+                      long long ldw, int M, int N, const float* bias, const float* bias2, int bias2_div, float scale,
+                      const void* residual, long long ldr, void* out, long long ldc, int out_f32, int block_n,
+                      const float* ln_stats, const float* ln_colsum, void* stream) {
   const int geglu = out_f32 == 2 ? 1 : 0;  // out_f32: 0 bf16, 1 fp32, 2 bf16 + GEGLU epilogue
   if (geglu) out_f32 = 0;
   VX_REQUIRE(M > 0 && N > 0 && K1 > 0, "vx_gemm_bf16: bad shape M=%d N=%d K1=%d", M, N, K1);
@@ -684,7 +725,28 @@ extern "C" int vx_gemm_bf16(const void* A, long long lda, int K1, const void* A2
   a.out_f32 = out_f32;
   a.bias = bias; a.bias2 = bias2; a.bias2_div = bias2_div > 0 ? bias2_div : 1; a.scale = scale;
   a.out32 = (float*)out; a.ldc = ldc;
+  a.ln_stats = ln_stats; a.ln_colsum = ln_colsum;
   return launch(mA, mA2, mB, mR, mC, a, (cudaStream_t)stream);
+}
+
+extern "C" int vx_gemm_bf16(const void* A, long long lda, int K1, const void* A2, long long lda2, int K2,
+                            const void* Wt, long long ldw, int M, int N, const float* bias, const float* bias2,
+                            int bias2_div, float scale, const void* residual, long long ldr, void* out,
+                            long long ldc, int out_f32, int block_n, void* stream) {
+  return gemm_entry(A, lda, K1, A2, lda2, K2, Wt, ldw, M, N, bias, bias2, bias2_div, scale, residual, ldr, out, ldc,
+                    out_f32, block_n, nullptr, nullptr, stream);
+}
+
+// LayerNorm folded into the GEMM: A holds the UN-normalised rows, Wt = W * gamma (per input channel),
+// out = rstd[m] * (A @ Wt^T - mean[m] * colsum) + bias (+ bias2, scale, residual, GEGLU as in vx_gemm_bf16) with
+// stats[m] = (mean, rstd) from vx_row_stats, colsum[n] = sum_k Wt[n,k], bias[n] = sum_k beta[k] W[n,k] + b[n].
+extern "C" int vx_gemm_lnfold_bf16(const void* A, long long lda, int K, const void* Wt, long long ldw, int M, int N,
+                                   const float* stats, const float* colsum, const float* bias, const float* bias2,
+                                   int bias2_div, float scale, const void* residual, long long ldr, void* out,
+                                   long long ldc, int geglu, int block_n, void* stream) {
+  VX_REQUIRE(stats && colsum, "vx_gemm_lnfold_bf16: stats / colsum missing (M=%d)", M);
+  return gemm_entry(A, lda, K, nullptr, 0, 0, Wt, ldw, M, N, bias, bias2, bias2_div, scale, residual, ldr, out, ldc,
+                    geglu ? 2 : 0, block_n, stats, colsum, stream);
 }
 
 // X: NHWC bf16 [NB, H, W, C];  Wt: [Cout, 9*C] with K index = (ky*3+kx)*C + c;  out: [NB*H*W, ldc]

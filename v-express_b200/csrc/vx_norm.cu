@@ -404,6 +404,95 @@ __global__ void __launch_bounds__(256) layernorm5_kernel(const __nv_bfloat16* __
   }
 }
 
+
+// ---- LayerNorm statistics only: stats[row] = (mean, rstd) with torch's two-pass variance, for the GEMM that applies the
+// normalisation in its epilogue (vx_gemm_lnfold_bf16).  C = 40 * LPR uses LPR lanes per row (five 16-byte vectors per
+// lane); any other C (multiple of 8, <= 2048) one warp per row.
+template <int LPR>
+__global__ void __launch_bounds__(256) row_stats5_kernel(const __nv_bfloat16* __restrict__ x, long long ldx,
+                                                         long long rows, float eps, float* __restrict__ stats) {
+  constexpr int RPW = 32 / LPR;
+  constexpr int C = LPR * 40;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LPR, l = lane % LPR;
+  const long long nwarps = (long long)gridDim.x * 8;
+  const long long ngroups = (rows + RPW - 1) / RPW;
+  for (long long grp = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); grp < ngroups; grp += nwarps) {
+    const long long row = grp * RPW + sub;
+    const bool ok = row < rows;
+    const __nv_bfloat16* xp = x + (ok ? row : 0) * ldx + l * 8;
+    uint4 u[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) u[i] = *reinterpret_cast<const uint4*>(xp + i * LPR * 8);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const uint32_t w4[4] = {u[i].x, u[i].y, u[i].z, u[i].w};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 v = unpack_bf16(w4[t]);
+        s += v.x + v.y;
+      }
+    }
+#pragma unroll
+    for (int o = LPR / 2; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * (1.0f / C);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const uint32_t w4[4] = {u[i].x, u[i].y, u[i].z, u[i].w};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 v = unpack_bf16(w4[t]);
+        const float d0 = v.x - mean, d1 = v.y - mean;
+        q = fmaf(d0, d0, q);
+        q = fmaf(d1, d1, q);
+      }
+    }
+#pragma unroll
+    for (int o = LPR / 2; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    if (ok && l == 0) *reinterpret_cast<float2*>(stats + 2 * row) = make_float2(mean, rsqrtf(q * (1.0f / C) + eps));
+  }
+}
+
+template <int MAXV>
+__global__ void row_stats_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, long long rows, int C, float eps,
+                                 float* __restrict__ stats) {
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const int V = C / 8;
+  float f[MAXV][8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int v = lane + i * 32;
+    if (v < V) {
+      load8(x + warp * ldx + v * 8, f[i]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += f[i][j];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int v = lane + i * 32;
+    if (v < V) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = f[i][j] - mean;
+        q += d * d;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  if (lane == 0) *reinterpret_cast<float2*>(stats + 2 * warp) = make_float2(mean, rsqrtf(q / C + eps));
+}
+
 }  // namespace vx
 
 using namespace vx;
@@ -515,6 +604,33 @@ extern "C" int vx_geglu(const void* x, long long ldx, long long rows, int inner,
   if (blocks > 148 * 16) blocks = 148 * 16;
   geglu_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, ldx, rows, inner,
                                                                   (__nv_bfloat16*)out, ldo);
+  VX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+
+// stats: float[rows][2] = (mean, rstd) of every row of x (LayerNorm statistics, eps inside the rsqrt like torch)
+extern "C" int vx_row_stats(const void* x, long long ldx, long long rows, int C, float eps, float* stats, void* stream) {
+  VX_REQUIRE(C % 8 == 0 && C <= 2048 && ldx % 8 == 0, "vx_row_stats: C=%d unsupported", C);
+  auto st = (cudaStream_t)stream;
+  if (C == 320 || C == 640 || C == 1280) {
+    const int lpr = C / 40;
+    const long long groups = (rows + 32 / lpr - 1) / (32 / lpr);
+    long long nb = (groups + 7) / 8;
+    if (nb > 148 * 8) nb = 148 * 8;
+    if (nb < 1) nb = 1;
+    if (lpr == 8) row_stats5_kernel<8><<<(unsigned)nb, 256, 0, st>>>((const __nv_bfloat16*)x, ldx, rows, eps, stats);
+    else if (lpr == 16) row_stats5_kernel<16><<<(unsigned)nb, 256, 0, st>>>((const __nv_bfloat16*)x, ldx, rows, eps, stats);
+    else row_stats5_kernel<32><<<(unsigned)nb, 256, 0, st>>>((const __nv_bfloat16*)x, ldx, rows, eps, stats);
+  } else {
+    const long long blocks = (rows * 32 + 255) / 256;
+    const int V = C / 8;
+    if (V <= 32) row_stats_kernel<1><<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16*)x, ldx, rows, C, eps, stats);
+    else if (V <= 64) row_stats_kernel<2><<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16*)x, ldx, rows, C, eps, stats);
+    else if (V <= 96) row_stats_kernel<3><<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16*)x, ldx, rows, C, eps, stats);
+    else if (V <= 160) row_stats_kernel<5><<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16*)x, ldx, rows, C, eps, stats);
+    else row_stats_kernel<8><<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16*)x, ldx, rows, C, eps, stats);
+  }
   VX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -21,6 +21,7 @@ from __future__ import annotations
 
 import json
 import math
+import os
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Tuple
 
@@ -358,6 +359,7 @@ class UNetEngine:
         self.sd = sd
         self.W: Dict[str, torch.Tensor] = {}
         self._pack(sd)
+        self._pack_ln_fold()
         self._bank_cache: Dict[str, tuple] = {}
         self._bank_buf: Dict[str, torch.Tensor] = {}
         self._bank_flag: Dict[str, bool] = {}
@@ -413,6 +415,61 @@ class UNetEngine:
             elif k.endswith("ff.net.0.proj.weight"):
                 p = k[:-len(".weight")]
                 W[p + ".geglu_w"], W[p + ".geglu_b"], _ = ops.pack_geglu(W[k], W[p + ".bias"])
+
+    # ---------------------------------------------------------------- LayerNorm folded into the consumer GEMM
+    def _pack_ln_fold(self):
+        """VX_LN_FOLD=1 (experiment, default off; not yet run on hardware): every LayerNorm -> Linear pair of the
+        transformer blocks runs as row statistics + one GEMM whose epilogue applies the normalisation
+        (ops.fold_layernorm / ops.gemm_lnfold), so LayerNorm(x) is never written to HBM."""
+        self.ln_fold = os.environ.get("VX_LN_FOLD") == "1"
+        self.F: Dict[str, tuple] = {}
+        self._pe_proj: Dict[str, torch.Tensor] = {}
+        self._pe_bias: Dict[tuple, torch.Tensor] = {}
+        if not self.ln_fold:
+            return
+        W = self.W
+        for k in list(W):
+            if k.endswith(".norm1.weight") and ".attentions." in k:
+                t = k[:-len(".norm1.weight")]
+                for norm, lin in (("norm1", "attn1.qkv"), ("norm1_5", "attn1_5.to_q.weight"), ("norm2", "attn2.to_q.weight")):
+                    if (t + "." + lin) in W:
+                        self.F[f"{t}.{norm}"] = ops.fold_layernorm(W[f"{t}.{lin}"], None, W[f"{t}.{norm}.weight"],
+                                                                   W[f"{t}.{norm}.bias"])
+                self.F[t + ".norm3"] = ops.fold_layernorm(W[t + ".ff.net.0.proj.weight"], W[t + ".ff.net.0.proj.bias"],
+                                                          W[t + ".norm3.weight"], W[t + ".norm3.bias"], geglu=True)
+            elif k.endswith(".ff_norm.weight"):
+                t = k[:-len(".ff_norm.weight")]
+                self.F[t + ".ff_norm"] = ops.fold_layernorm(W[t + ".ff.net.0.proj.weight"], W[t + ".ff.net.0.proj.bias"],
+                                                            W[t + ".ff_norm.weight"], W[t + ".ff_norm.bias"], geglu=True)
+                for i in (0, 1):
+                    a_ = f"{t}.attention_blocks.{i}"
+                    self.F[f"{t}.norms.{i}"] = ops.fold_layernorm(W[a_ + ".qkv"], None, W[f"{t}.norms.{i}.weight"],
+                                                                  W[f"{t}.norms.{i}.bias"])
+                    # (LayerNorm(x) + pe) W^T = LayerNorm(x) W^T + pe W^T: the positional encoding becomes a per-frame bias
+                    self._pe_proj[a_] = (W[a_ + ".pos_encoder.pe"] @ W[a_ + ".qkv"].float().t()).contiguous()
+
+    def _ln_gemm(self, h, norm_key, w_key, *, geglu=False, pe=None, rows_per_frame=0, b=1):
+        """LayerNorm(h) [+ pe] -> Linear.  Default: the LayerNorm kernel followed by the GEMM; under VX_LN_FOLD the
+        statistics kernel and the GEMM with the normalising epilogue."""
+        W = self.W
+        if not self.ln_fold:
+            n = ops.layernorm(h, W[norm_key + ".weight"], W[norm_key + ".bias"], pe=pe, rows_per_frame=rows_per_frame)
+            if geglu:
+                return ops.gemm(n, W[w_key + ".geglu_w"], W[w_key + ".geglu_b"], geglu=True)
+            return ops.gemm(n, W[w_key])
+        wf, cs, bf = self.F[norm_key]
+        st = ops.row_stats(h)
+        bias2, div = None, 1
+        if pe is not None:
+            f = pe.shape[0]
+            a_ = w_key[:-len(".qkv")]
+            key = (a_, b, f)
+            bias2 = self._pe_bias.get(key)
+            if bias2 is None:
+                bias2 = self._pe_proj[a_][:f].repeat(b, 1).contiguous()
+                self._pe_bias[key] = bias2
+            div = rows_per_frame
+        return ops.gemm_lnfold(h, wf, st, cs, bf, bias2=bias2, bias2_div=div, geglu=geglu)
 
     # ---------------------------------------------------------------- banks
     def _bank_kv(self, name: str, block: TemporalBasicTransformerBlock):
@@ -478,13 +535,11 @@ class UNetEngine:
         t = p + ".transformer_blocks.0"
         block = m.get_submodule(t)
         # attn1: self-attention
-        n = ops.layernorm(h, W[t + ".norm1.weight"], W[t + ".norm1.bias"])
-        qkv = ops.gemm(n, W[t + ".attn1.qkv"])
+        qkv = self._ln_gemm(h, t + ".norm1", t + ".attn1.qkv")
         a = ops.flash_attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], heads, HW, HW)
         h = ops.gemm(a, W[t + ".attn1.to_out.0.weight"], W[t + ".attn1.to_out.0.bias"], residual=h)
         # attn1_5: reference attention, K/V from the bank (one per CFG half, shared by the f frames)
-        n = ops.layernorm(h, W[t + ".norm1_5.weight"], W[t + ".norm1_5.bias"])
-        q = ops.gemm(n, W[t + ".attn1_5.to_q.weight"])
+        q = self._ln_gemm(h, t + ".norm1_5", t + ".attn1_5.to_q.weight")
         kv, uncond_zero = self._bank_kv(t, block)
         Nk = kv.shape[0] // (NB // f)
         if uncond_zero and NB == 2 * f:
@@ -496,16 +551,15 @@ class UNetEngine:
         h = ops.gemm(a, W[t + ".attn1_5.to_out.0.weight"], W[t + ".attn1_5.to_out.0.bias"],
                      scale=float(m.reference_attention_weight), residual=h)
         # attn2: audio cross-attention (5 tokens per frame)
-        n = ops.layernorm(h, W[t + ".norm2.weight"], W[t + ".norm2.bias"])
-        q = ops.gemm(n, W[t + ".attn2.to_q.weight"])
+        q = self._ln_gemm(h, t + ".norm2", t + ".attn2.to_q.weight")
         kv2 = ops.gemm(enc_flat, W[t + ".attn2.kv"])
         Lk = enc_flat.shape[0] // NB
         a = ops.smallkv_attention(q, kv2[:, :C], kv2[:, C:], HW, heads, Lk)
         h = ops.gemm(a, W[t + ".attn2.to_out.0.weight"], W[t + ".attn2.to_out.0.bias"],
                      scale=float(m.audio_attention_weight), residual=h)
-        # feed-forward
-        n = ops.layernorm(h, W[t + ".norm3.weight"], W[t + ".norm3.bias"])
-        h = self._ff(t + ".ff", n, h)
+        # feed-forward (GEGLU in the epilogue of the first GEMM)
+        g = self._ln_gemm(h, t + ".norm3", t + ".ff.net.0.proj", geglu=True)
+        h = ops.gemm(g, W[t + ".ff.net.2.weight"], W[t + ".ff.net.2.bias"], residual=h)
         return ops.gemm(h, W[p + ".proj_out.weight"], W[p + ".proj_out.bias"], residual=x)
 
     def _motion(self, p, x, NB, HW, b, f):
@@ -520,12 +574,11 @@ class UNetEngine:
             pe = W[a_ + ".pos_encoder.pe"]
             if f > pe.shape[0]:
                 raise ValueError(f"window of {f} frames exceeds temporal_position_encoding_max_len={pe.shape[0]}")
-            n = ops.layernorm(h, W[f"{t}.norms.{i}.weight"], W[f"{t}.norms.{i}.bias"], pe=pe[:f], rows_per_frame=HW)
-            qkv = ops.gemm(n, W[a_ + ".qkv"])
+            qkv = self._ln_gemm(h, f"{t}.norms.{i}", a_ + ".qkv", pe=pe[:f], rows_per_frame=HW, b=b)
             a = ops.temporal_attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], b, f, HW, self.heads)
             h = ops.gemm(a, W[a_ + ".to_out.0.weight"], W[a_ + ".to_out.0.bias"], residual=h)
-        n = ops.layernorm(h, W[t + ".ff_norm.weight"], W[t + ".ff_norm.bias"])
-        h = self._ff(t + ".ff", n, h)
+        g = self._ln_gemm(h, t + ".ff_norm", t + ".ff.net.0.proj", geglu=True)
+        h = ops.gemm(g, W[t + ".ff.net.2.weight"], W[t + ".ff.net.2.bias"], residual=h)
         return ops.gemm(h, W[p + ".proj_out.weight"], W[p + ".proj_out.bias"], residual=x)
 
     # ---------------------------------------------------------------- forward

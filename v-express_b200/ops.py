@@ -62,6 +62,47 @@ def gemm(a, w, bias=None, *, a2=None, bias2=None, bias2_div=1, scale=1.0, residu
     return out
 
 
+# ---- LayerNorm folded into the consumer GEMM (experiment; the engine uses it only under VX_LN_FOLD=1)
+def row_stats(x, eps=1e-5, out=None):
+    """(mean, rstd) of every row of x [rows, C] bf16 -> fp32 [rows, 2]."""
+    _chk_bf16(x)
+    rows, C = x.shape
+    if out is None:
+        out = torch.empty((rows, 2), device=x.device, dtype=torch.float32)
+    check(_ffi.lib().vx_row_stats(ptr(x), c_ll(x.stride(0)), c_ll(rows), c_int(C), c_float(eps), ptr(out), stream_ptr()),
+          "vx_row_stats")
+    return out
+
+
+def fold_layernorm(w, bias, gamma, beta, geglu=False):
+    """LayerNorm(x) @ w.T + bias  ==  rstd * (x @ wf.T - mean * colsum) + bf   with
+    wf = bf16(w * gamma), colsum = sum_k wf, bf = w @ beta + bias.  w bf16 [N, K]; gamma/beta/bias fp32.
+    geglu=True additionally applies pack_geglu's row order to all three."""
+    wf = (w.float() * gamma.float()[None, :]).to(BF16)
+    bf = w.float() @ beta.float()
+    if bias is not None:
+        bf = bf + bias.float()
+    if geglu:
+        wf, bf, _ = pack_geglu(wf, bf)
+    return wf.contiguous(), wf.float().sum(1).contiguous(), bf.contiguous()
+
+
+def gemm_lnfold(a, wf, stats, colsum, bias, *, bias2=None, bias2_div=1, scale=1.0, residual=None, out=None, geglu=False):
+    """out = rstd * (a @ wf.T - mean * colsum) + bias (+ bias2[row // bias2_div]) (* scale + residual | GEGLU)."""
+    _chk_bf16(a, wf, residual, out)
+    M, K = a.shape
+    N = wf.shape[0]
+    assert wf.shape[1] == K and stats.shape == (M, 2) and colsum.shape == (N,)
+    if out is None:
+        out = torch.empty((M, N // 2 if geglu else N), device=a.device, dtype=BF16)
+    check(_ffi.lib().vx_gemm_lnfold_bf16(
+        ptr(a), c_ll(a.stride(0)), c_int(K), ptr(wf), c_ll(wf.stride(0)), c_int(M), c_int(N), ptr(stats), ptr(colsum),
+        ptr(bias), ptr(bias2), c_int(bias2_div), c_float(scale), ptr(residual),
+        c_ll(0 if residual is None else residual.stride(0)), ptr(out), c_ll(out.stride(0)), c_int(int(geglu)),
+        c_int(geglu_block_n(N) if geglu else 0), stream_ptr()), "vx_gemm_lnfold_bf16")
+    return out
+
+
 def conv3x3(x, w, bias=None, *, bias2=None, bias2_div=1, scale=1.0, residual=None, out=None, block_n=0):
     """x: NHWC bf16 [NB,H,W,C]; w: [Cout, 9*C]; returns [NB*H*W, Cout] (= NHWC)."""
     _chk_bf16(x, w, residual, out)
