@@ -184,3 +184,116 @@ def test_refnet_layout_and_writer_pairing_cpu():
         assert bank[1, 0, 0].item() == float(wnames.index(n) + 1), n
     writer.clear()
     assert all(len(b.bank) == 0 for b in blocks)
+
+
+def _cpu_engine(cls, model):
+    """Engine object with the packed weights on the CPU (no kernels are called by packing)."""
+    import torch
+    from vexpress_b200.modules import unet_3d
+    eng = object.__new__(cls)
+    eng.model, eng.dev = model, torch.device("cpu")
+    c = model.config
+    eng.boc = tuple(c["block_out_channels"])
+    eng.heads, eng.groups, eng.eps, eng.cross = model.heads, c["norm_num_groups"], float(c["norm_eps"]), c["cross_attention_dim"]
+    eng.sd = {k: v.detach() for k, v in model.state_dict().items()}
+    eng.W = {}
+    eng._pack(eng.sd)
+    if cls is unet_3d.UNetEngine:
+        eng._pack_ln_fold()
+    else:
+        eng.ln_fold = False
+    return eng
+
+
+class _ShapeOps:
+    """Stands in for vexpress_b200.ops: checks operand shapes like the real wrappers and returns empty outputs."""
+
+    def __init__(self):
+        self.calls = []
+
+    def __getattr__(self, op):
+        import torch
+
+        def f(*a, **k):
+            self.calls.append(op)
+            if op == "row_stats":
+                return torch.zeros(a[0].shape[0], 2)
+            if op == "gemm_lnfold":
+                x, wf, st, cs, bf = a[:5]
+                M, K = x.shape
+                N = wf.shape[0]
+                assert wf.shape[1] == K and st.shape == (M, 2) and cs.shape == (N,) and bf.shape == (N,)
+                if k.get("bias2") is not None:
+                    assert k["bias2"].shape == (M // k["bias2_div"], N) and M % k["bias2_div"] == 0
+                return torch.zeros(M, N // 2 if k.get("geglu") else N)
+            if op == "gemm":
+                x, w = a[:2]
+                K = x.shape[1] + (k["a2"].shape[1] if k.get("a2") is not None else 0)
+                assert w.shape[1] == K, (x.shape, w.shape)
+                return torch.zeros(x.shape[0], w.shape[0] // 2 if k.get("geglu") else w.shape[0])
+            if op in ("layernorm", "groupnorm"):
+                return torch.zeros(a[0].shape[0], a[0].shape[1] + (k["x2"].shape[1] if k.get("x2") is not None else 0))
+            if op in ("flash_attention", "temporal_attention", "smallkv_attention"):
+                return k["out"] if k.get("out") is not None else torch.zeros_like(a[0])
+            raise AttributeError(op)
+        return f
+
+
+@pytest.mark.parametrize("fold", ["0", "1"])
+def test_transformer_block_schedules_dry_run(monkeypatch, fold):
+    """Host logic of UNetEngine._spatial / _motion with shape-checking fake ops: the default schedule and the
+    VX_LN_FOLD=1 one (every LayerNorm -> Linear pair becomes row_stats + gemm_lnfold, incl. the positional-encoding
+    bias of the motion modules) run through without touching a GPU."""
+    import torch
+    from oracle import vx_oracle as O
+    from vexpress_b200.modules import UNet3DConditionModel, unet_3d
+    monkeypatch.setenv("VX_LN_FOLD", fold)
+    cfg = O.small_cfg()
+    m = UNet3DConditionModel(
+        block_out_channels=cfg["block_out_channels"], cross_attention_dim=cfg["cross_attention_dim"],
+        use_inflated_groupnorm=True, use_motion_module=True, motion_module_mid_block=True, motion_module_type="Vanilla",
+        motion_module_kwargs=dict(num_attention_heads=8, num_transformer_block=1,
+                                  attention_block_types=["Temporal_Self", "Temporal_Self"],
+                                  temporal_position_encoding=True, temporal_position_encoding_max_len=32,
+                                  temporal_attention_dim_div=1))
+    m.load_state_dict(O.synth_state_dict(O.unet_param_shapes(cfg), 1234), strict=True)
+    eng = _cpu_engine(unet_3d.UNetEngine, m.to(torch.bfloat16))
+    assert eng.ln_fold == (fold == "1") and len(eng.F) == (127 if fold == "1" else 0)
+    fake = _ShapeOps()
+    monkeypatch.setattr(unet_3d, "ops", fake)
+    C, HW, f, b = 64, 256, 4, 2
+    NB = b * f
+    eng._bank_kv = lambda name, block: (torch.zeros(2 * HW, 2 * C), False)
+    x = torch.zeros(NB * HW, C)
+    enc = torch.zeros(NB * 5, cfg["cross_attention_dim"])
+    assert eng._spatial("down_blocks.0.attentions.0", x, NB, HW, f, enc).shape == x.shape
+    assert eng._motion("down_blocks.0.motion_modules.0", x, NB, HW, b, f).shape == x.shape
+    n_ln = 7                                   # norm1, norm1_5, norm2, norm3 + norms.0, norms.1, ff_norm
+    if fold == "1":
+        assert fake.calls.count("row_stats") == n_ln and fake.calls.count("gemm_lnfold") == n_ln
+        assert "layernorm" not in fake.calls
+    else:
+        assert fake.calls.count("layernorm") == n_ln and "gemm_lnfold" not in fake.calls
+
+
+def test_fold_layernorm_algebra():
+    """ops.fold_layernorm: rstd * (x @ wf.T - mean * colsum) + bf equals LayerNorm(x) @ w.T + b up to the bf16 rounding of
+    the folded weights (same size as the reference path's rounding of LayerNorm(x) to bf16)."""
+    import torch
+    import torch.nn.functional as F
+    from vexpress_b200 import ops
+    torch.manual_seed(0)
+    M, K, N = 64, 320, 960
+    x = (torch.randn(M, K) * 2 + 0.5).bfloat16()
+    w = (torch.randn(N, K) / K ** 0.5).bfloat16()
+    b, g, be = torch.randn(N), 1 + 0.1 * torch.randn(K), 0.1 * torch.randn(K)
+    wf, cs, bf = ops.fold_layernorm(w, b, g, be)
+    xf = x.float()
+    mean = xf.mean(1, keepdim=True)
+    rstd = (xf.var(1, unbiased=False, keepdim=True) + 1e-5).rsqrt()
+    out = rstd * (xf @ wf.float().t() - mean * cs[None]) + bf[None]
+    ref = F.layer_norm(xf, (K,), g, be, 1e-5) @ w.float().t() + b
+    assert ((out - ref).norm() / ref.norm()).item() < 3e-3
+    wp, csp, bp = ops.fold_layernorm(w, b, g, be, geglu=True)          # packed row order is applied consistently
+    w0, b0, _ = ops.pack_geglu(wf, bf)
+    assert torch.equal(wp, w0) and torch.equal(bp, b0) and torch.allclose(csp, w0.float().sum(1))
