@@ -231,10 +231,49 @@ class _ShapeOps:
                 K = x.shape[1] + (k["a2"].shape[1] if k.get("a2") is not None else 0)
                 assert w.shape[1] == K, (x.shape, w.shape)
                 return torch.zeros(x.shape[0], w.shape[0] // 2 if k.get("geglu") else w.shape[0])
-            if op in ("layernorm", "groupnorm"):
-                return torch.zeros(a[0].shape[0], a[0].shape[1] + (k["x2"].shape[1] if k.get("x2") is not None else 0))
+            if op == "layernorm":
+                assert a[1].shape == (a[0].shape[1],)
+                return torch.zeros_like(a[0])
+            if op == "groupnorm":
+                C = a[0].shape[1] + (k["x2"].shape[1] if k.get("x2") is not None else 0)
+                assert a[0].shape[0] == a[1] * a[2] and a[3].shape == (C,), (a[0].shape, a[1], a[2], a[3].shape)
+                return torch.zeros(a[0].shape[0], C)
             if op in ("flash_attention", "temporal_attention", "smallkv_attention"):
                 return k["out"] if k.get("out") is not None else torch.zeros_like(a[0])
+            if op == "conv_in":
+                x, w, bias, cout = a[:4]
+                NB, cin, H, W = x.shape
+                assert w.shape == (cin * 9, cout) and bias.shape == (cout,)
+                if k.get("addend") is not None:
+                    assert k["addend"].shape[1] == cout
+                return torch.zeros(NB * H * W, cout)
+            if op == "conv3x3":
+                x, w, bias = a[:3]
+                NB, H, W, C = x.shape
+                assert w.shape[1] == 9 * C and bias.shape == (w.shape[0],), (x.shape, w.shape)
+                if k.get("residual") is not None:
+                    assert k["residual"].shape == (NB * H * W, w.shape[0])
+                if k.get("bias2") is not None:
+                    assert k["bias2"].shape[1] == w.shape[0]
+                return torch.zeros(NB * H * W, w.shape[0])
+            if op == "im2col_s2":
+                x, NB, H, W = a[:4]
+                assert x.shape[0] == NB * H * W
+                return torch.zeros(NB * (H // 2) * (W // 2), 9 * x.shape[1])
+            if op == "upsample2x":
+                x, NB, H, W = a[:4]
+                assert x.shape[0] == NB * H * W
+                return torch.zeros(4 * x.shape[0], x.shape[1])
+            if op == "conv_out_tc":
+                x, NB, H, W = a[:4]
+                assert x.shape[0] == NB * H * W and a[6].shape[0] == NB and a[6].shape[2:] == (H, W)
+                return a[6]
+            if op == "timestep_embed":
+                return torch.zeros(a[0].shape[0], a[1])
+            if op == "skinny_linear":
+                x, w = a[:2]
+                assert w.shape[1] == x.shape[1]
+                return torch.zeros(x.shape[0], w.shape[0])
             raise AttributeError(op)
         return f
 
@@ -297,3 +336,47 @@ def test_fold_layernorm_algebra():
     wp, csp, bp = ops.fold_layernorm(w, b, g, be, geglu=True)          # packed row order is applied consistently
     w0, b0, _ = ops.pack_geglu(wf, bf)
     assert torch.equal(wp, w0) and torch.equal(bp, b0) and torch.allclose(csp, w0.float().sum(1))
+
+
+def test_unet_and_refnet_forward_schedules_dry_run(monkeypatch):
+    """Whole forward schedules (UNetEngine.forward_frames, RefNetEngine.forward) with shape-checking fake ops: every
+    resnet / transformer / motion / down- and up-sampling step hands consistently shaped operands to the kernels, the skip
+    stack empties, the ReferenceNet fills its 16 banks with (1, h*w, C) tensors."""
+    import torch
+    from oracle import vx_oracle as O
+    from vexpress_b200.modules import ReferenceAttentionControl, UNet2DConditionModel, UNet3DConditionModel
+    from vexpress_b200.modules import unet_2d_condition, unet_3d
+    monkeypatch.delenv("VX_LN_FOLD", raising=False)
+    cfg = O.small_cfg()
+    m = UNet3DConditionModel(
+        block_out_channels=cfg["block_out_channels"], cross_attention_dim=cfg["cross_attention_dim"],
+        use_inflated_groupnorm=True, use_motion_module=True, motion_module_mid_block=True, motion_module_type="Vanilla",
+        motion_module_kwargs=dict(num_attention_heads=8, num_transformer_block=1,
+                                  attention_block_types=["Temporal_Self", "Temporal_Self"],
+                                  temporal_position_encoding=True, temporal_position_encoding_max_len=32,
+                                  temporal_attention_dim_div=1))
+    m.load_state_dict(O.synth_state_dict(O.unet_param_shapes(cfg), 1234), strict=True)
+    eng = _cpu_engine(unet_3d.UNetEngine, m.to(torch.bfloat16))
+    net = UNet2DConditionModel(block_out_channels=cfg["block_out_channels"], cross_attention_dim=cfg["cross_attention_dim"])
+    net.load_state_dict(O.synth_state_dict(O.refnet_param_shapes(cfg), 4321), strict=True)
+    reng = _cpu_engine(unet_2d_condition.RefNetEngine, net.to(torch.bfloat16))
+    fake = _ShapeOps()
+    monkeypatch.setattr(unet_3d, "ops", fake)
+    monkeypatch.setattr(unet_2d_condition, "ops", fake)
+    b, f, h = 2, 4, 16
+    eng._bank_kv = lambda name, block: (torch.zeros(2 * 4, 2 * eng.W[name + ".norm1.weight"].shape[0]), False)
+    frames = torch.zeros(b * f, 4, h, h, dtype=torch.bfloat16)
+    enc = torch.zeros(b * f, 5, cfg["cross_attention_dim"])
+    kps = torch.zeros(b * f * h * h, cfg["block_out_channels"][0], dtype=torch.bfloat16)
+    out = eng.forward_frames(frames, 499, enc, kps, None, b, f)
+    assert out.shape == (b * f, 4, h, h)
+    assert fake.calls.count("conv3x3") == 22 * 2 + 3 and fake.calls.count("flash_attention") == 32
+    assert fake.calls.count("temporal_attention") == 42 and fake.calls.count("smallkv_attention") == 16
+    fake.calls.clear()
+    ReferenceAttentionControl(net, mode="write", fusion_blocks="full", do_classifier_free_guidance=True)
+    rout = reng.forward(torch.zeros(1, 4, h, h, dtype=torch.bfloat16), 0, torch.zeros(1, 1, cfg["cross_attention_dim"]))
+    assert rout.shape == (1, 4, h, h)
+    assert fake.calls.count("flash_attention") == 16 and fake.calls.count("temporal_attention") == 0
+    for name, blk in zip(unet_2d_condition.writer_block_names(), net.writer_blocks()):
+        C = blk.norm1.normalized_shape[0]
+        assert len(blk.bank) == 1 and blk.bank[0].shape[0] == 1 and blk.bank[0].shape[2] == C, name
