@@ -274,6 +274,9 @@ __device__ __forceinline__ float ex2_poly(float x) {
 }
 __device__ __forceinline__ void wg_bar_sync(int q) { asm volatile("bar.sync %0, 256;" ::"r"(q + 1) : "memory"); }
 // named barrier of the two warps (column halves) that share the rows of one TMEM lane quadrant: ids 3..10
+// baton between the two query tiles (256 softmax threads each): ids 11 / 12, 512 = 256 waiting + 256 arriving threads
+__device__ __forceinline__ void baton_wait(int q) { asm volatile("bar.sync %0, 512;" ::"r"(11 + q) : "memory"); }
+__device__ __forceinline__ void baton_pass(int q) { asm volatile("bar.arrive %0, 512;" ::"r"(12 - q) : "memory"); }
 __device__ __forceinline__ void pair_bar_sync(int q, int qd) { asm volatile("bar.sync %0, 64;" ::"r"(3 + q * 4 + qd) : "memory"); }
 
 struct Fa2Args {
@@ -295,7 +298,13 @@ struct Fa2Args {
 // ONES: the head dim is padded (hd 40 -> 48) and column `hd` of every V tile is set to 1.0, so the P.V product also
 // accumulates the softmax row sum in O[:, hd] (with exactly the bf16-rounded P it multiplies V with); the 64
 // per-element FADDs of the row sum disappear from the issue-bound softmax loop.
-template <bool ONES>
+// BATON (experiment, VX_FA_BATON=1, not yet run on hardware): the exponential phases of the two query tiles take turns
+// through a pair of named barriers.  Reading of the clock64 timeline + A/B sweeps (profiles/r01f_final_ncu.md): the two
+// tiles run in lock-step -- both groups of softmax warps sit in their MUFU-bound exponential phase together (~1550
+// clk), then both tiles' MMAs queue on the tensor pipe together (~1850 clk), and the two costs add up to the 3400-clk
+// iteration instead of overlapping; a one-off start offset does not survive.  With the baton one tile's exponentials
+// (alone on the MUFU units: ~900 clk) overlap the other tile's S load / row max / MMAs by construction.
+template <bool ONES, bool BATON>
 __global__ void __launch_bounds__(kFa2Threads, 1)
 flash_attn2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                    const __grid_constant__ CUtensorMap mapV, const Fa2Args p) {
@@ -476,6 +485,9 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
       }
     }
     const bool late_wait = p.p_tmem && p.late_wait;
+    if constexpr (BATON) {
+      if (q == 1) baton_pass(1);          // tile 0 exponentiates first
+    }
     for (int j = 0; j < T; ++j) {
       mbar_wait(&s_full[q], (uint32_t)(j & 1));
       tc_fence_after();
@@ -530,6 +542,7 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
       }
       const float mc = m_used * c;
       float ls[4] = {0.f, 0.f, 0.f, 0.f};
+      if constexpr (BATON) baton_wait(q);
       if (p.p_tmem) {
         uint32_t pk[32];
 #pragma unroll
@@ -548,6 +561,9 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
           }
         }
         FA_TR(6);
+        if constexpr (BATON) {
+          if (q == 0 || j + 1 < T) baton_pass(q);      // tile 1's last pass would have no taker
+        }
         if (j >= p.pbufs && late_wait) {   // P(j) overwrites the tile P.V(j - pbufs) reads: wait only now
           mbar_wait(&pv_done[2 * q + j % p.pbufs], (uint32_t)((j / p.pbufs - 1) & 1));
           tc_fence_after();
@@ -570,6 +586,9 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
             *reinterpret_cast<uint4*>(pb + (g * 4 + h) * 2048) =
                 make_uint4(pack_bf16(e[0], e[1]), pack_bf16(e[2], e[3]), pack_bf16(e[4], e[5]), pack_bf16(e[6], e[7]));
           }
+        }
+        if constexpr (BATON) {
+          if (q == 0 || j + 1 < T) baton_pass(q);
         }
         fence_proxy_async_smem();
       }
@@ -747,15 +766,19 @@ extern "C" int vx_flash_attention(const void* q, long long ldq, const void* k, l
     }
     static bool cfg2 = false;
     if (!cfg2) {
-      VX_CHECK_CUDA(cudaFuncSetAttribute(flash_attn2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      VX_CHECK_CUDA(cudaFuncSetAttribute(flash_attn2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      VX_CHECK_CUDA(cudaFuncSetAttribute(flash_attn2_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      VX_CHECK_CUDA(cudaFuncSetAttribute(flash_attn2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      VX_CHECK_CUDA(cudaFuncSetAttribute(flash_attn2_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      VX_CHECK_CUDA(cudaFuncSetAttribute(flash_attn2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       cfg2 = true;
     }
     dim3 grid2(Nq / 256, heads, Bq);
-    if (hdp > hd && !getenv("VX_FA_NOONES"))
-      flash_attn2_kernel<true><<<grid2, kFa2Threads, smem2, (cudaStream_t)stream>>>(mQ, mK, mV, a);
-    else
-      flash_attn2_kernel<false><<<grid2, kFa2Threads, smem2, (cudaStream_t)stream>>>(mQ, mK, mV, a);
+    const bool ones = hdp > hd && !getenv("VX_FA_NOONES");
+    const bool baton = getenv("VX_FA_BATON") && atoi(getenv("VX_FA_BATON")) != 0;
+    if (ones && baton) flash_attn2_kernel<true, true><<<grid2, kFa2Threads, smem2, (cudaStream_t)stream>>>(mQ, mK, mV, a);
+    else if (ones) flash_attn2_kernel<true, false><<<grid2, kFa2Threads, smem2, (cudaStream_t)stream>>>(mQ, mK, mV, a);
+    else if (baton) flash_attn2_kernel<false, true><<<grid2, kFa2Threads, smem2, (cudaStream_t)stream>>>(mQ, mK, mV, a);
+    else flash_attn2_kernel<false, false><<<grid2, kFa2Threads, smem2, (cudaStream_t)stream>>>(mQ, mK, mV, a);
     VX_CHECK_CUDA(cudaGetLastError());
     return 0;
   }
