@@ -486,6 +486,8 @@ def ours(args):
                     unet_ms_per_step=unet_ms_per_step, vae_decode_ms=vae_ms,
                     whole_path=dict(tflop_per_pass=work_tflop, achieved_tflops=work_tflop * args.steps / sec / n,
                                     frac_of_sustained_peak=work_tflop * args.steps / sec / n / pk["tf_sustained"]))
+        if n == 1 and os.environ.get("VX_BENCH_REFNET"):
+            line["refnet_write_pass_ms"] = refnet_time(h)
         if roof_k:
             dom = dict(tflops=0.0, seconds=0.0, launches=0, flop=0.0)
             for k in ("gemm", "conv3x3"):
@@ -505,6 +507,33 @@ def ours(args):
         print(json.dumps(line))
     if dist:
         torch.distributed.destroy_process_group()
+
+
+def refnet_time(h, iters=3):
+    """VX_BENCH_REFNET=1 (not part of the headline metric): ReferenceNet write pass, full SD-1.5 width,
+    one (1,4,h,h) reference latent at t = 0 with a zero text token, CUDA-event time per pass in ms."""
+    from vexpress_b200.modules import ReferenceAttentionControl, UNet2DConditionModel
+    with torch.device("cuda"):
+        net = UNet2DConditionModel(cross_attention_dim=768)
+    fill_synthetic_(net, 4321)
+    net = net.to(torch.bfloat16)
+    writer = ReferenceAttentionControl(net, do_classifier_free_guidance=True, mode="write", batch_size=1,
+                                       fusion_blocks="full")
+    x = torch.randn(1, 4, h, h, device="cuda").to(torch.bfloat16)
+    enc = torch.zeros(1, 1, 768, device="cuda", dtype=torch.bfloat16)
+    net(x, timestep=0, encoder_hidden_states=enc, return_dict=False)
+    writer.clear()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        net(x, timestep=0, encoder_hidden_states=enc, return_dict=False)
+        writer.clear()
+    e1.record()
+    torch.cuda.synchronize()
+    del net, writer
+    torch.cuda.empty_cache()
+    return e0.elapsed_time(e1) / iters
 
 
 def pipe_decode_device(pipe, latents, dist):
