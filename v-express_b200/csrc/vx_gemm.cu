@@ -517,7 +517,7 @@ static bool pair_ok(int out_f32, int block_n, long long tiles_m, int total_kb) {
   // the output stores, where two independent CTAs overlap better (profiles/tools/gemm_sweep.py).
   const int mode = env_int("VX_GEMM_CG", 0);   // 0 = auto, 1 = never, 2 = whenever legal
   if (out_f32 || block_n % 32 != 0 || tiles_m < 2 || mode == 1) return false;
-  return mode == 2 || total_kb >= 12;
+  return mode == 2 || total_kb >= env_int("VX_GEMM_CG_MINKB", 12);   // threshold from profiles/tools/gemm_sweep.py
 }
 
 // resident CTA pairs of the persistent cta_group::2 kernel (GPCs with an odd SM count strand one SM)
