@@ -212,14 +212,33 @@ def groupnorm(x1, NB, HW, gamma, beta, eps, silu, x2=None, groups=32, out=None, 
 
     VX_GN_FRAMES=n (experiment, default off) runs the statistics and the apply kernel on groups of n frames
     back to back so that the second read of a group is served by the L2 instead of HBM."""
+    grp = int(os.environ.get("VX_GN_FRAMES", "0"))
+    if 0 < grp < NB:
+        return _groupnorm_grouped(x1, NB, HW, gamma, beta, eps, silu, x2, groups, out, grp)
+    _chk_bf16(x1, x2, out)
+    C1 = x1.shape[1]
+    C2 = 0 if x2 is None else x2.shape[1]
+    S = _gn_S(NB, HW)
+    if ws is None:
+        ws = torch.empty(NB * S * groups * 3, device=x1.device, dtype=torch.float32)
+    if out is None:
+        out = torch.empty((NB * HW, C1 + C2), device=x1.device, dtype=BF16)
+    L = _ffi.lib()
+    ld2 = c_ll(0 if x2 is None else x2.stride(0))
+    check(L.vx_groupnorm_stats(ptr(x1), c_ll(x1.stride(0)), c_int(C1), ptr(x2), ld2, c_int(C2), c_int(NB), c_int(HW),
+                               c_int(groups), c_int(S), ptr(ws), stream_ptr()), "vx_groupnorm_stats")
+    check(L.vx_groupnorm_apply(ptr(x1), c_ll(x1.stride(0)), c_int(C1), ptr(x2), ld2, c_int(C2), c_int(NB), c_int(HW),
+                               c_int(groups), c_int(S), ptr(ws), ptr(gamma), ptr(beta), c_float(eps), c_int(int(silu)),
+                               ptr(out), c_ll(out.stride(0)), stream_ptr()), "vx_groupnorm_apply")
+    return out
+
+
+def _groupnorm_grouped(x1, NB, HW, gamma, beta, eps, silu, x2, groups, out, grp):
     _chk_bf16(x1, x2, out)
     C1 = x1.shape[1]
     C2 = 0 if x2 is None else x2.shape[1]
     if out is None:
         out = torch.empty((NB * HW, C1 + C2), device=x1.device, dtype=BF16)
-    grp = int(os.environ.get("VX_GN_FRAMES", "0"))
-    if grp <= 0 or grp >= NB:
-        grp = NB
     L = _ffi.lib()
     for n0 in range(0, NB, grp):
         nb = min(grp, NB - n0)
@@ -228,13 +247,13 @@ def groupnorm(x1, NB, HW, gamma, beta, eps, silu, x2=None, groups=32, out=None, 
         a2 = None if x2 is None else x2[r0:r1]
         o = out[r0:r1]
         S = _gn_S(nb, HW)
-        w = ws if (ws is not None and grp == NB) else torch.empty(nb * S * groups * 3, device=x1.device, dtype=torch.float32)
+        w = torch.empty(nb * S * groups * 3, device=x1.device, dtype=torch.float32)
         ld2 = c_ll(0 if a2 is None else a2.stride(0))
         check(L.vx_groupnorm_stats(ptr(a1), c_ll(a1.stride(0)), c_int(C1), ptr(a2), ld2, c_int(C2), c_int(nb), c_int(HW),
                                    c_int(groups), c_int(S), ptr(w), stream_ptr()), "vx_groupnorm_stats")
         check(L.vx_groupnorm_apply(ptr(a1), c_ll(a1.stride(0)), c_int(C1), ptr(a2), ld2, c_int(C2), c_int(nb), c_int(HW),
                                    c_int(groups), c_int(S), ptr(w), ptr(gamma), ptr(beta), c_float(eps), c_int(int(silu)),
-                                   ptr(out if grp == NB else o), c_ll(out.stride(0)), stream_ptr()), "vx_groupnorm_apply")
+                                   ptr(o), c_ll(out.stride(0)), stream_ptr()), "vx_groupnorm_apply")
     return out
 
 
