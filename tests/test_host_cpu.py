@@ -380,3 +380,90 @@ def test_unet_and_refnet_forward_schedules_dry_run(monkeypatch):
     for name, blk in zip(unet_2d_condition.writer_block_names(), net.writer_blocks()):
         C = blk.norm1.normalized_shape[0]
         assert len(blk.bank) == 1 and blk.bank[0].shape[0] == 1 and blk.bank[0].shape[2] == C, name
+
+
+class _EmuOps:
+    """Functional CPU emulation (fp32 math, bf16 outputs) of the operators the prologue modules compose, with the kernels'
+    layout conventions: conv_in's transposed fp32 weights, im2col's (tap, channel) K order, pack_geglu's tile layout."""
+
+    def __init__(self):
+        from vexpress_b200 import ops
+        self.real = ops
+
+    def __getattr__(self, name):           # pure-torch packers
+        return getattr(self.real, name)
+
+    @staticmethod
+    def conv_in(x, w, bias, cout, **_):
+        import torch.nn.functional as F
+        n, cin, H, W = x.shape
+        y = F.conv2d(x.float(), w.t().reshape(cout, cin, 3, 3), bias, padding=1)
+        return y.permute(0, 2, 3, 1).reshape(n * H * W, cout).to(torch.bfloat16)
+
+    @staticmethod
+    def im2col3x3(a, n, h, w, stride=1, silu=False, out=None):
+        import torch.nn.functional as F
+        C = a.shape[1]
+        x = a.float().view(n, h, w, C).permute(0, 3, 1, 2)
+        if silu:
+            x = F.silu(x).to(torch.bfloat16).float()
+        col = F.unfold(x, 3, padding=1, stride=stride)                       # (n, C*9, L), index c*9 + tap
+        L = col.shape[-1]
+        return col.view(n, C, 9, L).permute(0, 3, 2, 1).reshape(n * L, 9 * C).to(torch.bfloat16)
+
+    def gemm(self, a, w, bias=None, *, residual=None, geglu=False, **_):
+        import torch.nn.functional as F
+        acc = a.float() @ w.float().t()
+        if bias is not None:
+            acc = acc + bias
+        if geglu:
+            bn = self.real.geglu_block_n(w.shape[0])
+            t = acc.view(acc.shape[0], -1, 2, bn // 2)
+            acc = (t[:, :, 0] * F.gelu(t[:, :, 1])).reshape(acc.shape[0], -1)
+        if residual is not None:
+            acc = acc + residual.float()
+        return acc.to(torch.bfloat16)
+
+    @staticmethod
+    def layernorm(x, g, b, **_):
+        import torch.nn.functional as F
+        return F.layer_norm(x.float(), (x.shape[1],), g, b, 1e-5).to(torch.bfloat16)
+
+    @staticmethod
+    def flash_attention(q, k, v, heads, Nq, Nk, **_):
+        import torch.nn.functional as F
+        B, C = q.shape[0] // Nq, q.shape[1]
+        sp = lambda t, n: t.float().reshape(B, n, heads, C // heads).transpose(1, 2)
+        o = F.scaled_dot_product_attention(sp(q, Nq), sp(k, Nk), sp(v, Nk))
+        return o.transpose(1, 2).reshape(B * Nq, C).to(torch.bfloat16)
+
+
+import torch  # noqa: E402  (used by the emulation above)
+
+
+def test_prologue_modules_compose_correctly(monkeypatch, golden_dir):
+    """VKpsGuider / AudioProjection mirrors with the kernels replaced by functional CPU emulations: the
+    composition (channel padding to 32, conv_in weight transposition, im2col K order, stride pattern, GELU through the
+    GEGLU epilogue, perceiver token concatenation) reproduces the reference-generated golden to bf16 accuracy."""
+    from oracle import vx_oracle as O
+    from vexpress_b200 import _ffi
+    from vexpress_b200.modules import prologue
+    monkeypatch.setattr(_ffi, "require_sm100", lambda: None)
+    monkeypatch.setattr(prologue, "ops", _EmuOps())
+    g = torch.load(os.path.join(golden_dir, "prologue_small.pt"), weights_only=False)
+    rel = lambda a, b: ((a.float() - b.float()).norm() / b.float().norm()).item()
+    k = g["kps"]
+    m = prologue.VKpsGuider(320, block_out_channels=(16, 32, 96, 256))
+    m.load_state_dict(O.synth_state_dict(O.kps_guider_param_shapes(O.KPS_CFG), k["seed_weights"]))
+    m = m.to(torch.bfloat16)
+    x = torch.rand(*k["shape"], generator=torch.Generator().manual_seed(k["seed_input"]))
+    y = m(x, frames_per_chunk=1)
+    assert y.shape == k["feature"].shape and rel(y, k["feature"]) < 2e-2, rel(y, k["feature"])
+    a = g["audio_projection"]
+    p = prologue.AudioProjection(dim=768, depth=4, dim_head=64, heads=12, num_queries=5, embedding_dim=768,
+                                 output_dim=768, ff_mult=4, max_seq_len=10)
+    p.load_state_dict(O.synth_state_dict(O.audio_projection_param_shapes(O.AUDIO_PROJ_CFG), a["seed_weights"]))
+    p = p.to(torch.bfloat16)
+    xa = torch.randn(*a["shape"], generator=torch.Generator().manual_seed(a["seed_input"]))
+    ya = p(xa)
+    assert ya.shape == a["tokens"].shape and rel(ya, a["tokens"]) < 2e-2, rel(ya, a["tokens"])

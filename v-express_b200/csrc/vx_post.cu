@@ -4,8 +4,8 @@
 //   tensor per frame and moves every frame device <-> CPU; here one thread owns one output pixel (all channels),
 //   gathers the 27 neighbours through L1 and selects the median with a pruned Batcher odd-even merge network held in
 //   registers (selection, so the result is bit-exact).  Compute-light and HBM-light: 4 B read + 1 B written per value.
-// NOT YET RUN ON A GPU (written at the end of round 1 without budget left): tests/test_zz_post_gpu.py is skipped
-// unless VX_TEST_UNVERIFIED=1.
+// NOT YET RUN ON A GPU (written at the end of round 1 without budget left): tests/test_zz_post_gpu.py and
+// tests/test_zz_prologue_gpu.py are skipped unless VX_TEST_UNVERIFIED=1.
 #include "vx_host.h"
 #include "vx_ptx.cuh"
 
@@ -75,9 +75,54 @@ __global__ void __launch_bounds__(256) median3d_kernel(const float* __restrict__
   }
 }
 
+// ------------------------------------------------------------------ im2col (3x3, stride 1 or 2, pad 1), NHWC, with
+// an optional SiLU on the gathered input: the conv stacks of the conditioning prologue (VKpsGuider, SURVEY 8f-f2;
+// reference modules/v_kps_guider.py:35-45) are conv -> SiLU chains with 16..256 channels, too narrow for the
+// implicit-GEMM conv (C % 64); they run as im2col(SiLU(x)) + tensor-core GEMM instead.  K order = (tap, channel), the
+// order of pack_conv3x3_weight.  Same structure as im2col_s2_kernel (vx_misc.cu).
+__global__ void im2col3x3_kernel(const __nv_bfloat16* __restrict__ x, int NB, int H, int W, int C, int stride, int silu,
+                                 __nv_bfloat16* __restrict__ out) {
+  const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1, V = C / 8;
+  const long long total = (long long)NB * Ho * Wo * 9 * V;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(idx % V);
+    const int t = (int)((idx / V) % 9);
+    const long long opix = idx / ((long long)V * 9);
+    const int ox = (int)(opix % Wo), oy = (int)((opix / Wo) % Ho);
+    const long long n = opix / ((long long)Wo * Ho);
+    const int yy = oy * stride + t / 3 - 1, xx = ox * stride + t % 3 - 1;
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+      val = *reinterpret_cast<const uint4*>(x + ((n * H + yy) * W + xx) * C + v * 8);
+      if (silu) {
+        uint32_t w4[4] = {val.x, val.y, val.z, val.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = unpack_bf16(w4[i]);
+          w4[i] = pack_bf16(f.x / (1.f + __expf(-f.x)), f.y / (1.f + __expf(-f.y)));
+        }
+        val = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+      }
+    }
+    *reinterpret_cast<uint4*>(out + opix * 9 * C + (long long)t * C + v * 8) = val;
+  }
+}
+
 }  // namespace vx
 
 using namespace vx;
+
+extern "C" int vx_im2col3x3(const void* x, int NB, int H, int W, int C, int stride, int silu, void* out, void* stream) {
+  VX_REQUIRE(C % 8 == 0 && (stride == 1 || stride == 2), "vx_im2col3x3: C=%d stride=%d", C, stride);
+  const long long total = (long long)NB * ((H - 1) / stride + 1) * ((W - 1) / stride + 1) * 9 * (C / 8);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  im2col3x3_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, NB, H, W, C, stride, silu,
+                                                                      (__nv_bfloat16*)out);
+  VX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
 
 extern "C" int vx_median3d_u8(const float* video, int C, int T, int H, int W, float* filtered, unsigned char* frames,
                               void* stream) {
