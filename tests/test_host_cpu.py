@@ -394,11 +394,16 @@ class _EmuOps:
         return getattr(self.real, name)
 
     @staticmethod
-    def conv_in(x, w, bias, cout, **_):
+    def conv_in(x, w, bias, cout, addend=None, add_frame=None, out=None, **_):
         import torch.nn.functional as F
         n, cin, H, W = x.shape
         y = F.conv2d(x.float(), w.t().reshape(cout, cin, 3, 3), bias, padding=1)
-        return y.permute(0, 2, 3, 1).reshape(n * H * W, cout).to(torch.bfloat16)
+        y = y.permute(0, 2, 3, 1).reshape(n * H * W, cout)
+        if addend is not None:
+            fr = torch.arange(n) if add_frame is None else add_frame.long()
+            rows = (fr[:, None] * (H * W) + torch.arange(H * W)[None]).reshape(-1)
+            y = y + addend.float()[rows]
+        return y.to(torch.bfloat16)
 
     @staticmethod
     def im2col3x3(a, n, h, w, stride=1, silu=False, out=None):
@@ -411,31 +416,136 @@ class _EmuOps:
         L = col.shape[-1]
         return col.view(n, C, 9, L).permute(0, 3, 2, 1).reshape(n * L, 9 * C).to(torch.bfloat16)
 
-    def gemm(self, a, w, bias=None, *, residual=None, geglu=False, **_):
+    def gemm(self, a, w, bias=None, *, a2=None, bias2=None, bias2_div=1, scale=1.0, residual=None, out=None,
+             geglu=False, out_f32=False, **_):
         import torch.nn.functional as F
-        acc = a.float() @ w.float().t()
+        af = a.float() if a2 is None else torch.cat([a.float(), a2.float()], 1)
+        acc = af @ w.float().t()
         if bias is not None:
             acc = acc + bias
+        if bias2 is not None:
+            acc = acc + bias2[torch.arange(acc.shape[0]) // bias2_div]
         if geglu:
             bn = self.real.geglu_block_n(w.shape[0])
             t = acc.view(acc.shape[0], -1, 2, bn // 2)
             acc = (t[:, :, 0] * F.gelu(t[:, :, 1])).reshape(acc.shape[0], -1)
+        acc = acc * scale
         if residual is not None:
             acc = acc + residual.float()
-        return acc.to(torch.bfloat16)
+        return self._ret(acc if out_f32 else acc.to(torch.bfloat16), out)
 
     @staticmethod
-    def layernorm(x, g, b, **_):
+    def layernorm(x, g, b, eps=1e-5, pe=None, rows_per_frame=0, out=None):
         import torch.nn.functional as F
-        return F.layer_norm(x.float(), (x.shape[1],), g, b, 1e-5).to(torch.bfloat16)
+        y = F.layer_norm(x.float(), (x.shape[1],), g, b, eps)
+        if pe is not None:
+            y = y + pe[(torch.arange(x.shape[0]) // rows_per_frame) % pe.shape[0]]
+        return y.to(torch.bfloat16)
 
     @staticmethod
-    def flash_attention(q, k, v, heads, Nq, Nk, **_):
+    def _ret(val, out):
+        if out is not None:
+            out.copy_(val.to(out.dtype))
+            return out
+        return val
+
+    def flash_attention(self, q, k, v, heads, Nq, Nk, kv_div=1, out=None):
         import torch.nn.functional as F
         B, C = q.shape[0] // Nq, q.shape[1]
-        sp = lambda t, n: t.float().reshape(B, n, heads, C // heads).transpose(1, 2)
-        o = F.scaled_dot_product_attention(sp(q, Nq), sp(k, Nk), sp(v, Nk))
-        return o.transpose(1, 2).reshape(B * Nq, C).to(torch.bfloat16)
+        Bkv = k.shape[0] // Nk
+        qh = q.float().reshape(B, Nq, heads, C // heads).transpose(1, 2)
+        idx = torch.arange(B) // kv_div
+        kh = k.float().reshape(Bkv, Nk, heads, C // heads).transpose(1, 2)[idx]
+        vh = v.float().reshape(Bkv, Nk, heads, C // heads).transpose(1, 2)[idx]
+        o = F.scaled_dot_product_attention(qh, kh, vh)
+        return self._ret(o.transpose(1, 2).reshape(B * Nq, C).to(torch.bfloat16), out)
+
+    # ---- the remaining operators of the UNet / ReferenceNet schedules
+    @staticmethod
+    def timestep_embed(t, dim, out=None):
+        import math
+        half = dim // 2
+        freq = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32) / half)
+        a = t.float()[:, None] * freq[None]
+        return torch.cat([torch.cos(a), torch.sin(a)], 1).to(torch.bfloat16).float()
+
+    @staticmethod
+    def skinny_linear(x, w, bias, act_in=False, act_out=False, out=None):
+        import torch.nn.functional as F
+        y = (F.silu(x) if act_in else x) @ w.float().t() + bias
+        return F.silu(y) if act_out else y
+
+    def conv3x3(self, x, w, bias=None, *, bias2=None, bias2_div=1, scale=1.0, residual=None, out=None, **_):
+        import torch.nn.functional as F
+        NB, H, W, C = x.shape
+        w4 = w.float().view(w.shape[0], 3, 3, C).permute(0, 3, 1, 2)
+        y = F.conv2d(x.float().permute(0, 3, 1, 2), w4, bias, padding=1).permute(0, 2, 3, 1).reshape(NB * H * W, -1)
+        if bias2 is not None:
+            y = y + bias2[torch.arange(y.shape[0]) // bias2_div]
+        y = y * scale
+        if residual is not None:
+            y = y + residual.float()
+        return self._ret(y.to(torch.bfloat16), out)
+
+    def groupnorm(self, x1, NB, HW, gamma, beta, eps, silu, x2=None, groups=32, out=None, ws=None):
+        import torch.nn.functional as F
+        x = x1.float() if x2 is None else torch.cat([x1.float(), x2.float()], 1)
+        C = x.shape[1]
+        y = F.group_norm(x.view(NB, HW, C).transpose(1, 2), groups, gamma, beta, eps)
+        if silu:
+            y = F.silu(y)
+        return self._ret(y.transpose(1, 2).reshape(NB * HW, C).to(torch.bfloat16), out)
+
+    def temporal_attention(self, q, k, v, b, f, HW, heads, out=None):
+        import torch.nn.functional as F
+        C = q.shape[1]
+        sp = lambda t: t.float().reshape(b, f, HW, heads, C // heads).permute(0, 2, 3, 1, 4)      # (b, hw, heads, f, hd)
+        o = F.scaled_dot_product_attention(sp(q), sp(k), sp(v))
+        return self._ret(o.permute(0, 3, 1, 2, 4).reshape(b * f * HW, C).to(torch.bfloat16), out)
+
+    def smallkv_attention(self, q, k, v, rows_per_frame, heads, Lk, out=None):
+        import torch.nn.functional as F
+        C = q.shape[1]
+        fr = q.shape[0] // rows_per_frame
+        qh = q.float().reshape(fr, rows_per_frame, heads, C // heads).transpose(1, 2)
+        kh = k.float().reshape(fr, Lk, heads, C // heads).transpose(1, 2)
+        vh = v.float().reshape(fr, Lk, heads, C // heads).transpose(1, 2)
+        o = F.scaled_dot_product_attention(qh, kh, vh)
+        return self._ret(o.transpose(1, 2).reshape(q.shape[0], C).to(torch.bfloat16), out)
+
+    def im2col_s2(self, x, NB, H, W, out=None):
+        return self._ret(self.im2col3x3(x, NB, H, W, stride=2), out)
+
+    def upsample2x(self, x, NB, H, W, out=None):
+        C = x.shape[1]
+        y = x.view(NB, H, 1, W, 1, C).expand(NB, H, 2, W, 2, C).reshape(NB * 4 * H * W, C)
+        return self._ret(y.contiguous(), out)
+
+    def conv_out_tc(self, x, NB, H, W, wp, bp, out, post=False):
+        y = self.conv3x3(x.view(NB, H, W, -1), wp, bp).float()
+        co = out.shape[1]
+        out.copy_(y[:, :co].reshape(NB, H, W, co).permute(0, 3, 1, 2).to(out.dtype))
+        return out
+
+    @staticmethod
+    def row_stats(x, eps=1e-5, out=None):
+        xf = x.float()
+        return torch.stack([xf.mean(1), (xf.var(1, unbiased=False) + eps).rsqrt()], 1)
+
+    def gemm_lnfold(self, a, wf, stats, colsum, bias, *, bias2=None, bias2_div=1, scale=1.0, residual=None, out=None,
+                    geglu=False):
+        import torch.nn.functional as F
+        acc = stats[:, 1:2] * (a.float() @ wf.float().t() - stats[:, 0:1] * colsum[None]) + bias
+        if bias2 is not None:
+            acc = acc + bias2[torch.arange(acc.shape[0]) // bias2_div]
+        if geglu:
+            bn = self.real.geglu_block_n(wf.shape[0])
+            t = acc.view(acc.shape[0], -1, 2, bn // 2)
+            acc = (t[:, :, 0] * F.gelu(t[:, :, 1])).reshape(acc.shape[0], -1)
+        acc = acc * scale
+        if residual is not None:
+            acc = acc + residual.float()
+        return self._ret(acc.to(torch.bfloat16), out)
 
 
 import torch  # noqa: E402  (used by the emulation above)
@@ -467,3 +577,69 @@ def test_prologue_modules_compose_correctly(monkeypatch, golden_dir):
     xa = torch.randn(*a["shape"], generator=torch.Generator().manual_seed(a["seed_input"]))
     ya = p(xa)
     assert ya.shape == a["tokens"].shape and rel(ya, a["tokens"]) < 2e-2, rel(ya, a["tokens"])
+
+
+@pytest.mark.parametrize("fold", ["0", "1"])
+def test_unet_engine_matches_oracle_with_emulated_kernels(monkeypatch, golden_dir, fold):
+    """The whole UNetEngine.forward_frames host schedule (weight packing, split-K concat, time-embedding bias, banks,
+    CFG uncond-half skip, GEGLU packing, ...) with every kernel replaced by a functional CPU emulation, against the
+    oracle -- in the default mode and with VX_LN_FOLD=1 (LayerNorm folded into the GEMM epilogue, positional encoding
+    as a per-frame bias)."""
+    from oracle import vx_oracle as O
+    from vexpress_b200.modules import ReferenceAttentionControl, UNet3DConditionModel, unet_3d
+    monkeypatch.setenv("VX_LN_FOLD", fold)
+    cfg = O.small_cfg()
+    m = UNet3DConditionModel(
+        block_out_channels=cfg["block_out_channels"], cross_attention_dim=cfg["cross_attention_dim"],
+        use_inflated_groupnorm=True, use_motion_module=True, motion_module_mid_block=True, motion_module_type="Vanilla",
+        motion_module_kwargs=dict(num_attention_heads=8, num_transformer_block=1,
+                                  attention_block_types=["Temporal_Self", "Temporal_Self"],
+                                  temporal_position_encoding=True, temporal_position_encoding_max_len=32,
+                                  temporal_attention_dim_div=1))
+    sd = O.synth_state_dict(O.unet_param_shapes(cfg), 1234)
+    m.load_state_dict(sd, strict=True)
+    m = m.to(torch.bfloat16)
+    f, h = 4, 16
+    lat, kps, audio, banks = O.synth_inputs(cfg, f, h, h, True, 42)
+    reader = ReferenceAttentionControl(m, do_classifier_free_guidance=True, mode="read", fusion_blocks="full",
+                                       reference_attention_weight=0.95, audio_attention_weight=3.0)
+    reader.update(type("W", (), {"banks": [b[1:] for b in banks]})(), True, dtype=torch.bfloat16)
+    emu = _EmuOps()
+    monkeypatch.setattr(unet_3d, "ops", emu)          # packing below and the forward both go through the emulation
+    eng = _cpu_engine(unet_3d.UNetEngine, m)
+    eng._bank_cache, eng._bank_buf, eng._bank_flag, eng.bank_epoch = {}, {}, {}, 0
+    x = lat.repeat(2, 1, 1, 1, 1)
+    frames = x.to(torch.bfloat16).permute(0, 2, 1, 3, 4).reshape(2 * f, 4, h, h).contiguous()
+    kps_rows = kps.to(torch.bfloat16).permute(0, 2, 3, 4, 1).reshape(2 * f * h * h, -1).contiguous()
+    enc = audio.reshape(-1, 5, cfg["cross_attention_dim"])
+    out = eng.forward_frames(frames, 499, enc, kps_rows, None, 2, f)
+    out = out.view(2, f, 4, h, h).permute(0, 2, 1, 3, 4).float()
+    with torch.no_grad():
+        ref = O.unet_forward(sd, cfg, x, 499, enc, kps, banks, 0.95, 3.0)
+    err = ((out - ref).norm() / ref.norm()).item()
+    print(f"emulated engine vs oracle (VX_LN_FOLD={fold}): rel-L2 {err:.3e}")
+    assert err < 3e-2, err
+
+
+def test_refnet_engine_matches_golden_with_emulated_kernels(monkeypatch, golden_dir):
+    """RefNetEngine host schedule (write pass) on the functional CPU emulation against the golden produced by
+    the reference's own UNet2D + write hooks."""
+    from oracle import vx_oracle as O
+    from vexpress_b200.modules import ReferenceAttentionControl, UNet2DConditionModel, unet_2d_condition, unet_3d
+    g = torch.load(os.path.join(golden_dir, "refnet_small.pt"), weights_only=False)
+    cfg = g["cfg"]
+    net = UNet2DConditionModel(block_out_channels=cfg["block_out_channels"], cross_attention_dim=cfg["cross_attention_dim"])
+    net.load_state_dict(O.synth_state_dict(O.refnet_param_shapes(cfg), g["seed_weights"]), strict=True)
+    net = net.to(torch.bfloat16)
+    emu = _EmuOps()
+    monkeypatch.setattr(unet_3d, "ops", emu)
+    monkeypatch.setattr(unet_2d_condition, "ops", emu)
+    eng = _cpu_engine(unet_2d_condition.RefNetEngine, net)
+    writer = ReferenceAttentionControl(net, mode="write", fusion_blocks="full", do_classifier_free_guidance=True)
+    x = torch.randn(1, 4, g["h"], g["h"], generator=torch.Generator().manual_seed(g["seed_latents"]))
+    out = eng.forward(x.to(torch.bfloat16), 0, torch.zeros(1, 1, cfg["cross_attention_dim"]))
+    rel = lambda a, b: ((a.float() - b.float()).norm() / b.float().norm()).item()
+    banks = ReferenceAttentionControl._writer_banks(writer)
+    worst = max(rel(b[0], r) for b, r in zip(banks, g["banks"]))
+    print(f"emulated refnet: banks worst rel-L2 {worst:.3e}, out {rel(out, g['out']):.3e}")
+    assert worst < 3e-2 and rel(out, g["out"]) < 5e-2
