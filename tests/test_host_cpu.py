@@ -643,3 +643,37 @@ def test_refnet_engine_matches_golden_with_emulated_kernels(monkeypatch, golden_
     worst = max(rel(b[0], r) for b, r in zip(banks, g["banks"]))
     print(f"emulated refnet: banks worst rel-L2 {worst:.3e}, out {rel(out, g['out']):.3e}")
     assert worst < 3e-2 and rel(out, g["out"]) < 5e-2
+
+
+def test_pipeline_prologue_glue_matches_reference(golden_dir):
+    """prepare_audio_embeddings / prepare_kps_feature of the pipeline mirror (reference :350-407) with stub encoder,
+    identity projection and a stub guider: windowing bit-equal to the golden produced by the reference method itself,
+    CFG zero halves, 16-frame chunking of the guider."""
+    from PIL import Image
+    import numpy as np
+    from vexpress_b200.pipelines.v_express_pipeline import VExpressPipeline
+    g = torch.load(os.path.join(golden_dir, "prologue_small.pt"), weights_only=False)["audio_windows"]
+
+    class Unet:
+        device, dtype = torch.device("cpu"), torch.float32
+    calls = []
+
+    class Guider:
+        def __call__(self, x):
+            calls.append(x.shape[2])
+            return x[:, :1].repeat(1, 5, 1, 1, 1)[..., ::8, ::8] * 2.0
+
+    class Enc:
+        def __call__(self, w):
+            return type("R", (), {"last_hidden_state": w})()
+    pipe = VExpressPipeline(vae=None, reference_net=None, denoising_unet=Unet(), v_kps_guider=Guider(),
+                            audio_processor=None, audio_encoder=Enc(), audio_projection=lambda x: x, scheduler=None)
+    emb = torch.randn(*g["shape"], generator=torch.Generator().manual_seed(g["seed_input"]))
+    out = pipe.prepare_audio_embeddings(emb, g["video_length"], g["num_pad"], True)
+    assert out.shape[0] == 2 and torch.count_nonzero(out[0]).item() == 0 and torch.equal(out[1], g["windows"])
+    imgs = [Image.fromarray(np.full((64, 64, 3), i, dtype=np.uint8)) for i in range(20)]
+    kf = pipe.prepare_kps_feature(imgs, 64, 64, True)
+    assert calls == [16, 4] and kf.shape == (2, 5, 20, 8, 8) and torch.count_nonzero(kf[0]).item() == 0
+    assert torch.allclose(kf[1, 0, :, 0, 0], torch.arange(20) / 255.0 * 2.0)
+    with pytest.raises(ValueError):
+        pipe.prepare_kps_feature(torch.zeros(1, 3, 2, 32, 32), 64, 64, False)

@@ -146,11 +146,73 @@ class VExpressPipeline:
         raise NotImplementedError("prologue hook: VAE encode of the reference image is outside the hot path "
                                   "(SURVEY.md 8f-f4); override or pass precomputed banks")
 
+    @staticmethod
+    def _condition_images_to_tensor(images, height, width):
+        """The reference's ``condition_image_processor.preprocess`` (VaeImageProcessor(do_convert_rgb=True,
+        do_normalize=False), pipelines/v_express_pipeline.py:112-115,352-356) for the cases that need no resampling:
+        a (b,3,t,H,W) tensor in [0,1], or a list of RGB PIL images / HWC uint8 arrays.  -> (1,3,t,H,W) fp32 in [0,1]."""
+        import numpy as np
+        if torch.is_tensor(images):
+            if images.dim() != 5 or images.shape[-2:] != (height, width):
+                raise ValueError(f"kps images tensor must be (b,3,t,{height},{width}), got {tuple(images.shape)}")
+            return images.float()
+        frames = []
+        for img in images:
+            if hasattr(img, "convert"):                      # PIL
+                img = img.convert("RGB")
+                if img.size != (width, height):
+                    from PIL import Image
+                    img = img.resize((width, height), resample=Image.LANCZOS)   # VaeImageProcessor default "lanczos"
+            arr = np.asarray(img)
+            if arr.shape[:2] != (height, width):
+                raise ValueError(f"kps image of size {arr.shape[:2]} needs resampling to {(height, width)}: pass PIL images")
+            frames.append(torch.from_numpy(arr.astype(np.float32) / 255.0).permute(2, 0, 1))
+        return torch.stack(frames, 1).unsqueeze(0)
+
     def prepare_kps_feature(self, kps_images, height, width, do_classifier_free_guidance):
-        raise NotImplementedError("prologue hook: VKpsGuider is outside the hot path (SURVEY.md 8f-f2)")
+        """Reference pipelines/v_express_pipeline.py:350-372: keypoint images -> VKpsGuider in chunks of 16 frames ->
+        (b, 320, L, h, w) with the CFG zero half in front.  The features stay on the device (the reference parks
+        them on the CPU and copies a window per step)."""
+        if self.v_kps_guider is None:
+            raise NotImplementedError("prologue hook: pass a VKpsGuider (vexpress_b200.modules.VKpsGuider or the "
+                                      "reference's) or override prepare_kps_feature with precomputed features")
+        x = self._condition_images_to_tensor(kps_images, height, width)
+        feats = []
+        for i in range(0, x.shape[2], 16):
+            feats.append(self.v_kps_guider(x[:, :, i:i + 16].to(device=self.device, dtype=self.dtype)))
+        kps_feature = torch.cat(feats, dim=2)
+        if do_classifier_free_guidance:
+            kps_feature = torch.cat([torch.zeros_like(kps_feature), kps_feature], dim=0)
+        return kps_feature
+
+    @staticmethod
+    def audio_frame_windows(audio_embeddings, video_length, num_pad_audio_frames):
+        """Reference pipelines/v_express_pipeline.py:380-401: encoder states (1,T,d) -> linear interpolation (fp32) to
+        2*L steps, 2*num_pad zero rows on both sides, sliding windows (L, 2*(2*num_pad+1), d)."""
+        in_dtype = audio_embeddings.dtype
+        x = torch.nn.functional.interpolate(audio_embeddings.to(torch.float32).permute(0, 2, 1), size=2 * video_length,
+                                            mode="linear")[0].permute(1, 0).to(in_dtype)
+        pad = torch.zeros_like(x)[:2 * num_pad_audio_frames]
+        x = torch.cat([pad, x, pad], dim=0)
+        return torch.stack([x[2 * i:2 * (i + 2 * num_pad_audio_frames + 1)] for i in range(video_length)], dim=0)
 
     def prepare_audio_embeddings(self, audio_waveform, video_length, num_pad_audio_frames, do_classifier_free_guidance):
-        raise NotImplementedError("prologue hook: wav2vec2 + AudioProjection are outside the hot path (SURVEY.md 8f)")
+        """Reference pipelines/v_express_pipeline.py:374-407.  ``audio_processor`` / ``audio_encoder`` are the caller's
+        (wav2vec2, a third-party torch module outside this repo's kernels); the projection is
+        ``self.audio_projection`` (vexpress_b200.modules.AudioProjection or the reference's)."""
+        if self.audio_encoder is None or self.audio_projection is None:
+            raise NotImplementedError("prologue hook: pass audio_processor / audio_encoder / audio_projection or "
+                                      "override prepare_audio_embeddings with precomputed tokens")
+        wave = audio_waveform
+        if self.audio_processor is not None:
+            wave = self.audio_processor(audio_waveform, return_tensors="pt", sampling_rate=16000)["input_values"]
+        wave = wave.to(self.device, self.dtype)
+        states = self.audio_encoder(wave).last_hidden_state                       # (1, T, d)
+        windows = self.audio_frame_windows(states, video_length, num_pad_audio_frames)
+        audio_embeddings = self.audio_projection(windows).unsqueeze(0)
+        if do_classifier_free_guidance:
+            audio_embeddings = torch.cat([torch.zeros_like(audio_embeddings), audio_embeddings], dim=0)
+        return audio_embeddings
 
     def run_reference_net(self, reference_image_latents, writer):
         """Reference pipelines/v_express_pipeline.py:502-508: one ReferenceNet pass at t=0 fills the writer banks."""
