@@ -33,11 +33,12 @@ def run(B, N, Nk, heads, hd, kv_div, label):
     for k_ in ("VX_FA_STAGGER", "VX_FA_LATEWAIT", "VX_FA_PAIRSYNC"): os.environ.pop(k_, None)
     # exponential-phase baton between the two query tiles (VX_FA_BATON, template instantiation of its own)
     for lw in (0, 1):
-        os.environ["VX_FA_BATON"] = "1"; os.environ["VX_FA_LATEWAIT"] = str(lw)
-        ms, o = t_ms()
-        d = (o.float() - base.float()).abs().max().item()
-        print(f"  baton=1 latewait={lw}: {ms:.3f} ms" + ("" if d == 0 else f" (max abs diff vs baseline {d:.1e})"), flush=True)
-    for k_ in ("VX_FA_BATON", "VX_FA_LATEWAIT"): os.environ.pop(k_, None)
+        for poly in (8, 4, 2):             # 1/poly of the exponentials on the FMA pipe (hd <= 64 kernels only)
+            os.environ["VX_FA_BATON"] = "1"; os.environ["VX_FA_LATEWAIT"] = str(lw); os.environ["VX_FA_POLY"] = str(poly)
+            ms, o = t_ms()
+            d = (o.float() - base.float()).abs().max().item()
+            print(f"  baton=1 latewait={lw} poly=1/{poly}: {ms:.3f} ms" + ("" if d == 0 else f" (max abs diff vs baseline {d:.1e})"), flush=True)
+    for k_ in ("VX_FA_BATON", "VX_FA_LATEWAIT", "VX_FA_POLY"): os.environ.pop(k_, None)
 
 run(32, 4096, 4096, 8, 40, 1, "level-0 self (B=32 N=4096 hd=40)")
 run(16, 4096, 4096, 8, 40, 16, "level-0 bank (B=16 N=4096 hd=40 kv_div=16)")

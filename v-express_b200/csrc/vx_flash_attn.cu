@@ -304,7 +304,9 @@ struct Fa2Args {
 // clk), then both tiles' MMAs queue on the tensor pipe together (~1850 clk), and the two costs add up to the 3400-clk
 // iteration instead of overlapping; a one-off start offset does not survive.  With the baton one tile's exponentials
 // (alone on the MUFU units: ~900 clk) overlap the other tile's S load / row max / MMAs by construction.
-template <bool ONES, bool BATON>
+// PMASK: element i of every 8 takes the FMA-pipe exponential when (i & PMASK) == PMASK: 7 -> 1/8 (measured best without
+// the baton), 3 -> 1/4, 1 -> 1/2 (to be swept with the baton, where one tile owns the MUFU units during its phase).
+template <bool ONES, bool BATON, int PMASK>
 __global__ void __launch_bounds__(kFa2Threads, 1)
 flash_attn2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                    const __grid_constant__ CUtensorMap mapV, const Fa2Args p) {
@@ -553,7 +555,7 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const float xx = fmaf(__uint_as_float(v[g][h * 8 + i]), c, -mc);
-              e[i] = (i == 7) ? ex2_poly(xx) : ex2_approx(xx);   // 1/8 on the FMA pipe balances issue vs MUFU
+              e[i] = ((i & PMASK) == PMASK) ? ex2_poly(xx) : ex2_approx(xx);   // share of the FMA pipe: see PMASK
               if (!ONES) ls[i & 3] += e[i];
             }
 #pragma unroll
@@ -766,19 +768,25 @@ extern "C" int vx_flash_attention(const void* q, long long ldq, const void* k, l
     }
     static bool cfg2 = false;
     if (!cfg2) {
-      VX_CHECK_CUDA(cudaFuncSetAttribute(flash_attn2_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      VX_CHECK_CUDA(cudaFuncSetAttribute(flash_attn2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      VX_CHECK_CUDA(cudaFuncSetAttribute(flash_attn2_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      VX_CHECK_CUDA(cudaFuncSetAttribute(flash_attn2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      VX_CHECK_CUDA(cudaFuncSetAttribute(flash_attn2_kernel<true, false, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      VX_CHECK_CUDA(cudaFuncSetAttribute(flash_attn2_kernel<false, false, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      VX_CHECK_CUDA(cudaFuncSetAttribute(flash_attn2_kernel<true, true, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      VX_CHECK_CUDA(cudaFuncSetAttribute(flash_attn2_kernel<true, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      VX_CHECK_CUDA(cudaFuncSetAttribute(flash_attn2_kernel<true, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      VX_CHECK_CUDA(cudaFuncSetAttribute(flash_attn2_kernel<false, true, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       cfg2 = true;
     }
     dim3 grid2(Nq / 256, heads, Bq);
     const bool ones = hdp > hd && !getenv("VX_FA_NOONES");
     const bool baton = getenv("VX_FA_BATON") && atoi(getenv("VX_FA_BATON")) != 0;
-    if (ones && baton) flash_attn2_kernel<true, true><<<grid2, kFa2Threads, smem2, (cudaStream_t)stream>>>(mQ, mK, mV, a);
-    else if (ones) flash_attn2_kernel<true, false><<<grid2, kFa2Threads, smem2, (cudaStream_t)stream>>>(mQ, mK, mV, a);
-    else if (baton) flash_attn2_kernel<false, true><<<grid2, kFa2Threads, smem2, (cudaStream_t)stream>>>(mQ, mK, mV, a);
-    else flash_attn2_kernel<false, false><<<grid2, kFa2Threads, smem2, (cudaStream_t)stream>>>(mQ, mK, mV, a);
+    const int poly = getenv("VX_FA_POLY") ? atoi(getenv("VX_FA_POLY")) : 8;      // 1/poly of the exponentials on the FMA pipe
+    auto st2 = (cudaStream_t)stream;
+    if (ones && baton && poly == 4) flash_attn2_kernel<true, true, 3><<<grid2, kFa2Threads, smem2, st2>>>(mQ, mK, mV, a);
+    else if (ones && baton && poly == 2) flash_attn2_kernel<true, true, 1><<<grid2, kFa2Threads, smem2, st2>>>(mQ, mK, mV, a);
+    else if (ones && baton) flash_attn2_kernel<true, true, 7><<<grid2, kFa2Threads, smem2, st2>>>(mQ, mK, mV, a);
+    else if (ones) flash_attn2_kernel<true, false, 7><<<grid2, kFa2Threads, smem2, st2>>>(mQ, mK, mV, a);
+    else if (baton) flash_attn2_kernel<false, true, 7><<<grid2, kFa2Threads, smem2, st2>>>(mQ, mK, mV, a);
+    else flash_attn2_kernel<false, false, 7><<<grid2, kFa2Threads, smem2, st2>>>(mQ, mK, mV, a);
     VX_CHECK_CUDA(cudaGetLastError());
     return 0;
   }
