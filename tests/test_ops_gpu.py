@@ -27,7 +27,11 @@ def _gen(seed):
                                                     (2, 4096, 8, 40, 1, 4096), (4, 64, 8, 160, 1, 64),
                                                     (4, 1024, 8, 80, 2, 1024), (4, 256, 8, 16, 2, 256),
                                                     (2, 128, 2, 32, 1, 384), (3, 64, 8, 8, 1, 64),
-                                                    (8, 4, 8, 32, 1, 4), (4, 36, 8, 16, 2, 36)])
+                                                    (8, 4, 8, 32, 1, 4), (4, 36, 8, 16, 2, 36),
+                                                    # BASELINE configs[4] (768x768: 96x96 latents): N = 9216 / 2304 / 576 / 144
+                                                    (2, 9216, 8, 40, 1, 9216), (4, 9216, 8, 40, 2, 9216),
+                                                    (2, 2304, 8, 80, 1, 2304), (2, 576, 8, 160, 1, 576),
+                                                    (4, 144, 8, 160, 1, 144), (4, 144, 8, 160, 2, 144)])
 def test_flash_attention(ops, B, N, heads, hd, kv_div, Nk):
     g = _gen(B * N + hd)
     C = heads * hd
@@ -91,7 +95,9 @@ def test_smallkv_attention(ops, frames, N, heads, hd):
 
 @pytest.mark.parametrize("NB,HW,C1,C2,silu,eps", [(4, 4096, 320, 0, True, 1e-5), (3, 256, 1280, 640, True, 1e-5),
                                                   (2, 64, 1280, 1280, False, 1e-6), (5, 1024, 64, 0, False, 1e-6),
-                                                  (2, 256, 640, 320, True, 1e-5), (1, 65536, 128, 0, True, 1e-6)])
+                                                  (2, 256, 640, 320, True, 1e-5), (1, 65536, 128, 0, True, 1e-6),
+                                                  (3, 9216, 320, 0, True, 1e-5), (2, 2304, 640, 320, True, 1e-5),
+                                                  (2, 144, 1280, 1280, True, 1e-5), (1, 147456, 128, 0, True, 1e-6)])
 def test_groupnorm(ops, NB, HW, C1, C2, silu, eps):
     g = _gen(C1 + C2 + HW)
     x1 = (torch.randn(NB * HW, C1, device="cuda", generator=g) * 2 + 0.7).bfloat16()
@@ -110,7 +116,8 @@ def test_groupnorm(ops, NB, HW, C1, C2, silu, eps):
     assert err < 4e-3
 
 
-@pytest.mark.parametrize("rows,C,with_pe", [(4096, 320, False), (1000, 1280, True), (512, 640, True), (777, 64, False)])
+@pytest.mark.parametrize("rows,C,with_pe", [(4096, 320, False), (1000, 1280, True), (512, 640, True), (777, 64, False),
+                                            (2 * 9216, 320, False), (2 * 2304 + 3, 640, False), (4 * 144, 1280, True)])
 def test_layernorm(ops, rows, C, with_pe):
     g = _gen(rows + C)
     x = (torch.randn(rows, C, device="cuda", generator=g) * 3 + 1).bfloat16()

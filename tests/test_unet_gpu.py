@@ -37,7 +37,7 @@ def build_product(cfg, sd, banks_cond, ref_w=0.95, audio_w=3.0):
     model = UNet3DConditionModel(block_out_channels=cfg["block_out_channels"],
                                  cross_attention_dim=cfg["cross_attention_dim"], **UNET_EXTRA)
     model.load_state_dict(sd, strict=True)
-    model = model.to(dtype=torch.bfloat16, device="cuda")
+    model = model.to(torch.bfloat16).to("cuda")       # cast on the host: the upload is plain memcpys, no cast kernels
     reader = ReferenceAttentionControl(model, do_classifier_free_guidance=True, mode="read", batch_size=1,
                                        fusion_blocks="full", reference_attention_weight=ref_w,
                                        audio_attention_weight=audio_w)

@@ -1,6 +1,4 @@
-"""Median filter + uint8 frames against the reference-generated golden and the oracle.
-The kernel was written after the round-1 GPU budget was spent: skipped until it has been run once on hardware
-(set VX_TEST_UNVERIFIED=1)."""
+"""Median filter + uint8 frames against the reference-generated golden and the oracle."""
 import os
 
 import numpy as np
@@ -9,8 +7,7 @@ import torch
 
 from oracle import vx_oracle as O
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(not os.environ.get("VX_TEST_UNVERIFIED"), reason="kernel not yet run on a GPU")]
+pytestmark = pytest.mark.gpu
 
 
 def test_median3d_matches_reference_golden(golden_dir):

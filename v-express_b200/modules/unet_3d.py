@@ -378,9 +378,8 @@ class UNetEngine:
         W = self.W
         temb_w, temb_b, self.temb_off = [], [], {}
         off = 0
-        for k, v in sd.items():
-            if k.endswith(".bias") or (k.endswith(".weight") and v.dim() == 1):
-                W[k] = self._f32(v)
+        W.update(ops.f32_arena({k: v for k, v in sd.items()
+                                if k.endswith(".bias") or (k.endswith(".weight") and v.dim() == 1)}, self.dev))
         for k, v in sd.items():
             if not k.endswith(".weight") or v.dim() == 1:
                 continue
@@ -388,12 +387,12 @@ class UNetEngine:
             if p in ("conv_in",):
                 W[k] = self._f32(v).reshape(v.shape[0], -1).t().contiguous()                 # fp32 [Cin*9, Cout]
             elif p == "conv_out":
-                W["conv_out.packed_w"], W["conv_out.packed_b"] = ops.pack_conv_out(self._bf(v), self._f32(sd[p + ".bias"]))
+                W["conv_out.packed_w"], W["conv_out.packed_b"] = ops.pack_conv_out(self._bf(v), W[p + ".bias"])
             elif p.endswith("time_emb_proj"):
                 self.temb_off[p] = (off, v.shape[0])
                 off += v.shape[0]
                 temb_w.append(self._bf(v))
-                temb_b.append(self._f32(sd[p + ".bias"]))
+                temb_b.append(W[p + ".bias"])
             elif v.dim() == 4 and v.shape[-1] == 3:
                 W[k] = ops.pack_conv3x3_weight(self._bf(v))
             elif v.dim() == 4:

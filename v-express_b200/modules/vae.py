@@ -139,17 +139,18 @@ class VaeDecoderEngine:
         self.layers = model.config["layers_per_block"]
         self.W: Dict[str, torch.Tensor] = {}
         dev = self.dev
-        for k, v in model.state_dict().items():
+        msd = model.state_dict()
+        self.W.update(ops.f32_arena({k: v for k, v in msd.items() if k.endswith(".bias") or v.dim() == 1}, dev))
+        for k, v in msd.items():
             v = v.detach()
             p = k.rsplit(".", 1)[0]
             if k.endswith(".bias") or v.dim() == 1:
-                self.W[k] = v.to(device=dev, dtype=BF16).float().contiguous()
+                continue
             elif p == "decoder.conv_in":
                 self.W[k] = v.to(device=dev, dtype=BF16).float().reshape(v.shape[0], -1).t().contiguous()
             elif p == "decoder.conv_out":
-                bias = model.state_dict()[p + ".bias"].detach().to(device=dev, dtype=BF16).float()
                 self.W["conv_out.packed_w"], self.W["conv_out.packed_b"] = ops.pack_conv_out(
-                    v.to(device=dev, dtype=BF16), bias)
+                    v.to(device=dev, dtype=BF16), self.W[p + ".bias"])
             elif p == "post_quant_conv":
                 self.W[k] = v.to(device=dev, dtype=BF16).float().reshape(v.shape[0], v.shape[1]).contiguous()
             elif v.dim() == 4 and v.shape[-1] == 3:

@@ -20,6 +20,23 @@ def _chk_bf16(*ts):
             assert t.is_cuda and t.dtype == BF16 and t.stride(-1) == 1, (t.dtype, t.device, t.stride())
 
 
+def f32_arena(vectors, device):
+    """All 1-D parameters of a model (biases, norm affine) as fp32 views into ONE buffer: one concatenation and two
+    casts instead of a cast kernel per parameter.  Values are rounded to the model dtype first (what ``.to(bf16)`` does
+    to the reference's parameters) and then widened; every view is 16-byte aligned (float4 loads in the epilogues)."""
+    offs, parts, off = {}, [], 0
+    for k, v in vectors.items():
+        v = v.detach().reshape(-1)
+        pad = (-v.numel()) % 4
+        offs[k] = (off, v.numel())
+        parts.append(torch.nn.functional.pad(v, (0, pad)) if pad else v)
+        off += v.numel() + pad
+    if not parts:
+        return {}
+    flat = torch.cat(parts).to(device=device, dtype=BF16).float()
+    return {k: flat[o:o + n] for k, (o, n) in offs.items()}
+
+
 def geglu_block_n(N):
     """UMMA N used for a GEGLU-fused GEMM with N = 2*inner accumulator columns (fixed at weight-packing time)."""
     for bn in (256, 128, 64):
