@@ -538,18 +538,7 @@ def refnet_time(h, iters=3):
 
 def pipe_decode_device(pipe, latents, dist):
     """Decode with the result left on the device (HBM-resident `value` measurement); rank 0 gathers the shards."""
-    L = latents.shape[2]
-    if not dist:
-        return pipe.decode_latents(latents)
-    rank, world = torch.distributed.get_rank(), torch.distributed.get_world_size()
-    per = math.ceil(L / world)
-    ids = list(range(rank * per, min(L, (rank + 1) * per)))
-    part = pipe.decode_latents(latents, ids)
-    buf = torch.zeros((per, 3, latents.shape[3] * 8, latents.shape[4] * 8), device=latents.device, dtype=torch.float32)
-    buf[:part.shape[0]].copy_(part)
-    gathered = [torch.empty_like(buf) for _ in range(world)] if rank == 0 else None
-    torch.distributed.gather(buf, gathered, dst=0)
-    return gathered
+    return pipe.decode_to_device(latents, dist)
 
 
 def main():

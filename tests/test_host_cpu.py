@@ -677,3 +677,146 @@ def test_pipeline_prologue_glue_matches_reference(golden_dir):
     assert torch.allclose(kf[1, 0, :, 0, 0], torch.arange(20) / 255.0 * 2.0)
     with pytest.raises(ValueError):
         pipe.prepare_kps_feature(torch.zeros(1, 3, 2, 32, 32), 64, 64, False)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# VExpressPipeline.denoise host logic (window partition, local kps/audio range, overlap plan incl. reflected windows,
+# bf16 all-reduce, DDIM) with the UNet replaced by a cheap deterministic function and the two elementwise kernels by
+# torch emulations with the kernels' rounding points -- against the oracle's restatement of the reference's streaming loop.
+# ----------------------------------------------------------------------------------------------------------------------
+def _fake_unet_core(x, kmean, emean, t):
+    """x (b,f,4,h,w) fp32; kmean (b,f,1,h,w); emean (b,f,1,1,1) -> (b,f,4,h,w) bf16; mixes frames like the motion modules."""
+    return torch.tanh(0.9 * x + kmean + 0.1 * emean + 0.05 * x.mean(1, keepdim=True) + 1e-3 * t).bfloat16()
+
+
+class _FakeEngine:
+    dev = torch.device("cpu")
+    order = []
+
+    def time_embedding(self, t):
+        return torch.tensor([[float(t)]])
+
+    def graph_signature(self):
+        return 0
+
+    def forward_frames(self, frames, timestep, enc, kps, kps_idx, b, f, temb=None, taps=None):
+        NB, _, h, w = frames.shape
+        k = kps.view(-1, h * w, kps.shape[1])[kps_idx.long()].float().mean(-1).view(b, f, 1, h, w)
+        e = enc.float().mean((1, 2)).view(b, f, 1, 1, 1)
+        out = _fake_unet_core(frames.float().view(b, f, 4, h, w), k, e, float(temb.reshape(-1)[0]))
+        return out.view(NB, 4, h, w)
+
+
+def _fake_unet_fn(x, t, aud, kps):
+    """Same function in the oracle's layouts: x (b,4,f,h,w), aud ((b f),5,768), kps (b,C0,f,h,w)."""
+    b, _, f, h, w = x.shape
+    k = kps.float().permute(0, 2, 3, 4, 1).mean(-1).view(b, f, 1, h, w)
+    e = aud.float().mean((1, 2)).view(b, f, 1, 1, 1)
+    return _fake_unet_core(x.float().permute(0, 2, 1, 3, 4), k, e, float(t)).permute(0, 2, 1, 3, 4)
+
+
+class _ElementwiseEmu:
+    """torch emulation of vx_cfg_overlap_accumulate / vx_ddim_step with the kernels' rounding points (csrc/vx_misc.cu)."""
+
+    @staticmethod
+    def cfg_overlap_accumulate(noise, f, hw, L, do_cfg, win, count, guidance, acc):
+        n = noise.view(-1, f, 4, hw).float()
+        rb = lambda t: t.bfloat16().float()
+        v = rb(n[0] + rb(guidance * rb(n[1] - n[0]))) if do_cfg else n[0]
+        for i in range(f):
+            fr = int(win[i])
+            if fr < 0:
+                continue
+            acc[:, fr] = rb(acc[:, fr] + rb(v[i] / float(count[fr])))
+
+    @staticmethod
+    def ddim_step(lat, acc, sa, sb, sap, sbp):
+        rb = lambda t: t.bfloat16().float()
+        x, v = lat.float().view(acc.shape), rb(acc)
+        x0 = rb(rb(sa * x) - rb(sb * v))
+        eps = rb(rb(sa * v) + rb(sb * x))
+        lat.copy_((rb(sap * x0) + rb(sbp * eps)).bfloat16().view(lat.shape))
+
+
+def _fake_pipeline():
+    from vexpress_b200.pipelines import v_express_pipeline as vp
+    from vexpress_b200.pipelines.scheduler import DDIMScheduler
+    unet = type("U", (), {"engine": lambda self: _FakeEngine(), "get_submodule": lambda self, n: None})()
+    pipe = vp.VExpressPipeline(vae=None, reference_net=None, denoising_unet=unet, v_kps_guider=None, audio_processor=None,
+                               audio_encoder=None, audio_projection=None, scheduler=DDIMScheduler())
+    pipe.use_cuda_graph = False
+    vp.ops = _ElementwiseEmu()
+    return pipe, vp
+
+
+def _fake_inputs(L, h=4, C0=8):
+    g = torch.Generator().manual_seed(L)
+    lat = torch.randn(1, 4, L, h, h, generator=g).bfloat16()
+    kps = torch.cat([torch.zeros(1, C0, L, h, h), 0.1 * torch.randn(1, C0, L, h, h, generator=g)]).bfloat16()
+    audio = torch.cat([torch.zeros(1, L, 5, 16), torch.randn(1, L, 5, 16, generator=g)]).bfloat16()
+    return lat, kps, audio
+
+
+def _run_fake_denoise(L, S, Ov, steps, distributed=False):
+    from vexpress_b200.pipelines.v_express_pipeline import retrieve_timesteps
+    pipe, vp = _fake_pipeline()
+    try:
+        lat, kps, audio = _fake_inputs(L)
+        ts, _ = retrieve_timesteps(pipe.scheduler, steps, None)
+        return pipe.denoise(lat.clone(), kps, audio, ts, 3.5, S, Ov, distributed=distributed)
+    finally:
+        from vexpress_b200 import ops as real_ops
+        vp.ops = real_ops
+
+
+@pytest.mark.parametrize("L,S,Ov", [(12, 8, 4), (24, 16, 8), (20, 16, 4), (28, 16, 8), (33, 24, 4)])
+def test_denoise_host_logic_equals_reference_streaming_loop(monkeypatch, L, S, Ov):
+    """Tiling AND non-tiling lengths (reflected tail windows with repeated frames): bit-identical to
+    the oracle's restatement of pipelines/v_express_pipeline.py:527-572 in bf16."""
+    from oracle import vx_oracle as O
+    out = _run_fake_denoise(L, S, Ov, 3)
+    lat, kps, audio = _fake_inputs(L)
+
+    def step_cuda_semantics(self, model_output, timestep, sample, eta=0.0, **_):
+        """O.DDIM.step with the scalar handling of the device the reference runs on: CUDA elementwise kernels keep the
+        fp32 scalar in fp32 (opmath) and round the product to bf16, whereas CPU eager first rounds the SCALAR to bf16."""
+        a_t, a_prev = self.coeffs(int(timestep))
+        rb = lambda t: t.bfloat16().float()
+        x, v = sample.float(), model_output.float()
+        sa, sb, sap, sbp = float(a_t ** 0.5), float((1 - a_t) ** 0.5), float(a_prev ** 0.5), float((1 - a_prev) ** 0.5)
+        x0 = rb(rb(sa * x) - rb(sb * v))
+        eps = rb(rb(sa * v) + rb(sb * x))
+        return O._StepOut((rb(sap * x0) + rb(sbp * eps)).bfloat16())
+    monkeypatch.setattr(O.DDIM, "step", step_cuda_semantics)
+    ref = O.denoise(None, None, lat, kps, audio, None, 3, 3.5, S, Ov, unet_fn=_fake_unet_fn)
+    assert out.dtype == torch.bfloat16 and torch.equal(out, ref)
+
+
+def _gloo_denoise_worker(rank, world, port, L, S, Ov, ret):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    out = _run_fake_denoise(L, S, Ov, 3, distributed=True)
+    if rank == 0:
+        ret.put(out.float().numpy())
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("L,S,Ov,world", [(40, 16, 8, 2), (28, 16, 8, 2), (56, 16, 8, 3)])
+def test_denoise_sharded_over_ranks_equals_single_rank(L, S, Ov, world):
+    """VExpressPipeline.denoise(distributed=True) itself under gloo: rank-local kps/audio slices, bf16 all-reduce of the
+    overlap sums, replicated DDIM -- bit-identical to the one-rank run (and therefore to the reference's streaming loop)."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    port = 29500 + ((os.getpid() * 7 + L) % 2000)
+    procs = [ctx.Process(target=_gloo_denoise_worker, args=(r, world, port, L, S, Ov, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = torch.from_numpy(ret.get(timeout=120))
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    single = _run_fake_denoise(L, S, Ov, 3)
+    assert torch.equal(got, single.float())

@@ -119,12 +119,33 @@ def test_pipeline_vs_reference_golden(golden_dir, use_graph):
     assert torch.equal(video, video2)
 
 
-def test_pipeline_rejects_non_tiling_length(golden_dir):
+def test_pipeline_non_tiling_length_follows_reference_bookkeeping():
+    """video_length 20 with windows of 16 / overlap 4: the tail window is reflected and repeats frames 12..18; the
+    reference's index-put / streaming bookkeeping decides which slots count.  The integer plan is
+    proven bit-exact on the CPU (tests/test_host_cpu.py); here the real kernels run it and land on the oracle's
+    restatement of the reference loop within the trajectory tolerance."""
     from oracle import vx_oracle as O
     cfg, vcfg = O.small_cfg(), O.small_vae_cfg()
     sd = O.synth_state_dict(O.unet_param_shapes(cfg), 1234)
     vsd = O.synth_state_dict(O.vae_param_shapes(vcfg), 1235)
-    lat, kps, audio, banks = O.synth_inputs(cfg, 20, 16, 16, True, 42)
+    L = 20
+    lat, kps, audio, banks = O.synth_inputs(cfg, L, 16, 16, True, 42)
     pipe = build_pipeline(cfg, vcfg, sd, vsd, kps, audio, [b[1:] for b in banks], lat)
-    with pytest.raises(ValueError):
-        pipe(None, None, None, 128, 128, 20, 2, 3.5, context_frames=16, context_overlap=4)
+    captured = {}
+    orig = pipe._decode_to_host
+
+    def grab(latents, distributed):
+        captured["latents"] = latents.float().cpu()
+        return orig(latents, distributed)
+    pipe._decode_to_host = grab
+    video = pipe(None, None, None, 128, 128, L, 2, 3.5, context_frames=16, context_overlap=4,
+                 reference_attention_weight=0.95, audio_attention_weight=3.0)
+    assert video.shape == (1, 3, L, 128, 128)
+    r = lambda t: t.bfloat16().float()
+    with torch.no_grad():
+        ref = O.denoise({k: r(v) for k, v in sd.items()}, cfg, r(lat), r(kps), r(audio), [r(b) for b in banks], 2, 3.5, 16, 4,
+                        ref_w=0.95, audio_w=3.0)
+    e = _rel(captured["latents"], ref)
+    worst = max(_rel(captured["latents"][:, :, i], ref[:, :, i]) for i in range(L))
+    print(f"non-tiling L=20: final latents rel {e:.3e}, worst frame {worst:.3e}")
+    assert e < 5e-2 and worst < 8e-2

@@ -330,6 +330,8 @@ __global__ void cfg_overlap_kernel(const CfgArgs p) {
     const int i = (int)((idx / p.hw) % p.f);
     const int c = (int)(idx / ((long long)p.hw * p.f));
     const long long off = ((long long)i * 4 + c) * p.hw + px;
+    const int fr = p.win[i];
+    if (fr < 0) continue;            // slot discarded by the reference's bookkeeping (pipelines/context.py overlap_plan)
     float v;
     if (p.do_cfg) {
       const float u = __bfloat162float(p.noise[off]);
@@ -338,7 +340,6 @@ __global__ void cfg_overlap_kernel(const CfgArgs p) {
     } else {
       v = __bfloat162float(p.noise[off]);
     }
-    const int fr = p.win[i];
     v = rbf(v / (float)p.count[fr]);
     float* a = p.acc + ((long long)c * p.L + fr) * p.hw + px;
     *a = rbf(*a + v);
@@ -352,7 +353,7 @@ __global__ void ddim_step_kernel(__nv_bfloat16* __restrict__ latents, const floa
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
        idx += (long long)gridDim.x * blockDim.x) {
     const float x = __bfloat162float(latents[idx]);
-    const float v = acc[idx];
+    const float v = rbf(acc[idx]);   // no-op on one GPU; after the fp32 all-reduce of two bf16 partial sums = their bf16 sum
     const float x0 = rbf(rbf(sa * x) - rbf(sb * v));
     const float eps = rbf(rbf(sa * v) + rbf(sb * x));
     const float dir = rbf(sbp * eps);

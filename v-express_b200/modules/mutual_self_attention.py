@@ -81,6 +81,9 @@ class ReferenceAttentionControl:
         banks = self._writer_banks(writer)
         if len(banks) != len(readers):
             raise ValueError(f"writer exposes {len(banks)} banks, reader has {len(readers)} blocks")
+        if getattr(self.unet, "_engine", None) is not None:
+            # new bank tensors may reuse the address / version / shape of the previous ones: never trust the cache key
+            self.unet._engine._bank_cache.clear()
         for r, bank in zip(readers, banks):
             if do_classifier_free_guidance:
                 r.bank = [torch.cat([torch.zeros_like(v), v]).to(dtype) for v in bank]

@@ -102,7 +102,21 @@ class AutoencoderKL(nn.Module):
 
     def load_state_dict(self, state_dict, strict=True, **kw):
         self._engine = None
-        sd = {k: v for k, v in state_dict.items() if not (k.startswith("encoder.") or k.startswith("quant_conv."))}
+        sd = {}
+        # checkpoints saved before diffusers 0.18 (stabilityai/sd-vae-ft-mse among them) name the mid-block attention
+        # projections query / key / value / proj_attn; diffusers renames them at load time
+        # (AutoencoderKL._convert_deprecated_attention_blocks) -- same here
+        old = {".query.": ".to_q.", ".key.": ".to_k.", ".value.": ".to_v.", ".proj_attn.": ".to_out.0."}
+        for k, v in state_dict.items():
+            if k.startswith("encoder.") or k.startswith("quant_conv."):
+                continue
+            if ".attentions." in k:
+                for a, b in old.items():
+                    if a in k:
+                        k = k.replace(a, b)
+                        if v.dim() == 4:
+                            v = v.reshape(v.shape[0], v.shape[1])
+            sd[k] = v
         return super().load_state_dict(sd, strict=strict, **kw)
 
     def engine(self) -> "VaeDecoderEngine":
@@ -120,11 +134,12 @@ class AutoencoderKL(nn.Module):
         return DecoderOutput(out) if return_dict else (out,)
 
     @torch.no_grad()
-    def decode_latents(self, latents):
+    def decode_latents(self, latents, out=None):
         """Fused form of the reference's ``decode_latents`` (pipelines/v_express_pipeline.py:152-166):
-        latents (n,4,h,w) UNSCALED -> fp32 frames (n,3,8h,8w) in [0,1] on the device."""
+        latents (n,4,h,w) UNSCALED -> fp32 frames (n,3,8h,8w) in [0,1] on the device.  ``out``: optional fp32 view of
+        that shape whose (h, w) planes are contiguous (frame / channel strides are free)."""
         return self.engine().decode(latents.to(BF16), pre_scale=1.0 / self.config["scaling_factor"], post=True,
-                                    out_dtype=torch.float32)
+                                    out_dtype=torch.float32, out=out)
 
 
 class VaeDecoderEngine:
@@ -191,7 +206,7 @@ class VaeDecoderEngine:
             ops.gemm(probs, vt, W[p + ".to_v.bias"], out=o[sl])
         return ops.gemm(o, W[p + ".to_out.0.weight"], W[p + ".to_out.0.bias"], residual=x)
 
-    def decode(self, z, pre_scale: float, post: bool, out_dtype):
+    def decode(self, z, pre_scale: float, post: bool, out_dtype, out=None):
         W = self.W
         assert z.dim() == 4
         z = z.contiguous()
@@ -212,6 +227,8 @@ class VaeDecoderEngine:
                 x = ops.conv3x3(u.view(NB, H, Wd, -1), W[f"{d}.up_blocks.{i}.upsamplers.0.conv.weight"],
                                 W[f"{d}.up_blocks.{i}.upsamplers.0.conv.bias"])
         x = ops.groupnorm(x, NB, H * Wd, W[d + ".conv_norm_out.weight"], W[d + ".conv_norm_out.bias"], 1e-6, True)
-        out = torch.empty((NB, self.model.config["out_channels"], H, Wd), device=self.dev, dtype=out_dtype)
+        if out is None:
+            out = torch.empty((NB, self.model.config["out_channels"], H, Wd), device=self.dev, dtype=out_dtype)
+        assert out.shape == (NB, self.model.config["out_channels"], H, Wd) and out.dtype == out_dtype
         ops.conv_out_tc(x, NB, H, Wd, W["conv_out.packed_w"], W["conv_out.packed_b"], out, post=post)
         return out

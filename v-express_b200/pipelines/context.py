@@ -9,7 +9,7 @@ from typing import Callable, Iterator, List, Optional
 import numpy as np
 
 __all__ = ["ordered_halving", "uniform", "get_context_scheduler", "compute_num_context",
-           "compute_context_indices", "get_total_steps", "window_table"]
+           "compute_context_indices", "get_total_steps", "window_table", "overlap_plan"]
 
 
 def compute_num_context(init_video_length: int, context_size: int, context_overlap: int) -> int:
@@ -74,3 +74,46 @@ def window_table(video_length: int, context_frames: int, context_overlap: int, s
     for w in windows:
         count[np.unique(np.asarray(w, dtype=np.int64))] += 1
     return windows, count
+
+
+def overlap_plan(windows, count):
+    """Which window slots end up in a frame's noise prediction, for window lists that may repeat a frame inside one
+    (reflected) window.  Integer replay of the reference's streaming bookkeeping (pipelines/v_express_pipeline.py
+    :528-529,552-572): per window ``context_counter[context] += 1`` is a NON-accumulating index-put (a repeated frame
+    counts once), the Python loop then walks the slots in order, starts a frame's sum at its first slot
+    (``noise_preds[f] is None``), adds every further slot, and each time ``context_counter[f] == num_frame_context[f]``
+    holds it hands the current sum to ``scheduler.step`` and resets it -- so a frame repeated inside its LAST window is
+    stepped more than once from the same input latents and the last write wins (index-put on the host tensor).
+
+    Returns ``rounds[w]`` = list of int32 arrays of len(windows[w]): entry = frame index if that slot's prediction is
+    accumulated into the frame's final sum, -1 if the reference discards it; every array holds each frame at most
+    once, and the arrays of one window are in the reference's summation order."""
+    L = len(count)
+    counter = [0] * L
+    pending = [None] * L
+    final = {}
+    for wi, win in enumerate(windows):
+        for f in set(win):
+            counter[f] += 1
+        for li, f in enumerate(win):
+            if pending[f] is None:
+                pending[f] = []
+            pending[f].append((wi, li))
+            if counter[f] == int(count[f]):
+                final[f] = pending[f]
+                pending[f] = None
+    keep = set(slot for slots in final.values() for slot in slots)
+    rounds = []
+    for wi, win in enumerate(windows):
+        per_round = []
+        seen = {}
+        for li, f in enumerate(win):
+            if (wi, li) not in keep:
+                continue
+            r = seen.get(f, 0)
+            seen[f] = r + 1
+            while len(per_round) <= r:
+                per_round.append(np.full(len(win), -1, dtype=np.int32))
+            per_round[r][li] = f
+        rounds.append(per_round)
+    return rounds

@@ -28,7 +28,7 @@ import torch
 from .. import _ffi, ops
 from ..modules.mutual_self_attention import ReferenceAttentionControl
 from ..modules.unet_3d import UNet3DConditionModel
-from .context import window_table
+from .context import overlap_plan, window_table
 from .scheduler import ddim_coefficients
 
 BF16 = torch.bfloat16
@@ -239,18 +239,20 @@ class VExpressPipeline:
 
     # ------------------------------------------------------------------ decode
     @torch.no_grad()
-    def decode_latents(self, latents, frame_ids=None):
-        """latents (1,4,L,h,w) on the device -> (1,3,L,H,W) fp32 on the host in [0,1] (reference :152-166).
-        ``frame_ids`` restricts the decode to a subset (multi-GPU sharding)."""
+    def decode_latents(self, latents, frame_ids=None, out=None):
+        """latents (1,4,L,h,w) on the device -> frames in [0,1], fp32, ON THE DEVICE, already in the reference's output
+        layout (reference :152-166): ``out`` (3, n, H, W) (allocated when None), frame j of ``frame_ids`` (default: all)
+        written to out[:, j].  The conv_out kernel writes through the strides, so no permute pass exists."""
         L = latents.shape[2]
         ids = list(range(L)) if frame_ids is None else list(frame_ids)
+        H, W = latents.shape[3] * self.vae_scale_factor, latents.shape[4] * self.vae_scale_factor
+        if out is None:
+            out = torch.empty((3, len(ids), H, W), device=latents.device, dtype=torch.float32)
         z = latents[0].permute(1, 0, 2, 3)[ids].contiguous()                    # (n,4,h,w)
-        outs = []
         for i in range(0, z.shape[0], self.vae_chunk):
-            outs.append(self.vae.decode_latents(z[i:i + self.vae_chunk]))
-        video = torch.cat(outs) if outs else torch.empty((0, 3, latents.shape[3] * 8, latents.shape[4] * 8),
-                                                         device=latents.device)
-        return video                                                            # (n,3,H,W) fp32, device
+            n = min(self.vae_chunk, z.shape[0] - i)
+            self.vae.decode_latents(z[i:i + n], out=out[:, i:i + n].permute(1, 0, 2, 3))
+        return out
 
     # ------------------------------------------------------------------ the hot loop
     @torch.no_grad()
@@ -267,24 +269,29 @@ class VExpressPipeline:
         do_cfg = guidance_scale > 1.0
         b = 2 if do_cfg else 1
         windows, count = window_table(L, context_frames, context_overlap, context_schedule)
-        if any(len(set(wn)) != len(wn) for wn in windows):
-            # reflected tail windows repeat frames; the reference's bookkeeping for them is inconsistent
-            #  and its CLI always picks a tiling length, so refuse instead of guessing
-            raise ValueError(f"video_length={L} does not tile with context_frames={context_frames}, "
-                             f"context_overlap={context_overlap}: a window would contain duplicate frames")
+        # reflected tail windows may repeat frames: which slots reach a frame's final sum follows the reference's
+        # streaming bookkeeping exactly (context.overlap_plan); tiling lengths give one round with every slot kept
+        plan = overlap_plan(windows, count)
         rank, world = 0, 1
         if distributed and torch.distributed.is_available() and torch.distributed.is_initialized():
             rank, world = torch.distributed.get_rank(), torch.distributed.get_world_size()
         mine = partition_windows(len(windows), world, rank)
         count_dev = torch.from_numpy(count).to(device=dev, dtype=torch.int32)
-        # channels-last kps for all frames, row block (bi*L + frame); stays resident for the whole video
+        # channels-last kps of the frames this rank's windows touch, row block (bi*Lloc + frame - lo); stays resident for
+        # the whole video.  Only that slice crosses PCIe when the features live on the host.
+        own = sorted(set(fr for wi in mine for fr in windows[wi]))
+        lo, hi = (own[0], own[-1] + 1) if own else (0, 1)
+        Lloc = hi - lo
         C0 = kps_feature.shape[1]
-        kps_nhwc = kps_feature.to(device=dev, dtype=BF16).permute(0, 2, 3, 4, 1).reshape(b * L * hw, C0).contiguous()
-        audio = audio_embeddings.to(device=dev, dtype=BF16)
+        kps_nhwc = kps_feature[:, :, lo:hi].to(device=dev, dtype=BF16, non_blocking=True) \
+            .permute(0, 2, 3, 4, 1).reshape(b * Lloc * hw, C0).contiguous()
+        audio = audio_embeddings[:, lo:hi].to(device=dev, dtype=BF16, non_blocking=True)
         T = audio.shape[2]
         acc = torch.zeros((4, L, hw), device=dev, dtype=torch.float32)
+        acc_x = torch.empty((4, L, hw), device=dev, dtype=BF16) if world > 1 else None
         win_dev = [torch.tensor(wn, device=dev, dtype=torch.int32) for wn in windows]
         win_long = [t.long() for t in win_dev]
+        plan_dev = {wi: [torch.from_numpy(r).to(dev) for r in plan[wi]] for wi in mine}
         lat = latents[0]                                                        # (4, L, h, w) view
         # refresh the projected reference banks (outside any capture) and reuse graphs across calls while valid
         for name in eng.order:
@@ -306,16 +313,21 @@ class VExpressPipeline:
                 g.frames[:f].copy_(x)
                 if do_cfg:
                     g.frames[f:].copy_(x)
-                g.enc.copy_(audio[:, win_long[wi]].reshape(b * f, T, -1))
+                g.enc.copy_(audio[:, win_long[wi] - lo].reshape(b * f, T, -1))
                 for bi in range(b):
-                    g.kps_idx[bi * f:(bi + 1) * f].copy_(win_dev[wi] + bi * L)
+                    g.kps_idx[bi * f:(bi + 1) * f].copy_(win_dev[wi] + (bi * Lloc - lo))
                 if g.kps_token is not kps_nhwc:
                     g.set_kps(kps_nhwc)
                     g.kps_token = kps_nhwc
                 noise = g(temb)                                                 # ((b f),4,h,w) bf16
-                ops.cfg_overlap_accumulate(noise, f, hw, L, do_cfg, win_dev[wi], count_dev, float(guidance_scale), acc)
+                for slots in plan_dev[wi]:
+                    ops.cfg_overlap_accumulate(noise, f, hw, L, do_cfg, slots, count_dev, float(guidance_scale), acc)
             if world > 1:
-                torch.distributed.all_reduce(acc, op=torch.distributed.ReduceOp.SUM)
+                # every frame has at most two non-zero bf16 contributions across the ranks (its windows live on one rank
+                # or on two neighbours), so the bf16 sum is the reference's own bf16 add -- half the bytes of fp32
+                acc_x.copy_(acc)
+                torch.distributed.all_reduce(acc_x, op=torch.distributed.ReduceOp.SUM)
+                acc.copy_(acc_x)
             sa, sb, sap, sbp = ddim_coefficients(self.scheduler, int(t))
             ops.ddim_step(lat, acc, sa, sb, sap, sbp)
             if callback is not None and i % callback_steps == 0:
@@ -355,38 +367,51 @@ class VExpressPipeline:
         latents = self.prepare_latents(batch_size * num_images_per_prompt, num_channels_latents, width, height,
                                        video_length, self.dtype, torch.device("cpu"), generator)
         latents = latents.to(device=device, dtype=BF16, non_blocking=True)      # one H2D for the whole video
-        distributed = bool(do_multi_devices_inference)
-        latents = self.denoise(latents, kps_feature, audio_embeddings, timesteps, guidance_scale, context_frames,
-                               context_overlap, context_schedule, distributed, callback, callback_steps)
-        reader.clear()
-        if hasattr(writer, "clear") and isinstance(getattr(writer, "unet", None), torch.nn.Module):
-            try:
+        distributed = bool(do_multi_devices_inference) and torch.distributed.is_available() \
+            and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1
+        if distributed:
+            # every rank drew its own host noise (generator=None, or differently seeded generators): rank 0's is THE video
+            torch.distributed.broadcast(latents, src=0)
+        try:
+            latents = self.denoise(latents, kps_feature, audio_embeddings, timesteps, guidance_scale, context_frames,
+                                   context_overlap, context_schedule, distributed, callback, callback_steps)
+        finally:
+            reader.clear()
+            if isinstance(getattr(writer, "unet", None), torch.nn.Module) and hasattr(writer, "clear"):
                 writer.clear()
-            except Exception:
-                pass
         return self._decode_to_host(latents, distributed)
 
-    def _decode_to_host(self, latents, distributed):
+    def decode_to_device(self, latents, distributed):
+        """VAE decode, sharded by frame over the ranks: (3,L,H,W) fp32 on rank 0's device (None on the other ranks);
+        the shards meet over NVLink."""
         L = latents.shape[2]
+        H, W = latents.shape[3] * self.vae_scale_factor, latents.shape[4] * self.vae_scale_factor
         rank, world = 0, 1
         if distributed and torch.distributed.is_available() and torch.distributed.is_initialized():
             rank, world = torch.distributed.get_rank(), torch.distributed.get_world_size()
         if world == 1:
-            video = self.decode_latents(latents)
-            video = video.cpu()                                                  # one D2H for the whole video
-            return video.permute(1, 0, 2, 3).unsqueeze(0).contiguous()
+            return self.decode_latents(latents)
         per = math.ceil(L / world)
         ids = list(range(rank * per, min(L, (rank + 1) * per)))
-        part = self.decode_latents(latents, ids)
-        H, W = latents.shape[3] * 8, latents.shape[4] * 8
-        buf = torch.zeros((per, 3, H, W), device=latents.device, dtype=torch.float32)
-        buf[:part.shape[0]].copy_(part)
+        buf = torch.zeros((3, per, H, W), device=latents.device, dtype=torch.float32)
+        if ids:
+            self.decode_latents(latents, ids, out=buf[:, :len(ids)])
         gathered = [torch.empty_like(buf) for _ in range(world)] if rank == 0 else None
         torch.distributed.gather(buf, gathered, dst=0)
         if rank != 0:
             return None
-        video = torch.cat(gathered)[:L].cpu()
-        return video.permute(1, 0, 2, 3).unsqueeze(0).contiguous()
+        return torch.cat(gathered, dim=1)[:, :L]
+
+    def _decode_to_host(self, latents, distributed):
+        """-> (1,3,L,H,W) fp32 on the host (rank 0): one device->host copy into pinned memory from torch's caching host
+        allocator (a fresh tensor per call; the block is recycled when the caller drops it)."""
+        video = self.decode_to_device(latents, distributed)
+        if video is None:
+            return None
+        host = torch.empty((1,) + tuple(video.shape), dtype=torch.float32, pin_memory=True)
+        host[0].copy_(video, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return host
 
     def __call__(self, reference_image, kps_images, audio_waveform, width, height, video_length, num_inference_steps,
                  guidance_scale, strength=1., num_images_per_prompt=1, eta: float = 0.0, generator=None,
