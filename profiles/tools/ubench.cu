@@ -146,6 +146,85 @@ __global__ void __launch_bounds__(1024, 1) alu_kernel(int mode, int iters, long 
   if (s == 12345.f) sink[0] = s + __uint_as_float(pk);
 }
 
+
+// One softmax warp of the flash kernel in isolation, nw independent warps per CTA, no barriers between warps:
+//   LDTM 64 S columns -> [row max] -> 64 x (fma, ex2, pack) -> STTM 32 packed P columns.
+// VARIANT 0: max first (the exponentials depend on it).  1: stale max (exponentials use the previous tile's max; this
+// tile's max is computed alongside).  2: no max at all.  3: like 0, all exponentials on MUFU (no polynomial share).
+// 4: like 1 with the LDTM of the second 32 columns overlapped with the first 32 exponentials.
+template <int VARIANT>
+__global__ void __launch_bounds__(512, 1) softmax_warp_kernel(int iters, float c, long long* out, uint32_t* sink) {
+  __shared__ uint32_t slot;
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) { tmem_alloc(&slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t base = slot + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 64 & 255);
+  const uint32_t pbase = base + 256;
+  {  // fill the S region with something finite
+    uint32_t z[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) z[i] = __float_as_uint(-0.01f * (float)((threadIdx.x * 7 + i * 13) & 255));
+    tmem_st32(base, z);
+    tmem_st32(base + 32, z);
+    tmem_st_wait();
+  }
+  float m_used = 0.f;
+  uint32_t acc = 0;
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+    uint32_t v[2][32];
+    tmem_ld32(base, v[0]);
+    if (VARIANT != 4) tmem_ld32(base + 32, v[1]);
+    tmem_ld_wait();
+    if (VARIANT == 4) tmem_ld32(base + 32, v[1]);
+    float mc;
+    if (VARIANT == 0 || VARIANT == 3) {
+      float mxs[4] = {__uint_as_float(v[0][0]), __uint_as_float(v[0][1]), __uint_as_float(v[0][2]), __uint_as_float(v[0][3])};
+#pragma unroll
+      for (int g = 0; g < 2; ++g)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mxs[i & 3] = fmaxf(mxs[i & 3], __uint_as_float(v[g][i]));
+      m_used = fmaxf(m_used, fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3])));
+      mc = m_used * c;
+    } else {
+      mc = m_used * c;
+    }
+    uint32_t pk[32];
+    float mxs[4] = {-1e30f, -1e30f, -1e30f, -1e30f};
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      if (VARIANT == 4 && g == 1) tmem_ld_wait();
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        float e[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float sv = __uint_as_float(v[g][h * 8 + i]);
+          if (VARIANT == 1 || VARIANT == 4) mxs[i & 3] = fmaxf(mxs[i & 3], sv);
+          const float xx = fmaf(sv, c, -mc);
+          e[i] = (VARIANT != 3 && i == 7) ? ex2_poly(xx) : ex2a(xx);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) pk[g * 16 + h * 4 + i] = pack_bf16(e[2 * i], e[2 * i + 1]);
+      }
+    }
+    if (VARIANT == 1 || VARIANT == 4) m_used = fmaxf(m_used, fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3])));
+    tmem_st32(pbase, pk);
+    tmem_st_wait();
+    acc += pk[0];
+  }
+  const long long t1 = clock64();
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) atomicMax((unsigned long long*)&out[blockIdx.x], (unsigned long long)(t1 - t0));
+  if (acc == 0x12345678u) sink[0] = acc;
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(slot, 512); }
+}
+
 int main() {
   int sms = 0;
   CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
@@ -187,5 +266,29 @@ int main() {
       const double clk = med();
       printf("%-30s warps=%2d: %7.2f elements/clk/SM\n", an[mode], nw, (double)nw * 32 * iters * 16 / clk);
     }
+
+  {
+    const char* vn[5] = {"softmax warp: max first, 1/8 poly", "softmax warp: stale max, 1/8 poly", "softmax warp: no max, 1/8 poly",
+                         "softmax warp: max first, all MUFU", "softmax warp: stale max, split LDTM"};
+    for (int var = 0; var < 5; ++var)
+      for (int nw : {4, 8, 12, 16}) {
+        CK(cudaMemset(d_out, 0, sms * sizeof(long long)));
+        auto run = [&](int n) {
+          switch (var) {
+            case 0: softmax_warp_kernel<0><<<sms, nw * 32>>>(n, 0.2f, d_out, d_sink); break;
+            case 1: softmax_warp_kernel<1><<<sms, nw * 32>>>(n, 0.2f, d_out, d_sink); break;
+            case 2: softmax_warp_kernel<2><<<sms, nw * 32>>>(n, 0.2f, d_out, d_sink); break;
+            case 3: softmax_warp_kernel<3><<<sms, nw * 32>>>(n, 0.2f, d_out, d_sink); break;
+            default: softmax_warp_kernel<4><<<sms, nw * 32>>>(n, 0.2f, d_out, d_sink); break;
+          }
+        };
+        run(16);
+        CK(cudaMemset(d_out, 0, sms * sizeof(long long)));
+        run(2048);
+        const double clk = med();
+        printf("%-36s warps/SMSP=%d: %7.1f clk per (32 rows x 64 cols) per warp, %6.2f elements/clk/SM, 2 q-tiles x 128 keys = %6.0f clk\n",
+               vn[var], nw / 4, clk / 2048, (double)nw * 2048 * 2048 / clk, clk / 2048 * 16.0 / nw);
+      }
+  }
   return 0;
 }

@@ -48,35 +48,25 @@ def test_gemm_lnfold_matches_layernorm_then_linear(M, K, N, geglu, residual):
     assert err < 6e-3, err
 
 
-def test_unet_with_ln_fold_matches_default(golden_dir, monkeypatch):
-    """Whole small UNet: VX_LN_FOLD=1 against the default LayerNorm-kernel path (same weights, same inputs)."""
+def test_unet_with_ln_fold_vs_oracle(golden_dir, monkeypatch):
+    """Whole small UNet with VX_LN_FOLD=1 against the fp32 oracle on the same bf16-rounded weights: same bound as the
+    default LayerNorm-kernel path (two bf16 evaluation orders of the same network sit ~sqrt(2) x 1.6e-2 apart from each
+    other, so they are each compared with fp32, not with one another)."""
     from oracle import vx_oracle as O
-    from vexpress_b200.modules import ReferenceAttentionControl, UNet3DConditionModel
+    from test_unet_gpu import build_product
     cfg = O.small_cfg()
     sd = O.synth_state_dict(O.unet_param_shapes(cfg), 1234)
     lat, kps, audio, banks = O.synth_inputs(cfg, 4, 16, 16, True, 42)
-
-    def build():
-        m = UNet3DConditionModel(
-            block_out_channels=cfg["block_out_channels"], cross_attention_dim=cfg["cross_attention_dim"],
-            use_inflated_groupnorm=True, use_motion_module=True, motion_module_mid_block=True,
-            motion_module_type="Vanilla",
-            motion_module_kwargs=dict(num_attention_heads=8, num_transformer_block=1,
-                                      attention_block_types=["Temporal_Self", "Temporal_Self"],
-                                      temporal_position_encoding=True, temporal_position_encoding_max_len=32,
-                                      temporal_attention_dim_div=1))
-        m.load_state_dict(sd, strict=True)
-        m = m.to(device="cuda", dtype=torch.bfloat16)
-        r = ReferenceAttentionControl(m, do_classifier_free_guidance=True, mode="read", fusion_blocks="full",
-                                      reference_attention_weight=0.95, audio_attention_weight=3.0)
-        r.update(type("W", (), {"banks": [b[1:].cuda() for b in banks]})(), True, dtype=torch.bfloat16)
-        return m
-    x = lat.repeat(2, 1, 1, 1, 1).cuda().bfloat16()
-    enc = audio.reshape(-1, 5, cfg["cross_attention_dim"]).cuda().bfloat16()
-    k = kps.cuda().bfloat16()
-    base = build()(x, 499, enc, kps_features=k, return_dict=False)[0]
-    monkeypatch.setenv("VX_LN_FOLD", "1")
-    fold = build()(x, 499, enc, kps_features=k, return_dict=False)[0]
-    err = _rel(fold, base)
-    print(f"unet ln-fold vs default rel={err:.3e}")
-    assert err < 2e-2, err
+    x = lat.repeat(2, 1, 1, 1, 1)
+    enc = audio.reshape(-1, 5, cfg["cross_attention_dim"])
+    r = lambda t: t.bfloat16().float()
+    with torch.no_grad():
+        ref = O.unet_forward({k: r(v) for k, v in sd.items()}, cfg, r(x), 499, r(enc), r(kps), [r(b) for b in banks], 0.95, 3.0)
+    errs = {}
+    for fold in ("0", "1"):
+        monkeypatch.setenv("VX_LN_FOLD", fold)
+        model, _ = build_product(cfg, sd, [b[1:] for b in banks], 0.95, 3.0)
+        out = model(x.cuda().bfloat16(), 499, enc.cuda().bfloat16(), kps_features=kps.cuda().bfloat16(), return_dict=False)[0]
+        errs[fold] = _rel(out.cpu(), ref)
+    print(f"unet vs oracle: default {errs['0']:.3e}, ln-fold {errs['1']:.3e}")
+    assert errs["1"] < 3e-2 and errs["1"] < 1.5 * errs["0"], errs
