@@ -151,13 +151,20 @@ def gen_unet(msa, unet3d):
     print("unet_small.pt: out", tuple(out.shape), "absmean", out.abs().mean().item())
 
 
-def gen_pipeline(msa, unet3d, pipe):
+def scheduler_kwargs():
+    """noise_scheduler_kwargs of the reference's own inference_v2.yaml:23-33 (what inference.py:132-136 passes)."""
+    import yaml
+    with open(os.path.join(REF, "inference_v2.yaml")) as fh:
+        return dict(yaml.safe_load(fh)["noise_scheduler_kwargs"])
+
+
+def gen_pipeline(msa, unet3d, pipe, L=12, S=8, Ov=4, steps=3, name="pipeline_small.pt", with_video=True):
     cfg = O.small_cfg()
     vcfg = O.small_vae_cfg()
     sd = O.synth_state_dict(O.unet_param_shapes(cfg), seed=1234)
     vsd = O.synth_state_dict(O.vae_param_shapes(vcfg), seed=1235)
     model = build_reference_unet(unet3d, cfg, sd)
-    L, h, S, Ov, steps, gs = 12, 16, 8, 4, 3, 3.5
+    h, gs = 16, 3.5
     latents, kps, audio, banks = O.synth_inputs(cfg, L=L, h=h, w=h, do_cfg=True, seed=42)
     from diffusers import AutoencoderKL, DDIMScheduler
     vae = AutoencoderKL(vsd, vcfg)
@@ -197,7 +204,7 @@ def gen_pipeline(msa, unet3d, pipe):
     msa.ReferenceAttentionControl.update = update
     try:
         p = Pipe(vae=vae, reference_net=StubRefNet(), denoising_unet=model, v_kps_guider=None, audio_processor=None,
-                 audio_encoder=None, audio_projection=None, scheduler=DDIMScheduler())
+                 audio_encoder=None, audio_projection=None, scheduler=DDIMScheduler(**scheduler_kwargs()))
         captured = {}
         orig_decode = Pipe.decode_latents
 
@@ -211,10 +218,11 @@ def gen_pipeline(msa, unet3d, pipe):
                       context_overlap=Ov, reference_attention_weight=0.95, audio_attention_weight=3.0)
     finally:
         msa.ReferenceAttentionControl.update = real_update
-    torch.save(dict(cfg=cfg, vae_cfg=vcfg, L=L, h=h, S=S, O=Ov, steps=steps, guidance_scale=gs,
-                    final_latents=captured["latents"], video=video.half()),
-               os.path.join(GOLD, "pipeline_small.pt"))
-    print("pipeline_small.pt: video", tuple(video.shape), "latents absmean", captured["latents"].abs().mean().item())
+    out = dict(cfg=cfg, vae_cfg=vcfg, L=L, h=h, S=S, O=Ov, steps=steps, guidance_scale=gs, final_latents=captured["latents"])
+    if with_video:
+        out["video"] = video.half()
+    torch.save(out, os.path.join(GOLD, name))
+    print(name, ": video", tuple(video.shape), "latents absmean", captured["latents"].abs().mean().item())
 
 
 def gen_refnet(msa, unet3d):
@@ -322,9 +330,11 @@ def gen_prologue(pipe):
 
 
 def gen_ddim():
-    """Known-answer values of the restated DDIM -- self-pins, cross-checked
-    against the constants quoted in the survey."""
-    s = O.DDIM()
+    """Known-answer values of the DDIM configuration of inference_v2.yaml:23-33, produced by the shim's library-structured
+    ``DDIMScheduler`` (written separately from ``O.DDIM``; both are also held to float64 closed forms in
+    tests/test_oracle_golden.py)."""
+    from diffusers import DDIMScheduler
+    s = DDIMScheduler(**scheduler_kwargs())
     kat = dict(abar={str(i): float(s.alphas_cumprod[i]) for i in (0, 1, 499, 959, 998, 999)})
     for n in (2, 25, 50):
         s.set_timesteps(n)
@@ -351,6 +361,18 @@ if __name__ == "__main__":
         gen_unet(msa, unet3d)
     if "pipeline" in which:
         gen_pipeline(msa, unet3d, pipe)
+        # video_length that does NOT tile: the tail window is reflected and repeats frames.  The
+        # reference then writes `latents[:, :, step_frame_ids] = ...` with DUPLICATE indices on a host tensor
+        # (v_express_pipeline.py:572) -- torch documents index_put_ with duplicates as undefined, and with several intra-op
+        # threads which duplicate wins is a race (measured: 8 threads -> frames 13..15 keep the FIRST write, frames 12,
+        # 16..18 the LAST).  Single-threaded the writes are sequential and the last one wins; that defined behaviour is
+        # what the oracle and the product implement, so this golden is generated with one thread.
+        nthreads = torch.get_num_threads()
+        torch.set_num_threads(1)
+        try:
+            gen_pipeline(msa, unet3d, pipe, L=20, S=16, Ov=4, steps=2, name="pipeline_nontiling_small.pt", with_video=False)
+        finally:
+            torch.set_num_threads(nthreads)
     if "refnet" in which:
         gen_refnet(msa, unet3d)
     if "prologue" in which:

@@ -822,7 +822,12 @@ def denoise(sd, cfg, latents: Tensor, kps_feature: Tensor, audio_embeddings: Ten
                     preds.append(noise_preds[fi])
                     noise_preds[fi] = None
             preds = torch.stack(preds, dim=2)
-            latents[:, :, ids] = sched.step(preds, t, latents[:, :, ids]).prev_sample
+            stepped = sched.step(preds, t, latents[:, :, ids]).prev_sample
+            # the reference writes `latents[:, :, ids] = stepped` (:572).  When a reflected window repeats a frame, `ids`
+            # holds duplicates; torch leaves index_put_ with duplicates undefined (multi-threaded it is a race).  Defined
+            # here as the sequential order -- the last write wins -- which is what the reference does on one thread.
+            for k, fi in enumerate(ids):
+                latents[:, :, fi] = stepped[:, :, k]
     return latents
 
 

@@ -93,6 +93,20 @@ def test_pipeline_matches_reference(golden_dir):
     torch.testing.assert_close(video, g["video"].float(), atol=2e-3, rtol=0)
 
 
+def test_pipeline_non_tiling_length_matches_reference(golden_dir):
+    """video_length 20, windows of 16 with overlap 4: the reflected tail window repeats frames; the golden is the output
+    of the reference's own pipeline code for that call (its index-put / streaming bookkeeping)."""
+    g = torch.load(os.path.join(golden_dir, "pipeline_nontiling_small.pt"), weights_only=False)
+    cfg = g["cfg"]
+    sd = O.synth_state_dict(O.unet_param_shapes(cfg), 1234)
+    lat, kps, audio, banks = O.synth_inputs(cfg, g["L"], g["h"], g["h"], True, 42)
+    wins = O.context_windows(g["L"], g["S"], g["O"])
+    assert any(len(set(w)) != len(w) for w in wins)
+    with torch.no_grad():
+        final = O.denoise(sd, cfg, lat, kps, audio, banks, g["steps"], g["guidance_scale"], g["S"], g["O"], 0.95, 3.0)
+    torch.testing.assert_close(final, g["final_latents"], atol=5e-4, rtol=1e-4)
+
+
 def test_refnet_param_layout_full_width():
     S = O.refnet_param_shapes(O.DEFAULT_CFG)          # SD-1.5 UNet2D minus the conv_norm_out the reference drops
     assert len(S) == 684
@@ -141,3 +155,86 @@ def test_prologue_and_postprocessing_match_reference(golden_dir):
     filt = O.median_filter_3d(v, 3)
     assert torch.equal(filt, m["filtered"])                         # order statistics: bit-exact
     assert np.array_equal(O.video_to_uint8(filt), m["uint8"].numpy())
+
+
+# ---- independent pins of the DDIM scheduler and the VAE decoder (neither is reference code: diffusers 0.29.2) ---------
+def _shim():
+    import sys
+    p = os.path.join(os.path.dirname(os.path.abspath(O.__file__)), "diffusers_shim")
+    if p not in sys.path:
+        sys.path.insert(0, p)
+    import diffusers
+    return diffusers
+
+
+def _abar_float64():
+    """inference_v2.yaml:23-33 in closed form, float64: scaled-linear betas, then the zero-terminal-SNR rescale
+    sqrt(abar)_t -> (sqrt(abar)_t - sqrt(abar)_T) * sqrt(abar)_0 / (sqrt(abar)_0 - sqrt(abar)_T)."""
+    i = np.arange(1000, dtype=np.float64)
+    betas = (np.sqrt(0.00085) + i * (np.sqrt(0.012) - np.sqrt(0.00085)) / 999.0) ** 2
+    root = np.sqrt(np.cumprod(1.0 - betas))
+    root = (root - root[-1]) * root[0] / (root[0] - root[-1])
+    return root ** 2
+
+
+def test_ddim_against_float64_closed_form_and_independent_restatement():
+    abar = _abar_float64()
+    assert abar[999] == 0.0
+    s = O.DDIM()
+    got = s.alphas_cumprod.double().numpy()
+    # fp32 tables (linspace, two cumprods over 1000 factors) vs float64: a few fp32 ulps
+    np.testing.assert_allclose(got, abar, atol=1e-6, rtol=0)
+    for t in (0, 1, 499, 959):
+        assert abs(got[t] / abar[t] - 1) < 2e-5, t
+    # trailing spacing: round(1000 - k * 1000 / n) - 1
+    for n in (2, 25, 50):
+        s.set_timesteps(n)
+        want = [int(np.round(1000 - k * 1000.0 / n)) - 1 for k in range(n)]
+        assert s.timesteps.tolist() == want
+    # one v-prediction step (eta = 0) by hand in float64: x0 = sqrt(a) x - sqrt(1-a) v, eps = sqrt(a) v + sqrt(1-a) x,
+    # x' = sqrt(a') x0 + sqrt(1-a') eps; t = 959 -> prev = 919 (n = 25); and the last step t = 39 -> prev < 0 -> a' = 1
+    s.set_timesteps(25)
+    g = torch.Generator().manual_seed(3)
+    x, v = torch.randn(64, generator=g), torch.randn(64, generator=g)
+    for t, tp in ((959, 919), (39, None), (999, 959)):
+        a, ap = abar[t], (abar[tp] if tp is not None else 1.0)
+        x64, v64 = x.double().numpy(), v.double().numpy()
+        x0 = np.sqrt(a) * x64 - np.sqrt(1 - a) * v64
+        eps = np.sqrt(a) * v64 + np.sqrt(1 - a) * x64
+        want = np.sqrt(ap) * x0 + np.sqrt(1 - ap) * eps
+        np.testing.assert_allclose(s.step(v, t, x).prev_sample.double().numpy(), want, atol=3e-6)
+    # the product's host-side table (what vx_ddim_step is fed with)
+    from vexpress_b200.pipelines.scheduler import DDIMScheduler as Prod, ddim_coefficients
+    p = Prod()
+    p.set_timesteps(25)
+    sa, sb, sap, sbp = ddim_coefficients(p, 959)
+    np.testing.assert_allclose([sa, sb, sap, sbp], [np.sqrt(abar[959]), np.sqrt(1 - abar[959]), np.sqrt(abar[919]),
+                                                    np.sqrt(1 - abar[919])], rtol=2e-5)
+    # second, separately written implementation in the library's own structure (oracle/diffusers_shim)
+    lib = _shim().DDIMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", clip_sample=False,
+                                steps_offset=1, prediction_type="v_prediction", rescale_betas_zero_snr=True,
+                                timestep_spacing="trailing")
+    assert lib.__class__.__module__.startswith("diffusers") and not isinstance(lib, O.DDIM)
+    np.testing.assert_allclose(lib.alphas_cumprod.double().numpy(), abar, atol=1e-6, rtol=0)
+    for n in (2, 25, 50):
+        lib.set_timesteps(n)
+        s.set_timesteps(n)
+        assert lib.timesteps.tolist() == s.timesteps.tolist()
+        for t in lib.timesteps.tolist():
+            np.testing.assert_allclose(lib.step(v, t, x).prev_sample.numpy(), s.step(v, t, x).prev_sample.numpy(), atol=1e-6)
+
+
+def test_vae_decoder_against_independent_module_restatement():
+    """The oracle's functional decoder vs an nn.Module AutoencoderKL assembled in diffusers' structure from separately
+    written leaves (oracle/diffusers_shim/diffusers/autoencoder.py); the module tree also pins the state_dict layout."""
+    d = _shim()
+    vcfg = O.small_vae_cfg()
+    vsd = O.synth_state_dict(O.vae_param_shapes(vcfg), 1235)
+    vae = d.AutoencoderKL(vsd, vcfg)                       # strict load: key names + shapes of the diffusers layout
+    assert "vx_oracle" not in open(d.autoencoder.__file__).read().split('"""', 2)[2]
+    z = torch.randn(2, 4, 16, 16, generator=torch.Generator().manual_seed(8))
+    with torch.no_grad():
+        a = vae.decode(z).sample
+        b = O.vae_decode(vsd, vcfg, z)
+    assert a.shape == (2, 3, 128, 128)
+    np.testing.assert_allclose(a.numpy(), b.numpy(), atol=2e-5, rtol=1e-5)
