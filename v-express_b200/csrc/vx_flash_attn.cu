@@ -653,6 +653,269 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// v3: many small independent CTAs instead of one big choreographed one.  Measured on B200 (profiles/tools/ubench.cu,
+// profiles/r02_flash_notes.md): the hd = 40 attention is bound by the softmax instruction stream -- 16 ex2/clk/SM on the
+// MUFU pipe, ~14.5 elements/clk/SM for a whole LDTM -> row max -> fma/ex2/pack -> STTM warp iteration when the warps run
+// free of each other (2250 clk per 2 x 128 x 128 scores) -- while v2's 16 softmax warps advance in lock-step
+// (pair barriers for the split-row maxima, 256-thread P hand-offs, two tiles sharing one MUFU phase): every phase that is
+// not the exponential one is exposed and an iteration costs 3450 clk.  v3 removes every softmax-side rendezvous:
+//   * one CTA = ONE 128-row query tile, 64 keys per step; 4 softmax warps (one per TMEM lane quadrant, 1 thread = 1 row =
+//     64 scores: no split rows, no max exchange, no named barriers), 1 TMA warp, 1 MMA warp;
+//   * tensor memory per CTA: S (64 fp32 columns) + O (hdp columns) = 112 columns at hd 40 -> 128 allocated, so THREE
+//     CTAs are resident per SM (2 for hd 80 / 128); P (bf16, 32 packed columns) overwrites the S columns the thread has
+//     just read and feeds P.V as a TS-MMA straight from tensor memory;
+//   * S is single-buffered: softmax(j) -> P.V(j) -> S(j+1) is a serial chain inside a CTA, and the two other resident
+//     CTAs (at unrelated phases: the hardware scheduler staggers them by construction) fill the SM meanwhile.
+// Used when hd <= 128, Nq % 128 == 0 and Nk % 64 == 0.
+constexpr int kFa3Threads = 192;
+
+struct Fa3Args {
+  int Nq, Nk, hd, hdp, kv_div, stages;
+  float scale_log2;
+  __nv_bfloat16* out;
+  long long ldo;
+  int q_bytes, kv_bytes;     // Q tile (128 rows) / K or V tile (64 keys), padded head dim
+  uint32_t tmem_cols;        // power of two >= 64 + hdp
+};
+
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+
+template <bool ONES, int PMASK, int MINB>
+__global__ void __maxnreg__(MINB == 3 ? 112 : 168)     // 3 (2) resident CTAs x 192 threads within the 64 K registers of an SM
+flash_attn3_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
+                   const __grid_constant__ CUtensorMap mapV, const Fa3Args p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + p.q_bytes;
+  uint8_t* sV = sK + p.stages * p.kv_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + p.stages * p.kv_bytes);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;          // [<= 8]
+  uint64_t* kv_empty = kv_full + 8;      // [8]
+  uint64_t* s_full = kv_empty + 8;
+  uint64_t* p_ready = s_full + 1;
+  uint64_t* pv_done = p_ready + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q_tile = blockIdx.x, head = blockIdx.y, bq = blockIdx.z;
+  const int T = p.Nk / 64;
+  if (p.hdp > p.hd) {
+    // the padding chunk of Q / K / V (hd 40 -> 48) must read as exact zeros; TMA only ever writes chunks < hd / 8
+    const int total16 = (p.q_bytes + 2 * p.stages * p.kv_bytes) / 16;
+    uint4* z = reinterpret_cast<uint4*>(sQ);
+    for (int i = threadIdx.x; i < total16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+    if (ONES) {
+      __syncthreads();
+      // V tiles are [hdp/8 chunks][64 keys][8]: element (key, col hd) = chunk hd/8, slot hd%8
+      for (int i = threadIdx.x; i < p.stages * 64; i += blockDim.x) {
+        const int st = i / 64, key = i % 64;
+        reinterpret_cast<__nv_bfloat16*>(sV + st * p.kv_bytes + (p.hd / 8) * 1024 + key * 16)[p.hd % 8] = __float2bfloat16(1.0f);
+      }
+    }
+  }
+  if (threadIdx.x == 0) {
+    mbar_init(q_full, 1);
+    for (int s = 0; s < 8; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(p_ready, 128);
+    mbar_init(pv_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 5) {
+    tmem_alloc(tmem_slot, p.tmem_cols);
+    tmem_relinquish();
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_o = tmem_base + 64u;
+
+  if (warp == 4) {
+    // ------------------------------------------------------------ TMA producer (warp-uniform loop, elected lane issues)
+    const bool leader = elect_one();
+    const int col_chunk = head * p.hd / 8;
+    const int kv_row0 = (bq / p.kv_div) * p.Nk;
+    if (leader) {
+      tma_prefetch_desc(&mapQ);
+      tma_prefetch_desc(&mapK);
+      tma_prefetch_desc(&mapV);
+      mbar_expect_tx(q_full, 128 * p.hd * 2);
+      tma_load_3d(sQ, &mapQ, q_full, 0, bq * p.Nq + q_tile * 128, col_chunk);
+    }
+    __syncwarp();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int j = 0; j < T; ++j) {
+      mbar_wait(&kv_empty[stage], phase ^ 1);
+      if (leader) {
+        mbar_expect_tx(&kv_full[stage], 2 * 64 * p.hd * 2);
+        tma_load_3d(sK + stage * p.kv_bytes, &mapK, &kv_full[stage], 0, kv_row0 + j * 64, col_chunk);
+        tma_load_3d(sV + stage * p.kv_bytes, &mapV, &kv_full[stage], 0, kv_row0 + j * 64, col_chunk);
+      }
+      __syncwarp();
+      if (++stage == p.stages) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+  } else if (warp == 5) {
+    // ------------------------------------------------------------ MMA issuer
+    const bool leader = elect_one();
+    const uint32_t idesc_s = make_idesc_bf16(128, 64, 0, 0);
+    const uint32_t idesc_o = make_idesc_bf16(128, (uint32_t)p.hdp, 0, 1);   // B = V is MN-major
+    const uint64_t dq = make_smem_desc(smem_u32(sQ), 2048, 128, SWZ_NONE);
+    const int ksteps = p.hdp / 16;
+    mbar_wait(q_full, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int j = 0; j < T; ++j) {
+      mbar_wait(&kv_full[stage], phase);
+      tc_fence_after();
+      // S(j) = Q K_j^T.  Tensor-core operations of one CTA execute in issue order, so this write of the S columns is
+      // ordered behind P.V(j-1), which read P out of the same columns.
+      const uint64_t dk = make_smem_desc(smem_u32(sK + stage * p.kv_bytes), 1024, 128, SWZ_NONE);
+      if (leader) {
+        for (int k = 0; k < ksteps; ++k)   // Q: +4096 B (= +256) per 16 dims; K: 2 chunks of 64 keys = +2048 B (= +128)
+          umma_ss(tmem_base, dq + (uint64_t)(k * 256), dk + (uint64_t)(k * 128), idesc_s, k ? 1u : 0u);
+        umma_commit(s_full);
+      }
+      __syncwarp();
+      mbar_wait(p_ready, (uint32_t)(j & 1));
+      tc_fence_after();
+      const uint64_t dv = make_smem_desc(smem_u32(sV + stage * p.kv_bytes), 128, 1024, SWZ_NONE);
+      if (leader) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)   // A = P from tensor memory (8 packed columns per 16 keys); V: +256 B (= +16) per 16 keys
+          umma_ts(tmem_o, tmem_base + (uint32_t)(k * 8), dv + (uint64_t)(k * 16), idesc_o, (j | k) ? 1u : 0u);
+        umma_commit(&kv_empty[stage]);
+        umma_commit(pv_done);
+      }
+      __syncwarp();
+      if (++stage == p.stages) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ softmax: warp = TMEM lane quadrant, thread = query row
+    const int row = warp * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+    const uint32_t ts = tmem_base + lane_addr;
+    const uint32_t to = tmem_o + lane_addr;
+    float m_used = -INFINITY, l = 0.f;
+    const float c = p.scale_log2;
+    for (int j = 0; j < T; ++j) {
+      mbar_wait(s_full, (uint32_t)(j & 1));
+      tc_fence_after();
+      uint32_t v[2][32];
+      tmem_ld32(ts, v[0]);
+      tmem_ld32(ts + 32, v[1]);
+      tmem_ld_wait();
+      // row max of the 64 scores: 3-input max (sm_100), four independent chains
+#define VX_SV(k) __uint_as_float(v[(k) >> 5][(k) & 31])
+      float mxs[4] = {VX_SV(0), VX_SV(1), VX_SV(2), VX_SV(3)};
+#pragma unroll
+      for (int k = 4; k < 60; k += 8)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) mxs[u] = fmax3(mxs[u], VX_SV(k + u), VX_SV(k + 4 + u));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) mxs[u] = fmaxf(mxs[u], VX_SV(60 + u));
+#undef VX_SV
+      const float mx = fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3]));
+      const float m_new = fmaxf(m_used, mx);
+      const bool need = (m_new - m_used) * c > 8.0f;   // lazy rescale: only when the running max grew by > 2^8
+      if (__any_sync(0xffffffffu, need)) {
+        const float alpha = (m_used == -INFINITY) ? 0.f : ex2_approx((m_used - m_new) * c);
+        l *= alpha;
+        m_used = m_new;
+        if (j > 0) {
+          mbar_wait(pv_done, (uint32_t)((j - 1) & 1));   // P.V(j-1) has landed in O
+          tc_fence_after();
+          for (int cb = 0; cb < p.hdp; cb += 16) {
+            uint32_t o[16];
+            tmem_ld16(to + cb, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st16(to + cb, o);
+          }
+          tmem_st_wait();
+        }
+      }
+      const float mc = m_used * c;
+      float ls[4] = {0.f, 0.f, 0.f, 0.f};
+      uint32_t pk[32];
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          float e[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float xx = fmaf(__uint_as_float(v[g][h * 8 + i]), c, -mc);
+            e[i] = ((i & PMASK) == PMASK) ? ex2_poly(xx) : ex2_approx(xx);
+            if (!ONES) ls[i & 3] += e[i];
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) pk[g * 16 + h * 4 + i] = pack_bf16(e[2 * i], e[2 * i + 1]);
+        }
+      }
+      if (!ONES) l += (ls[0] + ls[1]) + (ls[2] + ls[3]);
+      tmem_st32(ts, pk);        // P(j): 64 keys = 32 packed columns over the S columns this thread has consumed
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(p_ready);
+    }
+    mbar_wait(pv_done, (uint32_t)((T - 1) & 1));
+    tc_fence_after();
+    const int qrow = q_tile * 128 + row;
+    __nv_bfloat16* op = p.out + ((long long)bq * p.Nq + qrow) * p.ldo + head * p.hd;
+    if (ONES) {
+      uint32_t o[16];
+      tmem_ld16(to + (p.hd / 16) * 16, o);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (i == (p.hd & 15)) l = __uint_as_float(o[i]);
+    }
+    const float inv = 1.f / l;
+    for (int cb = 0; cb < p.hdp; cb += 16) {
+      uint32_t o[16];
+      tmem_ld16(to + cb, o);
+      tmem_ld_wait();
+#pragma unroll
+      for (int h8 = 0; h8 < 2; ++h8) {
+        if (cb + h8 * 8 < p.hd) {
+          const int b8 = h8 * 8;
+          *reinterpret_cast<uint4*>(op + cb + b8) = make_uint4(
+              pack_bf16(__uint_as_float(o[b8]) * inv, __uint_as_float(o[b8 + 1]) * inv),
+              pack_bf16(__uint_as_float(o[b8 + 2]) * inv, __uint_as_float(o[b8 + 3]) * inv),
+              pack_bf16(__uint_as_float(o[b8 + 4]) * inv, __uint_as_float(o[b8 + 5]) * inv),
+              pack_bf16(__uint_as_float(o[b8 + 6]) * inv, __uint_as_float(o[b8 + 7]) * inv));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
 // Fallback for key counts the tensor-core tiling cannot express (Nk < 16 or Nk % 16 != 0, e.g. the 2x2 / 12x12
 // maps of reduced test resolutions): one warp per (batch, head, query), exact softmax, CUDA cores.
 struct GaArgs {
@@ -715,6 +978,41 @@ __global__ void __launch_bounds__(128) generic_attn_kernel(const GaArgs p) {
 
 using namespace vx;
 
+// A/B switches (bring-up only), read ONCE per process: the launch path itself never touches the environment.
+namespace {
+struct FaEnv {
+  int v1, v2, psmem, noones, stages, stagger, pairsync, latewait, baton, poly, v3_stages;
+  long long* trace;
+  static int geti(const char* n, int d) {
+    const char* e = getenv(n);
+    return e ? atoi(e) : d;
+  }
+  FaEnv() {
+    v1 = geti("VX_FA_V1", 0);
+    v2 = geti("VX_FA_V2", 0);
+    psmem = geti("VX_FA_PSMEM", 0);
+    noones = geti("VX_FA_NOONES", 0);
+    stages = geti("VX_FA_STAGES", 0);
+    stagger = geti("VX_FA_STAGGER", 0);
+    pairsync = geti("VX_FA_PAIRSYNC", 1);
+    latewait = geti("VX_FA_LATEWAIT", 0);
+    baton = geti("VX_FA_BATON", 0);
+    poly = geti("VX_FA_POLY", 8);
+    v3_stages = geti("VX_FA3_STAGES", 0);
+    const char* t = getenv("VX_FA_TRACE");
+    trace = t ? (long long*)strtoull(t, nullptr, 10) : nullptr;
+  }
+};
+const FaEnv& fa_env() {
+  static const FaEnv e;
+  return e;
+}
+}  // namespace
+
+extern "C" void vx_flash_reload_env() {   // test / sweep hook: re-read the switches (not used by the product)
+  const_cast<FaEnv&>(fa_env()) = FaEnv();
+}
+
 // q: [Bq*Nq, ldq], k/v: [Bkv*Nk, ldk] / [.., ldv] (bf16, heads*hd columns used), out: [Bq*Nq, ldo].
 // kv batch of query batch b is b / kv_div.
 extern "C" int vx_flash_attention(const void* q, long long ldq, const void* k, long long ldk, const void* v,
@@ -733,7 +1031,54 @@ extern "C" int vx_flash_attention(const void* q, long long ldq, const void* k, l
     return 0;
   }
   const int hdp = (hd + 15) / 16 * 16;
-  if (hdp <= 128 && Nq % 256 == 0 && Nk % 128 == 0 && !getenv("VX_FA_V1")) {
+  const FaEnv& env = fa_env();
+  if (hdp <= 128 && Nq % 128 == 0 && Nk % 64 == 0 && !env.v1 && !env.v2) {
+    // ---- v3: one query tile per CTA, 64 keys per step, 2-3 CTAs per SM
+    Fa3Args a{};
+    a.Nq = Nq; a.Nk = Nk; a.hd = hd; a.hdp = hdp; a.kv_div = kv_div;
+    a.scale_log2 = 1.4426950408889634f / sqrtf((float)hd);
+    a.out = (__nv_bfloat16*)out; a.ldo = ldo;
+    a.q_bytes = 128 * hdp * 2;
+    a.kv_bytes = 64 * hdp * 2;
+    a.tmem_cols = 64 + hdp <= 128 ? 128u : 256u;
+    const int ctas = a.tmem_cols == 128 ? 3 : 2;
+    const size_t budget = (size_t)(227 * 1024) / ctas - 1024;          // 1 KB per CTA is reserved by the hardware
+    auto need3 = [&](int st) { return (size_t)a.q_bytes + (size_t)2 * st * a.kv_bytes + 256 + 128; };
+    a.stages = env.v3_stages > 0 ? env.v3_stages : 6;
+    while (a.stages > 2 && need3(a.stages) > budget) --a.stages;
+    if (a.stages > 8) a.stages = 8;
+    const size_t smem3 = need3(a.stages);
+    VX_REQUIRE(smem3 <= 227 * 1024, "vx_flash_attention: smem %zu too large (hd=%d)", smem3, hd);
+    CUtensorMap mQ, mK, mV;
+    const void* ptrs[3] = {q, k, v};
+    const long long lds[3] = {ldq, ldk, ldv};
+    const long long rows[3] = {(long long)Bq * Nq, (long long)Bkv * Nk, (long long)Bkv * Nk};
+    CUtensorMap* maps[3] = {&mQ, &mK, &mV};
+    for (int i = 0; i < 3; ++i) {
+      uint64_t dims[3] = {8, (uint64_t)rows[i], (uint64_t)lds[i] / 8};
+      uint64_t str[2] = {(uint64_t)lds[i] * 2, 16};
+      uint32_t box[3] = {8, i == 0 ? 128u : 64u, (uint32_t)hd / 8};
+      if (make_tmap_bf16(maps[i], ptrs[i], 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
+    }
+    static bool cfg3 = false;
+    if (!cfg3) {
+      VX_CHECK_CUDA(cudaFuncSetAttribute(flash_attn3_kernel<true, 7, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      VX_CHECK_CUDA(cudaFuncSetAttribute(flash_attn3_kernel<true, 3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      VX_CHECK_CUDA(cudaFuncSetAttribute(flash_attn3_kernel<false, 7, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      VX_CHECK_CUDA(cudaFuncSetAttribute(flash_attn3_kernel<false, 7, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+      cfg3 = true;
+    }
+    dim3 grid3(Nq / 128, heads, Bq);
+    const bool ones = hdp > hd && !env.noones;
+    auto st3 = (cudaStream_t)stream;
+    if (ctas == 2) flash_attn3_kernel<false, 7, 2><<<grid3, kFa3Threads, smem3, st3>>>(mQ, mK, mV, a);
+    else if (ones && env.poly == 4) flash_attn3_kernel<true, 3, 3><<<grid3, kFa3Threads, smem3, st3>>>(mQ, mK, mV, a);
+    else if (ones) flash_attn3_kernel<true, 7, 3><<<grid3, kFa3Threads, smem3, st3>>>(mQ, mK, mV, a);
+    else flash_attn3_kernel<false, 7, 3><<<grid3, kFa3Threads, smem3, st3>>>(mQ, mK, mV, a);
+    VX_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
+  if (hdp <= 128 && Nq % 256 == 0 && Nk % 128 == 0 && !env.v1) {
     Fa2Args a{};
     a.Nq = Nq; a.Nk = Nk; a.hd = hd; a.hdp = hdp; a.kv_div = kv_div;
     a.scale_log2 = 1.4426950408889634f / sqrtf((float)hd);
@@ -741,18 +1086,18 @@ extern "C" int vx_flash_attention(const void* q, long long ldq, const void* k, l
     a.q_bytes = 128 * hdp * 2;
     a.kv_bytes = 128 * hdp * 2;
     a.stages = 3;
-    a.stagger = getenv("VX_FA_STAGGER") ? atoi(getenv("VX_FA_STAGGER")) : 0;
-    a.pair_sync = getenv("VX_FA_PAIRSYNC") ? atoi(getenv("VX_FA_PAIRSYNC")) : 1;
-    a.late_wait = getenv("VX_FA_LATEWAIT") ? atoi(getenv("VX_FA_LATEWAIT")) : 0;
-    a.trace = getenv("VX_FA_TRACE") ? (long long*)strtoull(getenv("VX_FA_TRACE"), nullptr, 10) : nullptr;
+    a.stagger = env.stagger;
+    a.pair_sync = env.pairsync;
+    a.late_wait = env.latewait;
+    a.trace = env.trace;
     auto need = [&](int st, int pb) { return (size_t)2 * a.q_bytes + (size_t)2 * st * a.kv_bytes + (size_t)2 * pb * 32768 + 6144 + 512 + 128; };
     // P in tensor memory whenever O (2 x hdp) + S (2 x 128) + P (2 x 64) columns fit the 512-column TMEM
-    a.p_tmem = (hdp <= 64 && !getenv("VX_FA_PSMEM")) ? 1 : 0;
+    a.p_tmem = (hdp <= 64 && !env.psmem) ? 1 : 0;
     a.pbufs = 1;
     a.stages = 6;
     const int psm = a.p_tmem ? 0 : 1;
     while (a.stages > 2 && need(a.stages, psm) > 227 * 1024) --a.stages;
-    if (getenv("VX_FA_STAGES")) a.stages = atoi(getenv("VX_FA_STAGES"));
+    if (env.stages) a.stages = env.stages;
     const size_t smem2 = need(a.stages, psm);
     VX_REQUIRE(smem2 <= 227 * 1024, "vx_flash_attention: smem %zu too large (hd=%d)", smem2, hd);
     CUtensorMap mQ, mK, mV;
@@ -777,9 +1122,9 @@ extern "C" int vx_flash_attention(const void* q, long long ldq, const void* k, l
       cfg2 = true;
     }
     dim3 grid2(Nq / 256, heads, Bq);
-    const bool ones = hdp > hd && !getenv("VX_FA_NOONES");
-    const bool baton = getenv("VX_FA_BATON") && atoi(getenv("VX_FA_BATON")) != 0;
-    const int poly = getenv("VX_FA_POLY") ? atoi(getenv("VX_FA_POLY")) : 8;      // 1/poly of the exponentials on the FMA pipe
+    const bool ones = hdp > hd && !env.noones;
+    const bool baton = env.baton != 0;
+    const int poly = env.poly;      // 1/poly of the exponentials on the FMA pipe
     auto st2 = (cudaStream_t)stream;
     if (ones && baton && poly == 4) flash_attn2_kernel<true, true, 3><<<grid2, kFa2Threads, smem2, st2>>>(mQ, mK, mV, a);
     else if (ones && baton && poly == 2) flash_attn2_kernel<true, true, 1><<<grid2, kFa2Threads, smem2, st2>>>(mQ, mK, mV, a);
