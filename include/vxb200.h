@@ -134,22 +134,13 @@ int vx_ddim_step(void* latents, const float* acc, long long n, float sqrt_a, flo
 /* ---- post-processing of the decoded video: 3x3x3 median over (t, y, x) with reflect padding
  * (pipelines/utils.py:46-63) and the uint8 frames save_video hands to the encoder (:70-73, truncation of v*255).
  * video [C,T,H,W] fp32 (device); filtered (nullable) same layout; frames (nullable) [T,H,W,C] uint8.
- * Written at the end of round 1 without GPU budget left: not yet run on hardware. */
+ * Bit-exact vs the reference-generated golden (tests/test_zz_post_gpu.py). */
 int vx_median3d_u8(const float* video, int C, int T, int H, int W, float* filtered, unsigned char* frames, void* stream);
 
 /* ---- conditioning prologue: im2col of a 3x3 conv (stride 1 or 2, pad 1, NHWC bf16) with an
  * optional SiLU on the gathered input; VKpsGuider's narrow conv -> SiLU chain (modules/v_kps_guider.py:35-45) runs as
- * im2col(SiLU(x)) + vx_gemm_bf16.  out [NB*Ho*Wo, 9*C], K order (tap, channel).  Not yet run on hardware. */
+ * im2col(SiLU(x)) + vx_gemm_bf16.  out [NB*Ho*Wo, 9*C], K order (tap, channel). */
 int vx_im2col3x3(const void* x, int NB, int H, int W, int C, int stride, int silu, void* out, void* stream);
-
-/* ---- bring-up probes used by tests/test_probe_gpu.py (descriptor / TMA layout conventions) */
-int vx_probe_umma(const void* a_img, int a_bytes, const void* b_img, int b_bytes, unsigned lboA, unsigned sboA,
-                  unsigned layA, unsigned lboB, unsigned sboB, unsigned layB, int a_mn, int b_mn, int N, int ksteps,
-                  int a_step, int b_step, float* out, void* stream);
-int vx_probe_umma_ts(const void* a_packed, int K, const void* b_img, int b_bytes, unsigned lboB, unsigned sboB,
-                     unsigned layB, int b_mn, int N, int b_step, float* out, void* stream);
-int vx_probe_tma(const void* base, int rank, const unsigned long long* dims, const unsigned long long* strides_bytes,
-                 const unsigned* box, int swizzle, const int* coords, int nbytes, void* out, void* stream);
 
 #ifdef __cplusplus
 }

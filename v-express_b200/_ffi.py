@@ -50,3 +50,19 @@ def stream_ptr():
 
 def require_sm100():
     check(lib().vx_require_sm100(), "vx_require_sm100")
+
+
+_WARNED = set()
+
+
+def note_compute_dtype(model_dtype, what):
+    """The kernels compute in bf16 with fp32 accumulation, whatever dtype the caller's modules hold.  The reference CLI
+    defaults to fp16 (inference.py:44,150-151): such a model is accepted -- weights are re-rounded to bf16 (same 16 bits,
+    3 fewer mantissa bits, no overflow risk), inputs / outputs are converted at the boundary -- but never silently."""
+    import warnings
+    import torch
+    if model_dtype != torch.bfloat16 and (what, model_dtype) not in _WARNED:
+        _WARNED.add((what, model_dtype))
+        warnings.warn(f"vexpress_b200: {what} holds {model_dtype} parameters; the sm_100a kernels compute in bfloat16 "
+                      f"(fp32 accumulation): weights are re-rounded to bf16, inputs/outputs converted at the boundary. "
+                      f"Use .to(torch.bfloat16) to make this explicit.", stacklevel=3)

@@ -654,19 +654,21 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// v3: many small independent CTAs instead of one big choreographed one.  Measured on B200 (profiles/tools/ubench.cu,
+// v3: small independent CTAs whose softmax warps never wait.  Measured on B200 (profiles/tools/ubench.cu,
 // profiles/r02_flash_notes.md): the hd = 40 attention is bound by the softmax instruction stream -- 16 ex2/clk/SM on the
-// MUFU pipe, ~14.5 elements/clk/SM for a whole LDTM -> row max -> fma/ex2/pack -> STTM warp iteration when the warps run
-// free of each other (2250 clk per 2 x 128 x 128 scores) -- while v2's 16 softmax warps advance in lock-step
-// (pair barriers for the split-row maxima, 256-thread P hand-offs, two tiles sharing one MUFU phase): every phase that is
-// not the exponential one is exposed and an iteration costs 3450 clk.  v3 removes every softmax-side rendezvous:
+// MUFU pipe, ~14 elements/clk/SM for a whole LDTM -> row max -> fma/ex2/pack -> STTM warp iteration when the warps run
+// free of each other (2300 clk per 2 x 128 x 128 scores) -- while v2's 16 softmax warps advance in lock-step (pair
+// barriers for the split-row maxima, 256-thread P hand-offs, two tiles sharing one MUFU phase): every phase that is not the
+// exponential one is exposed and an iteration costs 3450 clk.  A first v3 with a single S buffer and three CTAs per SM
+// showed the same convoy ACROSS CTAs (all resident CTAs sat in their softmax -> P.V -> S turnaround together: 2990 clk).
+// So the rule is: a softmax warp must always find its next S tile already computed.
 //   * one CTA = ONE 128-row query tile, 64 keys per step; 4 softmax warps (one per TMEM lane quadrant, 1 thread = 1 row =
 //     64 scores: no split rows, no max exchange, no named barriers), 1 TMA warp, 1 MMA warp;
-//   * tensor memory per CTA: S (64 fp32 columns) + O (hdp columns) = 112 columns at hd 40 -> 128 allocated, so THREE
-//     CTAs are resident per SM (2 for hd 80 / 128); P (bf16, 32 packed columns) overwrites the S columns the thread has
-//     just read and feeds P.V as a TS-MMA straight from tensor memory;
-//   * S is single-buffered: softmax(j) -> P.V(j) -> S(j+1) is a serial chain inside a CTA, and the two other resident
-//     CTAs (at unrelated phases: the hardware scheduler staggers them by construction) fill the SM meanwhile.
+//   * S is DOUBLE-buffered in tensor memory: S(j+1) = Q K_{j+1}^T is issued before softmax(j) starts, P.V(j) and S(j+2)
+//     are issued when the last of the four warps has stored P(j) -- by then every warp is already inside softmax(j+1),
+//     i.e. the tensor-core turnaround has a whole iteration of slack and never stalls a softmax warp;
+//   * P (bf16, 32 packed columns) overwrites the S columns the thread has just read and feeds P.V as a TS-MMA straight
+//     from tensor memory; tensor memory per CTA: 2 x 64 (S) + hdp (O) <= 256 columns -> two CTAs per SM.
 // Used when hd <= 128, Nq % 128 == 0 and Nk % 64 == 0.
 constexpr int kFa3Threads = 192;
 
@@ -686,7 +688,7 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
 }
 
 template <bool ONES, int PMASK, int MINB>
-__global__ void __maxnreg__(MINB == 3 ? 112 : 168)     // 3 (2) resident CTAs x 192 threads within the 64 K registers of an SM
+__global__ void __maxnreg__(MINB == 3 ? 112 : 168)     // MINB resident CTAs x 192 threads within the 64 K registers of an SM
 flash_attn3_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                    const __grid_constant__ CUtensorMap mapV, const Fa3Args p) {
   extern __shared__ uint8_t smem_raw[];
@@ -698,9 +700,9 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
   uint64_t* q_full = bars;
   uint64_t* kv_full = bars + 1;          // [<= 8]
   uint64_t* kv_empty = kv_full + 8;      // [8]
-  uint64_t* s_full = kv_empty + 8;
-  uint64_t* p_ready = s_full + 1;
-  uint64_t* pv_done = p_ready + 1;
+  uint64_t* s_full = kv_empty + 8;       // [2]
+  uint64_t* p_ready = s_full + 2;        // [2]
+  uint64_t* pv_done = p_ready + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -726,8 +728,10 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
       mbar_init(&kv_full[s], 1);
       mbar_init(&kv_empty[s], 1);
     }
-    mbar_init(s_full, 1);
-    mbar_init(p_ready, 128);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&s_full[s], 1);
+      mbar_init(&p_ready[s], 128);
+    }
     mbar_init(pv_done, 1);
     fence_barrier_init();
   }
@@ -740,7 +744,7 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_o = tmem_base + 64u;
+  const uint32_t tmem_o = tmem_base + 128u;     // S buffers at columns [0, 64) and [64, 128)
 
   if (warp == 4) {
     // ------------------------------------------------------------ TMA producer (warp-uniform loop, elected lane issues)
@@ -778,46 +782,49 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
     const uint64_t dq = make_smem_desc(smem_u32(sQ), 2048, 128, SWZ_NONE);
     const int ksteps = p.hdp / 16;
     mbar_wait(q_full, 0);
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int j = 0; j < T; ++j) {
-      mbar_wait(&kv_full[stage], phase);
+    // S(t) = Q K_t^T into S buffer t & 1.  Tensor-core operations of one CTA execute in issue order, so S(t) -- issued
+    // after P.V(t-2) -- overwrites that buffer only once P(t-2) has been consumed out of it.
+    auto issue_s = [&](int t) {
+      const int st = t % p.stages;
+      mbar_wait(&kv_full[st], (uint32_t)((t / p.stages) & 1));
       tc_fence_after();
-      // S(j) = Q K_j^T.  Tensor-core operations of one CTA execute in issue order, so this write of the S columns is
-      // ordered behind P.V(j-1), which read P out of the same columns.
-      const uint64_t dk = make_smem_desc(smem_u32(sK + stage * p.kv_bytes), 1024, 128, SWZ_NONE);
+      const uint64_t dk = make_smem_desc(smem_u32(sK + st * p.kv_bytes), 1024, 128, SWZ_NONE);
+      const uint32_t d_s = tmem_base + (uint32_t)((t & 1) * 64);
       if (leader) {
         for (int k = 0; k < ksteps; ++k)   // Q: +4096 B (= +256) per 16 dims; K: 2 chunks of 64 keys = +2048 B (= +128)
-          umma_ss(tmem_base, dq + (uint64_t)(k * 256), dk + (uint64_t)(k * 128), idesc_s, k ? 1u : 0u);
-        umma_commit(s_full);
+          umma_ss(d_s, dq + (uint64_t)(k * 256), dk + (uint64_t)(k * 128), idesc_s, k ? 1u : 0u);
+        umma_commit(&s_full[t & 1]);
       }
       __syncwarp();
-      mbar_wait(p_ready, (uint32_t)(j & 1));
+    };
+    issue_s(0);
+    if (T > 1) issue_s(1);
+    for (int j = 0; j < T; ++j) {
+      const int stage = j % p.stages;
+      mbar_wait(&p_ready[j & 1], (uint32_t)((j >> 1) & 1));
       tc_fence_after();
       const uint64_t dv = make_smem_desc(smem_u32(sV + stage * p.kv_bytes), 128, 1024, SWZ_NONE);
+      const uint32_t t_p = tmem_base + (uint32_t)((j & 1) * 64);
       if (leader) {
 #pragma unroll
         for (int k = 0; k < 4; ++k)   // A = P from tensor memory (8 packed columns per 16 keys); V: +256 B (= +16) per 16 keys
-          umma_ts(tmem_o, tmem_base + (uint32_t)(k * 8), dv + (uint64_t)(k * 16), idesc_o, (j | k) ? 1u : 0u);
+          umma_ts(tmem_o, t_p + (uint32_t)(k * 8), dv + (uint64_t)(k * 16), idesc_o, (j | k) ? 1u : 0u);
         umma_commit(&kv_empty[stage]);
         umma_commit(pv_done);
       }
       __syncwarp();
-      if (++stage == p.stages) {
-        stage = 0;
-        phase ^= 1;
-      }
+      if (j + 2 < T) issue_s(j + 2);
     }
   } else {
     // ------------------------------------------------------------ softmax: warp = TMEM lane quadrant, thread = query row
     const int row = warp * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
-    const uint32_t ts = tmem_base + lane_addr;
     const uint32_t to = tmem_o + lane_addr;
     float m_used = -INFINITY, l = 0.f;
     const float c = p.scale_log2;
     for (int j = 0; j < T; ++j) {
-      mbar_wait(s_full, (uint32_t)(j & 1));
+      const uint32_t ts = tmem_base + lane_addr + (uint32_t)((j & 1) * 64);
+      mbar_wait(&s_full[j & 1], (uint32_t)((j >> 1) & 1));
       tc_fence_after();
       uint32_t v[2][32];
       tmem_ld32(ts, v[0]);
@@ -876,7 +883,7 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
       tmem_st32(ts, pk);        // P(j): 64 keys = 32 packed columns over the S columns this thread has consumed
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(p_ready);
+      mbar_arrive(&p_ready[j & 1]);
     }
     mbar_wait(pv_done, (uint32_t)((T - 1) & 1));
     tc_fence_after();
@@ -1040,8 +1047,8 @@ extern "C" int vx_flash_attention(const void* q, long long ldq, const void* k, l
     a.out = (__nv_bfloat16*)out; a.ldo = ldo;
     a.q_bytes = 128 * hdp * 2;
     a.kv_bytes = 64 * hdp * 2;
-    a.tmem_cols = 64 + hdp <= 128 ? 128u : 256u;
-    const int ctas = a.tmem_cols == 128 ? 3 : 2;
+    a.tmem_cols = 256u;                       // 2 x 64 (S double buffer) + hdp (<= 128) columns
+    const int ctas = 2;
     const size_t budget = (size_t)(227 * 1024) / ctas - 1024;          // 1 KB per CTA is reserved by the hardware
     auto need3 = [&](int st) { return (size_t)a.q_bytes + (size_t)2 * st * a.kv_bytes + 256 + 128; };
     a.stages = env.v3_stages > 0 ? env.v3_stages : 6;
@@ -1062,19 +1069,19 @@ extern "C" int vx_flash_attention(const void* q, long long ldq, const void* k, l
     }
     static bool cfg3 = false;
     if (!cfg3) {
-      VX_CHECK_CUDA(cudaFuncSetAttribute(flash_attn3_kernel<true, 7, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-      VX_CHECK_CUDA(cudaFuncSetAttribute(flash_attn3_kernel<true, 3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-      VX_CHECK_CUDA(cudaFuncSetAttribute(flash_attn3_kernel<false, 7, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      VX_CHECK_CUDA(cudaFuncSetAttribute(flash_attn3_kernel<true, 7, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+      VX_CHECK_CUDA(cudaFuncSetAttribute(flash_attn3_kernel<true, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+      VX_CHECK_CUDA(cudaFuncSetAttribute(flash_attn3_kernel<true, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
       VX_CHECK_CUDA(cudaFuncSetAttribute(flash_attn3_kernel<false, 7, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
       cfg3 = true;
     }
     dim3 grid3(Nq / 128, heads, Bq);
     const bool ones = hdp > hd && !env.noones;
     auto st3 = (cudaStream_t)stream;
-    if (ctas == 2) flash_attn3_kernel<false, 7, 2><<<grid3, kFa3Threads, smem3, st3>>>(mQ, mK, mV, a);
-    else if (ones && env.poly == 4) flash_attn3_kernel<true, 3, 3><<<grid3, kFa3Threads, smem3, st3>>>(mQ, mK, mV, a);
-    else if (ones) flash_attn3_kernel<true, 7, 3><<<grid3, kFa3Threads, smem3, st3>>>(mQ, mK, mV, a);
-    else flash_attn3_kernel<false, 7, 3><<<grid3, kFa3Threads, smem3, st3>>>(mQ, mK, mV, a);
+    if (ones && env.poly == 4) flash_attn3_kernel<true, 3, 2><<<grid3, kFa3Threads, smem3, st3>>>(mQ, mK, mV, a);
+    else if (ones && env.poly == 2) flash_attn3_kernel<true, 1, 2><<<grid3, kFa3Threads, smem3, st3>>>(mQ, mK, mV, a);
+    else if (ones) flash_attn3_kernel<true, 7, 2><<<grid3, kFa3Threads, smem3, st3>>>(mQ, mK, mV, a);
+    else flash_attn3_kernel<false, 7, 2><<<grid3, kFa3Threads, smem3, st3>>>(mQ, mK, mV, a);
     VX_CHECK_CUDA(cudaGetLastError());
     return 0;
   }

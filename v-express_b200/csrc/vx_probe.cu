@@ -2,6 +2,7 @@
 // shared-memory images + descriptor fields, and dump what a TMA box load leaves in shared memory.
 // They pin the descriptor / layout conventions the production kernels rely on.
 #include "vx_host.h"
+#include "vx_bringup.h"
 #include "vx_ptx.cuh"
 
 namespace vx {

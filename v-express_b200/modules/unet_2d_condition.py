@@ -247,6 +247,7 @@ class RefNetEngine(UNetEngine):
         dev = model.device
         if dev.type != "cuda":
             raise RuntimeError("vexpress_b200: the model must live on a CUDA (sm_100a) device; there is no CPU path")
+        _ffi.note_compute_dtype(model.dtype, "UNet2DConditionModel")
         self.model = model
         self.dev = dev
         cfg = model.config

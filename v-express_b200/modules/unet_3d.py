@@ -347,6 +347,7 @@ class UNetEngine:
         dev = model.device
         if dev.type != "cuda":
             raise RuntimeError("vexpress_b200: the model must live on a CUDA (sm_100a) device; there is no CPU path")
+        _ffi.note_compute_dtype(model.dtype, "UNet3DConditionModel")
         self.model = model
         self.dev = dev
         cfg = model.config

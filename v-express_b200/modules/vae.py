@@ -148,6 +148,7 @@ class VaeDecoderEngine:
         _ffi.require_sm100()
         if model.device.type != "cuda":
             raise RuntimeError("vexpress_b200: the VAE must live on a CUDA (sm_100a) device; there is no CPU path")
+        _ffi.note_compute_dtype(model.dtype, "AutoencoderKL")
         self.model = model
         self.dev = model.device
         self.boc = tuple(model.config["block_out_channels"])
