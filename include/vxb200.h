@@ -137,6 +137,13 @@ int vx_ddim_step(void* latents, const float* acc, long long n, float sqrt_a, flo
  * Bit-exact vs the reference-generated golden (tests/test_zz_post_gpu.py). */
 int vx_median3d_u8(const float* video, int C, int T, int H, int W, float* filtered, unsigned char* frames, void* stream);
 
+/* ---- nearest-2x upsample folded into the following 3x3 convolution (reference modules/resnet.py:53-90 Upsample3D;
+ * diffusers Upsample2D in AutoencoderKL.decode): out = conv3x3(upsample2x(X)) computed as four 2x2 convolutions of X, one per
+ * output parity class, with the 3x3 weights pre-summed per class (ops.pack_upconv_weight): Wt [4*Cout, 4*C]; out is the
+ * NHWC [NB*2H*2W, ldc] upsampled image.  4/9 of the FLOPs, no 4x intermediate. */
+int vx_upconv3x3_bf16(const void* X, int NB, int H, int W, int C, const void* Wt, int Cout, const float* bias, void* out,
+                      long long ldc, int block_n, void* stream);
+
 /* ---- conditioning prologue: im2col of a 3x3 conv (stride 1 or 2, pad 1, NHWC bf16) with an
  * optional SiLU on the gathered input; VKpsGuider's narrow conv -> SiLU chain (modules/v_kps_guider.py:35-45) runs as
  * im2col(SiLU(x)) + vx_gemm_bf16.  out [NB*Ho*Wo, 9*C], K order (tap, channel). */

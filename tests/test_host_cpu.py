@@ -264,6 +264,11 @@ class _ShapeOps:
                 x, NB, H, W = a[:4]
                 assert x.shape[0] == NB * H * W
                 return torch.zeros(4 * x.shape[0], x.shape[1])
+            if op == "upconv3x3":
+                x, w4, bias = a[:3]
+                NB, H, W, C = x.shape
+                assert w4.shape[1] == 4 * C and w4.shape[0] % 4 == 0 and bias.shape == (w4.shape[0] // 4,), (x.shape, w4.shape)
+                return torch.zeros(NB * 4 * H * W, w4.shape[0] // 4)
             if op == "conv_out_tc":
                 x, NB, H, W = a[:4]
                 assert x.shape[0] == NB * H * W and a[6].shape[0] == NB and a[6].shape[2:] == (H, W)
@@ -370,7 +375,7 @@ def test_unet_and_refnet_forward_schedules_dry_run(monkeypatch):
     kps = torch.zeros(b * f * h * h, cfg["block_out_channels"][0], dtype=torch.bfloat16)
     out = eng.forward_frames(frames, 499, enc, kps, None, b, f)
     assert out.shape == (b * f, 4, h, h)
-    assert fake.calls.count("conv3x3") == 22 * 2 + 3 and fake.calls.count("flash_attention") == 32
+    assert fake.calls.count("conv3x3") == 22 * 2 and fake.calls.count("upconv3x3") == 3 and fake.calls.count("flash_attention") == 32
     assert fake.calls.count("temporal_attention") == 42 and fake.calls.count("smallkv_attention") == 16
     fake.calls.clear()
     ReferenceAttentionControl(net, mode="write", fusion_blocks="full", do_classifier_free_guidance=True)
@@ -515,6 +520,24 @@ class _EmuOps:
 
     def im2col_s2(self, x, NB, H, W, out=None):
         return self._ret(self.im2col3x3(x, NB, H, W, stride=2), out)
+
+    def upconv3x3(self, x, w4, bias, out=None, block_n=0):
+        """conv3x3(upsample2x(x)) from the parity-folded weights (ops.pack_upconv_weight), like vx_upconv3x3_bf16."""
+        import torch.nn.functional as F
+        NB, H, W, C = x.shape
+        Cout = w4.shape[0] // 4
+        xp = F.pad(x.float().permute(0, 3, 1, 2), (1, 1, 1, 1))
+        wv = w4.float().view(4, Cout, 4, C)
+        y = torch.zeros(NB, Cout, 2 * H, 2 * W)
+        for py in (0, 1):
+            for px in (0, 1):
+                acc = bias.view(1, -1, 1, 1).expand(NB, Cout, H, W).clone()
+                for a in (0, 1):
+                    for b in (0, 1):
+                        acc = acc + torch.einsum("nchw,oc->nohw", xp[:, :, py + a:py + a + H, px + b:px + b + W],
+                                                 wv[py * 2 + px][:, a * 2 + b, :])
+                y[:, :, py::2, px::2] = acc
+        return self._ret(y.permute(0, 2, 3, 1).reshape(NB * 4 * H * W, Cout).to(torch.bfloat16), out)
 
     def upsample2x(self, x, NB, H, W, out=None):
         C = x.shape[1]

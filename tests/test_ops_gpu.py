@@ -229,3 +229,22 @@ def test_cfg_overlap_ddim_matches_bf16_eager(ops):
     ref = a_p ** 0.5 * x0 + (1 - a_p) ** 0.5 * eps
     ops.ddim_step(lat, acc, float(a_t ** 0.5), float((1 - a_t) ** 0.5), float(a_p ** 0.5), float((1 - a_p) ** 0.5))
     assert torch.equal(lat, ref)
+
+
+@pytest.mark.parametrize("NB,H,W,C,Cout", [(2, 8, 8, 1280, 1280), (3, 16, 16, 128, 64), (2, 32, 32, 640, 640),
+                                           (1, 64, 64, 512, 512), (1, 128, 128, 64, 64), (2, 256, 256, 64, 32),
+                                           (5, 12, 12, 64, 96), (1, 8, 24, 128, 128)])
+def test_upconv3x3_equals_upsample_then_conv(ops, NB, H, W, C, Cout):
+    """Nearest-2x upsample folded into the 3x3 conv (four parity-class 2x2 convolutions) vs torch on the same bf16 inputs.
+    Tolerance: one extra bf16 rounding of the pre-summed weights (2^-9 relative) on top of the output rounding."""
+    g = _gen(NB * H + C + Cout)
+    x = torch.randn(NB, H, W, C, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(Cout, C, 3, 3, device="cuda", generator=g) / (9 * C) ** 0.5).bfloat16()
+    b = torch.randn(Cout, device="cuda", generator=g)
+    out = ops.upconv3x3(x, ops.pack_upconv_weight(w), b)
+    up = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest")
+    ref = F.conv2d(up, w.float(), b, padding=1).permute(0, 2, 3, 1).reshape(-1, Cout)
+    assert out.shape == ref.shape
+    err = _rel(out, ref)
+    print(f"upconv NB={NB} {H}x{W} C={C}->{Cout} rel={err:.3e}")
+    assert err < 5e-3, err

@@ -35,7 +35,8 @@ struct GemmArgs {
   int M, N;        // N = number of accumulator columns overall (2x the output width in GEGLU mode)
   int kblocks1;    // 64-wide K blocks taken from A (per tap for conv)
   int kblocks2;    // ... then from A2 (plain mode only)
-  int taps;        // 1 = plain GEMM, 9 = 3x3 conv
+  int taps;        // 1 = plain GEMM, 9 = 3x3 conv, 4 = nearest-2x upsample folded into the 3x3 conv (see `ups`)
+  int ups;         // 1: output parity classes (py, px) of conv3x3(upsample2x(x)) as four 2x2 convolutions on x (vx_upconv3x3_bf16)
   int block_n;     // UMMA N (multiple of 32, <= 256)
   int stages;
   int nbuf;        // staging tiles (2 when shared memory allows: TMA store/residual latency fully hidden)
@@ -61,6 +62,12 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* s
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                    reinterpret_cast<uint64_t>(m)),
                "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
                : "memory");
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
@@ -171,7 +178,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   const int lane = threadIdx.x & 31;
   const int total_kb = p.taps * p.kblocks1 + p.kblocks2;
   // work items are (row-tile group of CG tiles, column tile); every CTA of a pair walks the same sequence
-  const int num_tiles = ((p.tiles_m + CG - 1) / CG) * p.tiles_n;
+  const int tiles_per_par = ((p.tiles_m + CG - 1) / CG) * p.tiles_n;
+  const int num_tiles = tiles_per_par * (p.ups ? 4 : 1);   // ups: (parity, row-tile group, column tile), parity slowest
   const int first_item = blockIdx.x / CG, item_stride = gridDim.x / CG;
 
   if (warp == 0 && lane == 0) {
@@ -179,7 +187,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     tma_prefetch_desc(&mapB);
     if (p.kblocks2) tma_prefetch_desc(&mapA2);
     if (!p.out_f32) tma_prefetch_desc(&mapC);
-    if (p.has_residual) tma_prefetch_desc(&mapR);
+    if (p.has_residual || p.ups) tma_prefetch_desc(&mapR);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -214,10 +222,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     int stage = 0;
     uint32_t phase = 0;
     for (int t = first_item; t < num_tiles; t += item_stride) {
-      const int tile_n = t % p.tiles_n, tile_m = (t / p.tiles_n) * CG + (int)cta_rank;
+      const int par = t / tiles_per_par, tt = t - par * tiles_per_par;
+      const int tile_n = tt % p.tiles_n, tile_m = (tt / p.tiles_n) * CG + (int)cta_rank;
       int n0 = 0, y0 = 0, x0 = 0;
       const long long m0 = (long long)tile_m * p.rows_valid;
-      if (p.taps == 9) {
+      if (p.taps != 1) {
         const long long hw = (long long)p.H * p.W;
         n0 = (int)(m0 / hw);
         const int rem = (int)(m0 % hw);
@@ -226,19 +235,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       }
       // the pair's loads all complete on the LEADER's full barrier (it alone waits for the operands)
       const uint32_t tx_bytes = (uint32_t)(CG * (p.rows_valid * kBlockK * 2 + b_bytes));
-      const int b_row = tile_n * p.block_n + (int)cta_rank * (p.block_n / CG);
+      const int b_row = par * p.N + tile_n * p.block_n + (int)cta_rank * (p.block_n / CG);
       for (int kb = 0; kb < total_kb; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * stage_bytes;
         uint8_t* sb = sa + a_bytes;
-        const int tap = p.taps == 9 ? kb / p.kblocks1 : 0;
+        const int tap = p.taps != 1 ? kb / p.kblocks1 : 0;
         const int cb = kb - tap * p.kblocks1;
-        const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+        // 3x3: taps (dy, dx) in {-1, 0, 1}^2.  Folded upsample: output pixel (2i + py, 2j + px) reads the 2x2 input
+        // neighbourhood rows i + py - 1 + {0, 1}, columns j + px - 1 + {0, 1} (weights pre-summed per parity on the host).
+        const int dy = p.ups ? (tap >> 1) + (par >> 1) - 1 : tap / 3 - 1;
+        const int dx = p.ups ? (tap & 1) + (par & 1) - 1 : tap % 3 - 1;
         if (leader) {
           if (CG == 2) {
             const uint32_t fb = mapa_rank(smem_u32(&full_bar[stage]), 0);
             if (pair_leader) mbar_expect_tx(&full_bar[stage], tx_bytes);
-            if (p.taps == 9) {
+            if (p.taps != 1) {
               tma_load_4d_cg2(sa, &mapA, fb, cb * kBlockK, x0 + dx, y0 + dy, n0);
             } else if (kb < p.kblocks1) {
               tma_load_2d_cg2(sa, &mapA, fb, kb * kBlockK, (int)m0);
@@ -248,7 +260,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             tma_load_2d_cg2(sb, &mapB, fb, kb * kBlockK, b_row);
           } else {
             mbar_expect_tx(&full_bar[stage], tx_bytes);
-            if (p.taps == 9) {
+            if (p.taps != 1) {
               tma_load_4d(sa, &mapA, &full_bar[stage], cb * kBlockK, x0 + dx, y0 + dy, n0);
             } else if (kb < p.kblocks1) {
               tma_load_2d(sa, &mapA, &full_bar[stage], kb * kBlockK, (int)m0);
@@ -309,7 +321,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     if (lane == 0 && !p.out_f32) {   // few TMA ops per tile: the single-lane form is good enough here
       const uint32_t res_bytes = (uint32_t)(p.rows_valid * out_cols * 2);
       auto arm = [&](int t, int b) {  // make staging tile b usable for output tile t
-        if (p.has_residual) {
+        if (p.has_residual) {   // (never with ups: the upsampler convs have no residual)
           const int tn_ = t % p.tiles_n, tm_ = (t / p.tiles_n) * CG + (int)cta_rank;
           mbar_expect_tx(&c_ready[b], res_bytes);
           for (int pn = 0; pn < npanels; ++pn)
@@ -324,11 +336,24 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       int it = 0;
       for (int t = first_item; t < num_tiles; t += item_stride, ++it) {
         const int b = it % p.nbuf;
-        const int tile_n = t % p.tiles_n, tile_m = (t / p.tiles_n) * CG + (int)cta_rank;
+        const int par = t / tiles_per_par, tt = t - par * tiles_per_par;
+        const int tile_n = tt % p.tiles_n, tile_m = (tt / p.tiles_n) * CG + (int)cta_rank;
         mbar_wait(&staged[b], (uint32_t)((it / p.nbuf) & 1));
-        for (int pn = 0; pn < npanels; ++pn)
-          tma_store_2d(&mapC, sC + b * buf_bytes + pn * kPanelBytes, tile_n * out_cols + pn * kPanelCols,
-                       tile_m * p.rows_valid);
+        if (p.ups) {
+          // rows of the tile = low-resolution pixels (n, i, j); they land on (n, 2i + py, 2j + px): 5-D map (c, j, i, n, py)
+          // per px (mapC: px = 0, mapR: px = 1)
+          const long long m0 = (long long)tile_m * p.rows_valid, hw = (long long)p.H * p.W;
+          const int n0 = (int)(m0 / hw), rem = (int)(m0 % hw);
+          const CUtensorMap* mo = (par & 1) ? &mapR : &mapC;
+          if (m0 < p.M)
+            for (int pn = 0; pn < npanels; ++pn)
+              tma_store_5d(mo, sC + b * buf_bytes + pn * kPanelBytes, tile_n * out_cols + pn * kPanelCols, rem % p.W, rem / p.W,
+                           n0, par >> 1);
+        } else {
+          for (int pn = 0; pn < npanels; ++pn)
+            tma_store_2d(&mapC, sC + b * buf_bytes + pn * kPanelBytes, tile_n * out_cols + pn * kPanelCols,
+                         tile_m * p.rows_valid);
+        }
         tma_store_commit();
         const int tnext = t + p.nbuf * item_stride;
         if (tnext < num_tiles) {
@@ -351,7 +376,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     const uint32_t te_leader0 = CG == 2 ? mapa_rank(smem_u32(&tmem_empty[0]), 0) : 0u;
     const uint32_t te_leader1 = CG == 2 ? mapa_rank(smem_u32(&tmem_empty[1]), 0) : 0u;
     for (int t = first_item; t < num_tiles; t += item_stride, ++it) {
-      const int tile_n = t % p.tiles_n, tile_m = (t / p.tiles_n) * CG + (int)cta_rank;
+      const int tt = t % tiles_per_par;
+      const int tile_n = tt % p.tiles_n, tile_m = (tt / p.tiles_n) * CG + (int)cta_rank;
       const int as = it & 1;
       const long long m = (long long)tile_m * p.rows_valid + row;
       const bool row_ok = row < p.rows_valid && m < p.M;
@@ -613,13 +639,14 @@ static int launch(const CUtensorMap& mA, const CUtensorMap& mA2, const CUtensorM
     VX_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
+  const int npar = a.ups ? 4 : 1;
   if (cg == 1) {
-    const int tiles = a.tiles_m * a.tiles_n;
+    const int tiles = a.tiles_m * a.tiles_n * npar;
     const int grid = tiles < num_sms() ? tiles : num_sms();
     if (a.ln_stats) gemm_tcgen05_kernel<1, true><<<grid, kThreads, smem, st>>>(mA, mA2, mB, mR, mC, a);
     else gemm_tcgen05_kernel<1, false><<<grid, kThreads, smem, st>>>(mA, mA2, mB, mR, mC, a);
   } else {
-    const int items = ((a.tiles_m + 1) / 2) * a.tiles_n;
+    const int items = ((a.tiles_m + 1) / 2) * a.tiles_n * npar;
     const int pairs = items < num_pairs() ? items : num_pairs();
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(2 * pairs);
@@ -813,4 +840,84 @@ extern "C" int vx_conv3x3_bf16(const void* X, int NB, int H, int W, int C, const
   a.bias = bias; a.bias2 = bias2; a.bias2_div = bias2_div > 0 ? bias2_div : 1; a.scale = scale;
   a.out32 = (float*)out; a.ldc = ldc;
   return launch(mA, mA, mB, mR, mC, a, (cudaStream_t)stream);
+}
+
+// conv3x3(nearest_upsample_2x(X)) without the upsampled tensor (reference modules/resnet.py:53-90 Upsample3D,
+// diffusers Upsample2D in the VAE decoder): output pixel (2i + py, 2j + px) only ever sees the 2x2 input neighbourhood
+// rows {i + py - 1, i + py}, columns {j + px - 1, j + px}, so each of the four output parity classes is a 2x2 convolution of
+// X with the 3x3 weights summed over the taps that land on the same input pixel (host: vexpress_b200.ops.pack_upconv_weight)
+// -- 4/9 of the FLOPs, and the 4x tensor is never written or read.
+// X: NHWC bf16 [NB, H, W, C];  Wt: [4 * Cout, 4 * C] = parity-major (py, px) blocks, K index = (a * 2 + b) * C + c;
+// out: [NB * 2H * 2W, ldc] (NHWC of the upsampled image).
+extern "C" int vx_upconv3x3_bf16(const void* X, int NB, int H, int W, int C, const void* Wt, int Cout, const float* bias,
+                                 void* out, long long ldc, int block_n, void* stream) {
+  VX_REQUIRE(C % kBlockK == 0 && Cout % 32 == 0, "vx_upconv3x3_bf16: C=%d must be %%64, Cout=%d %%32", C, Cout);
+  VX_REQUIRE(ldc % 8 == 0, "vx_upconv3x3_bf16: ldc must be %%8");
+  int wbox, hbox = 1, nbox = 1;
+  if (W >= kBlockM) {
+    VX_REQUIRE(W % kBlockM == 0, "vx_upconv3x3_bf16: W=%d must be a multiple of 128 when >= 128", W);
+    wbox = kBlockM;
+  } else {
+    wbox = W;
+    hbox = kBlockM / W;
+    if (hbox > H) {
+      hbox = H;
+      nbox = kBlockM / (W * H);
+      if (nbox > NB) nbox = NB;
+      if (nbox < 1) nbox = 1;
+      while (NB % nbox) --nbox;
+    } else {
+      while (H % hbox) --hbox;
+    }
+  }
+  const int rows_valid = wbox * hbox * nbox;
+  const long long M = (long long)NB * H * W;
+  VX_REQUIRE(M % rows_valid == 0, "vx_upconv3x3_bf16: NB*H*W=%lld not tileable by %d", M, rows_valid);
+  const long long tiles_m = M / rows_valid;
+  const int total_kb = 4 * (C / kBlockK);
+  if (block_n <= 0) block_n = env_int("VX_GEMM_BN", 0);
+  if (block_n <= 0) block_n = pick_block_n(tiles_m * 4, Cout, 32, 0, total_kb);
+  VX_REQUIRE(block_n % 32 == 0 && block_n >= 32 && block_n <= 256 && Cout % block_n == 0,
+             "vx_upconv3x3_bf16: block_n=%d invalid for Cout=%d", block_n, Cout);
+  const bool pair = pair_ok(0, block_n, tiles_m, total_kb);
+  CUtensorMap mA, mB, mC0, mC1;
+  {
+    uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)NB};
+    uint64_t str[3] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
+    uint32_t box[4] = {kBlockK, (uint32_t)wbox, (uint32_t)hbox, (uint32_t)nbox};
+    if (make_tmap_bf16(&mA, X, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)4 * C, (uint64_t)4 * Cout};
+    uint64_t str[1] = {(uint64_t)4 * C * 2};
+    uint32_t box[2] = {kBlockK, (uint32_t)(pair ? block_n / 2 : block_n)};
+    if (make_tmap_bf16(&mB, Wt, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+  }
+  for (int px = 0; px < 2; ++px) {
+    // (c, j, i, n, py) view of the [NB, 2H, 2W, ldc] output for one column parity
+    uint64_t dims[5] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)NB, 2};
+    uint64_t str[4] = {(uint64_t)2 * ldc * 2, (uint64_t)2 * (2 * W) * ldc * 2, (uint64_t)(2 * H) * (2 * W) * ldc * 2,
+                       (uint64_t)(2 * W) * ldc * 2};
+    uint32_t box[5] = {kPanelCols, (uint32_t)wbox, (uint32_t)hbox, (uint32_t)nbox, 1};
+    if (make_tmap_bf16(px ? &mC1 : &mC0, (const __nv_bfloat16*)out + (long long)px * ldc, 5, dims, str, box,
+                       CU_TENSOR_MAP_SWIZZLE_64B))
+      return 1;
+  }
+  GemmArgs a{};
+  a.M = (int)M; a.N = Cout;
+  a.kblocks1 = C / kBlockK;
+  a.kblocks2 = 0;
+  a.taps = 4;
+  a.ups = 1;
+  a.block_n = block_n;
+  a.rows_valid = rows_valid;
+  a.W = W; a.H = H;
+  a.tiles_m = (int)tiles_m;
+  a.tiles_n = Cout / block_n;
+  a.geglu = 0;
+  a.has_residual = 0;
+  a.out_f32 = 0;
+  a.bias = bias; a.bias2 = nullptr; a.bias2_div = 1; a.scale = 1.0f;
+  a.out32 = (float*)out; a.ldc = ldc;
+  return launch(mA, mA, mB, mC1, mC0, a, (cudaStream_t)stream);
 }

@@ -321,9 +321,8 @@ class RefNetEngine(UNetEngine):
                 if i > 0:
                     x = self._transformer_write(f"{p}.attentions.{j}", x, NB, h_ * w_, enc_flat)
             if i < 3:
-                u = ops.upsample2x(x, NB, h_, w_)
+                x = ops.upconv3x3(x.view(NB, h_, w_, -1), W[f"{p}.upsamplers.0.conv.weight"], W[f"{p}.upsamplers.0.conv.bias"])
                 h_, w_ = 2 * h_, 2 * w_
-                x = ops.conv3x3(u.view(NB, h_, w_, -1), W[f"{p}.upsamplers.0.conv.weight"], W[f"{p}.upsamplers.0.conv.bias"])
         # no conv_norm_out / activation: the reference resets conv_norm_out to None (unet_2d_condition.py:650,1301-1304)
         out = torch.empty((NB, self.model.config["out_channels"], H, Wd), device=self.dev, dtype=BF16)
         ops.conv_out_tc(x, NB, H, Wd, W["conv_out.packed_w"], W["conv_out.packed_b"], out)

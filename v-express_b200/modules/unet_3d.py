@@ -394,6 +394,9 @@ class UNetEngine:
                 off += v.shape[0]
                 temb_w.append(self._bf(v))
                 temb_b.append(W[p + ".bias"])
+            elif v.dim() == 4 and v.shape[-1] == 3 and ".upsamplers." in k:
+                # nearest-2x upsample folded into the conv: four parity-class 2x2 kernels (ops.pack_upconv_weight)
+                W[k] = ops.pack_upconv_weight(self._bf(v))
             elif v.dim() == 4 and v.shape[-1] == 3:
                 W[k] = ops.pack_conv3x3_weight(self._bf(v))
             elif v.dim() == 4:
@@ -649,9 +652,9 @@ class UNetEngine:
                 x = self._motion(f"{p}.motion_modules.{j}", x, NB, h_ * w_, b, f)
                 tap(f"{p}.motion_modules.{j}", x, h_, w_)
             if i < 3:
-                u = ops.upsample2x(x, NB, h_, w_)
+                # Upsample3D (modules/resnet.py:53-90): nearest x2 + conv3x3, without the 4x intermediate
+                x = ops.upconv3x3(x.view(NB, h_, w_, -1), W[f"{p}.upsamplers.0.conv.weight"], W[f"{p}.upsamplers.0.conv.bias"])
                 h_, w_ = 2 * h_, 2 * w_
-                x = ops.conv3x3(u.view(NB, h_, w_, -1), W[f"{p}.upsamplers.0.conv.weight"], W[f"{p}.upsamplers.0.conv.bias"])
                 tap(f"{p}.upsamplers.0", x, h_, w_)
         x = ops.groupnorm(x, NB, h_ * w_, W["conv_norm_out.weight"], W["conv_norm_out.bias"], self.eps, True, groups=self.groups)
         out = torch.empty((NB, self.model.config["out_channels"], H, Wd), device=self.dev, dtype=BF16)

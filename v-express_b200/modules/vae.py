@@ -169,6 +169,8 @@ class VaeDecoderEngine:
                     v.to(device=dev, dtype=BF16), self.W[p + ".bias"])
             elif p == "post_quant_conv":
                 self.W[k] = v.to(device=dev, dtype=BF16).float().reshape(v.shape[0], v.shape[1]).contiguous()
+            elif v.dim() == 4 and v.shape[-1] == 3 and ".upsamplers." in k:
+                self.W[k] = ops.pack_upconv_weight(v.to(device=dev, dtype=BF16))    # upsample folded into the conv
             elif v.dim() == 4 and v.shape[-1] == 3:
                 self.W[k] = ops.pack_conv3x3_weight(v.to(device=dev, dtype=BF16))
             elif v.dim() == 4:
@@ -223,10 +225,9 @@ class VaeDecoderEngine:
             for j in range(self.layers + 1):
                 x = self._res(f"{d}.up_blocks.{i}.resnets.{j}", x, NB, H, Wd)
             if i < nb - 1:
-                u = ops.upsample2x(x, NB, H, Wd)
+                x = ops.upconv3x3(x.view(NB, H, Wd, -1), W[f"{d}.up_blocks.{i}.upsamplers.0.conv.weight"],
+                                  W[f"{d}.up_blocks.{i}.upsamplers.0.conv.bias"])
                 H, Wd = 2 * H, 2 * Wd
-                x = ops.conv3x3(u.view(NB, H, Wd, -1), W[f"{d}.up_blocks.{i}.upsamplers.0.conv.weight"],
-                                W[f"{d}.up_blocks.{i}.upsamplers.0.conv.bias"])
         x = ops.groupnorm(x, NB, H * Wd, W[d + ".conv_norm_out.weight"], W[d + ".conv_norm_out.bias"], 1e-6, True)
         if out is None:
             out = torch.empty((NB, self.model.config["out_channels"], H, Wd), device=self.dev, dtype=out_dtype)

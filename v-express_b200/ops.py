@@ -136,6 +136,42 @@ def conv3x3(x, w, bias=None, *, bias2=None, bias2_div=1, scale=1.0, residual=Non
     return out
 
 
+def pack_upconv_weight(w):
+    """(Cout, Cin, 3, 3) conv weight of an `nearest-2x upsample -> conv3x3` pair -> [4*Cout, 4*Cin] bf16 for
+    vx_upconv3x3_bf16: block (py, px) holds the 2x2 kernel seen by output pixels (2i+py, 2j+px); tap a (b) of that kernel
+    reads input row i + py - 1 + a (column j + px - 1 + b) and is the fp32 sum of the 3x3 rows (columns) that fall on it:
+    py = 0: a=0 <- ky {0}, a=1 <- ky {1,2};  py = 1: a=0 <- ky {0,1}, a=1 <- ky {2}.  K order (a, b, cin)."""
+    groups = {0: ((0,), (1, 2)), 1: ((0, 1), (2,))}
+    wf = w.float()
+    blocks = []
+    for py in (0, 1):
+        for px in (0, 1):
+            taps = []
+            for a in (0, 1):
+                for b in (0, 1):
+                    acc = 0
+                    for ky in groups[py][a]:
+                        for kx in groups[px][b]:
+                            acc = acc + wf[:, :, ky, kx]
+                    taps.append(acc)                                  # (Cout, Cin)
+            blocks.append(torch.stack(taps, 1).reshape(w.shape[0], -1))   # (Cout, 4*Cin), K = (tap, cin)
+    return torch.cat(blocks, 0).to(BF16).contiguous()
+
+
+def upconv3x3(x, w4, bias, out=None, block_n=0):
+    """x: NHWC bf16 [NB,H,W,C]; w4 from pack_upconv_weight; returns conv3x3(upsample2x(x)) as [NB*2H*2W, Cout]."""
+    _chk_bf16(x, w4, out)
+    assert x.is_contiguous()
+    NB, H, W, C = x.shape
+    Cout = w4.shape[0] // 4
+    assert w4.shape[1] == 4 * C
+    if out is None:
+        out = torch.empty((NB * 4 * H * W, Cout), device=x.device, dtype=BF16)
+    check(_ffi.lib().vx_upconv3x3_bf16(ptr(x), c_int(NB), c_int(H), c_int(W), c_int(C), ptr(w4), c_int(Cout), ptr(bias),
+                                       ptr(out), c_ll(out.stride(0)), c_int(block_n), stream_ptr()), "vx_upconv3x3_bf16")
+    return out
+
+
 def pack_conv3x3_weight(w):
     """(Cout, Cin, 3, 3) -> [Cout, (ky kx cin)] bf16, the K order the implicit-GEMM producer walks."""
     co, ci, kh, kw = w.shape
