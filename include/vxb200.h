@@ -80,6 +80,14 @@ int vx_groupnorm_stats(const void* x1, long long ld1, int C1, const void* x2, lo
 int vx_groupnorm_apply(const void* x1, long long ld1, int C1, const void* x2, long long ld2, int C2, int NB, int HW,
                        int G, int S, const float* partial, const float* gamma, const float* beta, float eps,
                        int silu, void* out, long long ldo, void* stream);
+/* Number of GroupNorm CTAs (for C channels) resident at once on the device: NB * S must not exceed it for the fused kernel. */
+int vx_groupnorm_capacity(int C);
+/* Both passes in ONE launch behind a per-frame rendezvous (the second read of a frame is served by the L2 at UNet sizes).
+ * counters: int[2*NB], zeroed once by the caller (the kernel recycles them).  Returns 2 without launching when NB*S CTAs
+ * cannot be co-resident: use the two-kernel pair then.  Results are bit-identical to vx_groupnorm_stats + _apply. */
+int vx_groupnorm_fused(const void* x1, long long ld1, int C1, const void* x2, long long ld2, int C2, int NB, int HW, int G,
+                       int S, float* partial, int* counters, const float* gamma, const float* beta, float eps, int silu,
+                       void* out, long long ldo, void* stream);
 
 /* ---- LayerNorm over C, optional + pe[(row / rows_per_frame) % pe_frames] (temporal positional encoding).
  * Replaces nn.LayerNorm (modules/attention.py:329-333; modules/motion_module.py:228,234) and

@@ -248,3 +248,27 @@ def test_upconv3x3_equals_upsample_then_conv(ops, NB, H, W, C, Cout):
     err = _rel(out, ref)
     print(f"upconv NB={NB} {H}x{W} C={C}->{Cout} rel={err:.3e}")
     assert err < 5e-3, err
+
+
+@pytest.mark.parametrize("NB,HW,C1,C2,silu", [(32, 4096, 320, 0, True), (32, 1024, 640, 320, True), (32, 64, 1280, 1280, True),
+                                              (16, 16384, 512, 0, False), (3, 9216, 320, 0, True), (1, 256, 64, 0, False)])
+def test_groupnorm_one_launch_equals_two_kernel_pair(ops, NB, HW, C1, C2, silu):
+    """The fused (per-frame rendezvous) GroupNorm merges the same partial statistics in the same order as the
+    statistics + apply pair: bit-identical, launch after launch (the rendezvous counters recycle themselves)."""
+    g = _gen(NB + HW + C1)
+    x1 = (torch.randn(NB * HW, C1, device="cuda", generator=g) * 2 + 0.7).bfloat16()
+    x2 = (torch.randn(NB * HW, C2, device="cuda", generator=g) - 0.3).bfloat16() if C2 else None
+    C = C1 + C2
+    gamma = 1 + 0.1 * torch.randn(C, device="cuda", generator=g)
+    beta = 0.1 * torch.randn(C, device="cuda", generator=g)
+    was = ops._GN_FUSED
+    try:
+        ops._GN_FUSED = False
+        ref = ops.groupnorm(x1, NB, HW, gamma, beta, 1e-5, silu, x2=x2)
+        ops._GN_FUSED = True
+        outs = [ops.groupnorm(x1, NB, HW, gamma, beta, 1e-5, silu, x2=x2) for _ in range(3)]
+        torch.cuda.synchronize()
+    finally:
+        ops._GN_FUSED = was
+    for o in outs:
+        assert torch.equal(o, ref)

@@ -39,11 +39,10 @@ struct GnStatsArgs {
   float* partial;
 };
 
-__global__ void gn_stats_kernel(const GnStatsArgs p) {
-  extern __shared__ float sm[];  // [R][C] sums, [R][C] sumsq
+__device__ __forceinline__ void gn_stats_body(const GnStatsArgs& p, float* sm, const int n, const int s) {
+  // sm: [R][C] sums, [R][C] sumsq
   const int C = p.C1 + p.C2;
   const int V = C / 8;
-  const int n = blockIdx.y, s = blockIdx.x;
   const int v = threadIdx.x % V, r = threadIdx.x / V;
   const int chunk = (p.HW + p.S - 1) / p.S;
   const int p0 = s * chunk;
@@ -92,6 +91,11 @@ __global__ void gn_stats_kernel(const GnStatsArgs p) {
   }
 }
 
+__global__ void gn_stats_kernel(const GnStatsArgs p) {
+  extern __shared__ float sm[];
+  gn_stats_body(p, sm, blockIdx.y, blockIdx.x);
+}
+
 // ------------------------------------------------------------------ GroupNorm finalise + apply (+SiLU)
 struct GnApplyArgs {
   const __nv_bfloat16* x1; long long ld1; int C1;
@@ -104,14 +108,16 @@ struct GnApplyArgs {
   int chunk;  // pixels per CTA
 };
 
-__global__ void gn_apply_kernel(const GnApplyArgs p) {
-  extern __shared__ float sm[];  // scale[C], shift[C], mean[G], rstd[G]
+// `depart` (fused kernel only): called by every thread once the partial statistics of the frame have been merged, i.e.
+// when this CTA no longer depends on its peers.
+template <typename Depart>
+__device__ __forceinline__ void gn_apply_body(const GnApplyArgs& p, float* sm, const int n, const int chunk_idx, Depart depart) {
+  // sm: scale[C], shift[C], mean[G], rstd[G]
   const int C = p.C1 + p.C2;
   float* scale = sm;
   float* shift = sm + C;
   float* gmean = sm + 2 * C;
   float* grstd = gmean + p.G;
-  const int n = blockIdx.y;
   {
     // Chan et al. parallel-variance merge of the S partials of every group: one warp per group, lane s holds partial
     // s (and s + 32), then a fixed shuffle-down tree -- the same order in every CTA and every run (deterministic).
@@ -121,7 +127,7 @@ __global__ void gn_apply_kernel(const GnApplyArgs p) {
         float cnt = 0.f, mean = 0.f, m2 = 0.f;
         for (int s = lane; s < p.S; s += 32) {
           const float* q = p.partial + ((long long)(n * p.S + s) * p.G + g) * 3;
-          const float cb = q[0], mb = q[1], qb = q[2];
+          const float cb = __ldcg(q), mb = __ldcg(q + 1), qb = __ldcg(q + 2);   // written by other CTAs: bypass L1
           if (cb > 0.f) {
             const float tot = cnt + cb, delta = mb - mean;
             mean += delta * (cb / tot);
@@ -149,6 +155,7 @@ __global__ void gn_apply_kernel(const GnApplyArgs p) {
     }
   }
   __syncthreads();
+  depart();
   const int cpg = C / p.G;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const int g = c / cpg;
@@ -158,7 +165,7 @@ __global__ void gn_apply_kernel(const GnApplyArgs p) {
   }
   __syncthreads();
   const int V = C / 8;
-  const int p0 = blockIdx.x * p.chunk;
+  const int p0 = chunk_idx * p.chunk;
   const int p1 = min(p.HW, p0 + p.chunk);
   // thread = (channel vector v, pixel lane r): scale/shift of its 8 channels live in registers
   const int R = blockDim.x / V;
@@ -193,6 +200,51 @@ __global__ void gn_apply_kernel(const GnApplyArgs p) {
     }
     store8(dst + px * p.ldo, f);
   }
+}
+
+__global__ void gn_apply_kernel(const GnApplyArgs p) {
+  extern __shared__ float sm[];
+  gn_apply_body(p, sm, blockIdx.y, blockIdx.x, [] {});
+}
+
+// ------------------------------------------------------------------ GroupNorm in ONE launch
+// Statistics and apply of the two-kernel pair above fused behind a per-frame rendezvous: grid (S, NB), every CTA writes
+// the partial statistics of its pixel chunk, arrives on the frame's counter, waits until all S chunks of the frame have
+// arrived, merges the S partials (same fixed order as gn_apply_kernel: bit-identical results) and normalises the SAME
+// chunk it has just read -- at the UNet's sizes (<= 84 MB per tensor) that second read is served by the 126 MB L2 instead
+// of HBM, and one launch latency disappears.  The host only launches it when all NB * S CTAs are co-resident (occupancy
+// query), which is what makes the spin-wait safe.  counters: int[2 * NB] = {arrived, departed} per frame, zero before the
+// first launch; the last CTA to leave a frame resets both, so the buffer is reusable launch after launch (and under CUDA
+// graph replay) without a memset.
+struct GnFusedArgs {
+  GnStatsArgs st;
+  GnApplyArgs ap;
+  int* counters;
+};
+
+__global__ void gn_fused_kernel(const GnFusedArgs p) {
+  extern __shared__ float sm[];
+  const int n = blockIdx.y, s = blockIdx.x;
+  gn_stats_body(p.st, sm, n, s);
+  int* arrived = p.counters + 2 * n;
+  int* departed = arrived + 1;
+  __threadfence();                      // partial statistics visible device-wide before the arrival
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    atomicAdd(arrived, 1);
+    while (*reinterpret_cast<volatile int*>(arrived) < p.st.S) __nanosleep(64);
+    __threadfence();
+  }
+  __syncthreads();
+  gn_apply_body(p.ap, sm, n, s, [&] {
+    if (threadIdx.x == 0) {
+      if (atomicAdd(departed, 1) == p.st.S - 1) {   // every CTA of the frame has read the counter: safe to recycle
+        *reinterpret_cast<volatile int*>(arrived) = 0;
+        *reinterpret_cast<volatile int*>(departed) = 0;
+        __threadfence();
+      }
+    }
+  });
 }
 
 // ------------------------------------------------------------------ LayerNorm (+PE)
@@ -550,6 +602,61 @@ extern "C" int vx_groupnorm_apply(const void* x1, long long ld1, int C1, const v
   int Rr;
   const int threads = gn_block(C, &Rr);
   gn_apply_kernel<<<dim3((HW + chunk - 1) / chunk, NB), threads, smem, (cudaStream_t)stream>>>(a);
+  VX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// CTAs of the GroupNorm kernels that are resident at once on the whole device for C channels (occupancy query): the host
+// sizes S with it so that NB * S CTAs form exactly one wave -- required by the rendezvous of the fused kernel, and what
+// keeps the two-kernel pair free of a ragged second wave.
+extern "C" int vx_groupnorm_capacity(int C) {
+  int R = 1;
+  const int threads = gn_block(C, &R);
+  size_t smem = (size_t)2 * R * C * sizeof(float);
+  if (smem > 200 * 1024) return 0;
+  if (smem > 48 * 1024) cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  int per_sm = 0, dev = 0, sms = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gn_fused_kernel, threads, smem) != cudaSuccess) return 0;
+  int per_sm2 = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, gn_apply_kernel, threads, (size_t)(2 * C + 64) * sizeof(float)) ==
+          cudaSuccess && per_sm2 < per_sm)
+    per_sm = per_sm2;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return per_sm * sms;
+}
+
+// One-launch GroupNorm.  Returns 2 (and launches nothing) when the NB * S CTAs cannot all be resident at once -- the
+// caller then uses the two-kernel pair.  counters: int[2 * NB], zero-initialised once by the caller.
+extern "C" int vx_groupnorm_fused(const void* x1, long long ld1, int C1, const void* x2, long long ld2, int C2, int NB,
+                                  int HW, int G, int S, float* partial, int* counters, const float* gamma,
+                                  const float* beta, float eps, int silu, void* out, long long ldo, void* stream) {
+  const int C = C1 + C2;
+  VX_REQUIRE(C1 % 8 == 0 && C2 % 8 == 0 && C % G == 0 && S >= 1, "vx_groupnorm_fused: bad C1=%d C2=%d G=%d", C1, C2, G);
+  VX_REQUIRE(C / 8 <= 1024 && counters, "vx_groupnorm_fused: C=%d too wide / no counters", C);
+  GnFusedArgs a{};
+  a.st = GnStatsArgs{(const __nv_bfloat16*)x1, ld1, C1, (const __nv_bfloat16*)x2, ld2, C2, HW, G, S, 0, partial};
+  const int threads = gn_block(C, &a.st.R);
+  int chunk = (HW + S - 1) / S;
+  if (chunk < 1) chunk = 1;
+  a.ap = GnApplyArgs{(const __nv_bfloat16*)x1, ld1, C1, (const __nv_bfloat16*)x2, ld2, C2, HW, G, S, partial, gamma, beta,
+                     eps, silu, (__nv_bfloat16*)out, ldo, chunk};
+  a.counters = counters;
+  size_t smem = (size_t)2 * a.st.R * C * sizeof(float);
+  const size_t smem_apply = (size_t)(2 * C + 2 * G) * sizeof(float);
+  if (smem_apply > smem) smem = smem_apply;
+  if (smem > 200 * 1024) return 2;
+  static size_t configured = 48 * 1024;
+  if (smem > configured) {
+    VX_CHECK_CUDA(cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured = 200 * 1024;
+  }
+  int per_sm = 0, dev = 0, sms = 0;
+  VX_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gn_fused_kernel, threads, smem));
+  VX_CHECK_CUDA(cudaGetDevice(&dev));
+  VX_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  if ((long long)NB * S > (long long)per_sm * sms) return 2;   // a rendezvous needs every CTA resident
+  gn_fused_kernel<<<dim3(S, NB), threads, smem, (cudaStream_t)stream>>>(a);
   VX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -254,10 +254,33 @@ def smallkv_attention(q, k, v, rows_per_frame, heads, Lk, out=None):
 
 
 # ----------------------------------------------------------------------------- norms / activations
-def _gn_S(NB, HW):
-    # NB * S CTAs = 8 per SM in one balanced wave (both GroupNorm kernels use the same partition)
-    s = max(1, min(HW // 32, (148 * 8) // max(NB, 1)))
+_GN_CAP = {}
+
+
+def _gn_S(NB, HW, C=0):
+    """Pixel chunks per frame: NB * S CTAs = ONE wave of what the device actually keeps resident for this channel count
+    (occupancy query in the library), so both GroupNorm passes run without a ragged second wave and the one-launch
+    kernel's rendezvous is safe."""
+    cap = _GN_CAP.get(C)
+    if cap is None:
+        cap = _ffi.lib().vx_groupnorm_capacity(c_int(C)) if C else 148 * 4
+        _GN_CAP[C] = cap = max(int(cap), 1)
+    s = max(1, min(HW // 32, cap // max(NB, 1)))
     return max(1, min(s, 64))
+
+
+_GN_FUSED = os.environ.get("VX_GN_FUSED", "1") != "0"
+_GN_COUNTERS = {}
+
+
+def _gn_counters(device, NB):
+    """int32 [2 * NB] rendezvous counters of the one-launch GroupNorm, zeroed once (the kernel recycles them)."""
+    key = (device.type, device.index)
+    t = _GN_COUNTERS.get(key)
+    if t is None or t.numel() < 2 * NB:
+        t = torch.zeros(max(2 * NB, 1024), device=device, dtype=torch.int32)
+        _GN_COUNTERS[key] = t
+    return t
 
 
 def groupnorm(x1, NB, HW, gamma, beta, eps, silu, x2=None, groups=32, out=None, ws=None):
@@ -271,13 +294,20 @@ def groupnorm(x1, NB, HW, gamma, beta, eps, silu, x2=None, groups=32, out=None, 
     _chk_bf16(x1, x2, out)
     C1 = x1.shape[1]
     C2 = 0 if x2 is None else x2.shape[1]
-    S = _gn_S(NB, HW)
+    S = _gn_S(NB, HW, C1 + C2)
     if ws is None:
         ws = torch.empty(NB * S * groups * 3, device=x1.device, dtype=torch.float32)
     if out is None:
         out = torch.empty((NB * HW, C1 + C2), device=x1.device, dtype=BF16)
     L = _ffi.lib()
     ld2 = c_ll(0 if x2 is None else x2.stride(0))
+    if _GN_FUSED:
+        rc = L.vx_groupnorm_fused(ptr(x1), c_ll(x1.stride(0)), c_int(C1), ptr(x2), ld2, c_int(C2), c_int(NB), c_int(HW),
+                                  c_int(groups), c_int(S), ptr(ws), ptr(_gn_counters(x1.device, NB)), ptr(gamma), ptr(beta),
+                                  c_float(eps), c_int(int(silu)), ptr(out), c_ll(out.stride(0)), stream_ptr())
+        if rc != 2:                     # 2 = grid cannot be co-resident: fall through to the two-kernel pair
+            check(rc, "vx_groupnorm_fused")
+            return out
     check(L.vx_groupnorm_stats(ptr(x1), c_ll(x1.stride(0)), c_int(C1), ptr(x2), ld2, c_int(C2), c_int(NB), c_int(HW),
                                c_int(groups), c_int(S), ptr(ws), stream_ptr()), "vx_groupnorm_stats")
     check(L.vx_groupnorm_apply(ptr(x1), c_ll(x1.stride(0)), c_int(C1), ptr(x2), ld2, c_int(C2), c_int(NB), c_int(HW),
@@ -299,7 +329,7 @@ def _groupnorm_grouped(x1, NB, HW, gamma, beta, eps, silu, x2, groups, out, grp)
         a1 = x1[r0:r1]
         a2 = None if x2 is None else x2[r0:r1]
         o = out[r0:r1]
-        S = _gn_S(nb, HW)
+        S = _gn_S(nb, HW, C1 + C2)
         w = torch.empty(nb * S * groups * 3, device=x1.device, dtype=torch.float32)
         ld2 = c_ll(0 if a2 is None else a2.stride(0))
         check(L.vx_groupnorm_stats(ptr(a1), c_ll(a1.stride(0)), c_int(C1), ptr(a2), ld2, c_int(C2), c_int(nb), c_int(HW),
