@@ -237,7 +237,8 @@ def kernel_roofline(pipe, host, L, h):
     CUDA events on the launching stream; achieved = sum(2*M*N*K) / sum(duration)."""
     from vexpress_b200 import ops
     recs = []
-    orig = dict(gemm=ops.gemm, conv3x3=ops.conv3x3, flash_attention=ops.flash_attention)
+    orig = dict(gemm=ops.gemm, conv3x3=ops.conv3x3, flash_attention=ops.flash_attention, upconv3x3=ops.upconv3x3,
+                groupnorm=ops.groupnorm, layernorm=ops.layernorm)
 
     def timed(name, fn, flops_of):
         def w(*a, **k):
@@ -261,9 +262,20 @@ def kernel_roofline(pipe, host, L, h):
         q, heads, nq, nk = a[0], a[3], a[4], a[5]
         return 4.0 * q.shape[0] * nk * q.shape[1]
 
+    def f_upconv(a, k, out):       # canonical FLOPs of conv3x3(upsample2x(x)): 9 taps at the upsampled resolution
+        nb, hh, ww, c = a[0].shape
+        return 2.0 * nb * 4 * hh * ww * 9 * c * (a[1].shape[0] // 4)
+
+    def b_norm(a, k, out):         # algorithmic bytes of a normalisation: input once + output once
+        x2 = k.get("x2")
+        return 2.0 * (a[0].numel() + (x2.numel() if x2 is not None else 0)) + 2.0 * out.numel()
+
     ops.gemm = timed("gemm", orig["gemm"], f_gemm)
     ops.conv3x3 = timed("conv3x3", orig["conv3x3"], f_conv)
+    ops.upconv3x3 = timed("conv3x3", orig["upconv3x3"], f_upconv)
     ops.flash_attention = timed("flash", orig["flash_attention"], f_fa)
+    ops.groupnorm = timed("groupnorm", orig["groupnorm"], b_norm)
+    ops.layernorm = timed("layernorm", orig["layernorm"], b_norm)
     try:
         eng = pipe.denoising_unet.engine()
         f = min(L, 16)
@@ -275,14 +287,49 @@ def kernel_roofline(pipe, host, L, h):
             eng.forward_frames(frames, 499, enc, kps, None, 2, f)
             torch.cuda.synchronize()
     finally:
-        ops.gemm, ops.conv3x3, ops.flash_attention = orig["gemm"], orig["conv3x3"], orig["flash_attention"]
+        for k_, v_ in orig.items():
+            setattr(ops, k_, v_)
     agg = {}
     for name, fl, e0, e1 in recs:
         d = agg.setdefault(name, [0.0, 0.0, 0])
         d[0] += fl
         d[1] += e0.elapsed_time(e1) * 1e-3
         d[2] += 1
-    return {k: dict(tflops=v[0] / v[1] / 1e12, seconds=v[1], launches=v[2], flop=v[0]) for k, v in agg.items()}
+    out = {}
+    for k, v in agg.items():
+        if k in ("groupnorm", "layernorm"):
+            out[k] = dict(algorithmic_gbs=v[0] / v[1] / 1e9, seconds=v[1], calls=v[2], algorithmic_bytes=v[0])
+        else:
+            out[k] = dict(tflops=v[0] / v[1] / 1e12, seconds=v[1], launches=v[2], flop=v[0])
+    return out
+
+
+def ncu_evidence():
+    """Counters of the dominant kernel from THIS round's ncu capture of the same forward (profiles/r02_roofline.csv, made by
+    profiles/tools/forward_once.py + roofline_merge.py): per-launch DRAM traffic next to the algorithmic bytes of the same
+    launches, tensor-pipe activity, and the flash / GroupNorm rows."""
+    import csv
+    p = os.path.join(ROOT, "profiles", "r02_roofline.csv")
+    if not os.path.exists(p):
+        return None
+    rows = [r for r in csv.DictReader(open(p)) if r["part"] == "unet"]
+    f = lambda r, k: float(r[k]) if r.get(k) not in (None, "") else 0.0
+    dom = [r for r in rows if r["kernel"].startswith("gemm_tcgen05_kernel") and r["op"] in ("gemm", "conv3x3")]
+    n = sum(int(r["launches"]) for r in dom)
+    if not n:
+        return None
+    us = sum(f(r, "us_total") for r in dom)
+    ev = dict(source="profiles/r02_roofline.csv (ncu, cold caches, serialised)", launches=n,
+              dram_bytes_per_launch=sum(f(r, "dram_mb_per_launch") * int(r["launches"]) for r in dom) / n * 1e6,
+              algorithmic_bytes_per_launch=sum(f(r, "algorithmic_mb_per_launch") * int(r["launches"]) for r in dom) / n * 1e6,
+              l2_bytes_per_launch=sum(f(r, "l2_mb_per_launch") * int(r["launches"]) for r in dom) / n * 1e6,
+              tensor_pipe_active_pct=sum(f(r, "tensor_pipe_active_pct") * f(r, "us_total") for r in dom) / us)
+    fl = [r for r in rows if r["op"] == "flash_attention"]
+    if fl:
+        uf = sum(f(r, "us_total") for r in fl)
+        ev["flash_tensor_pipe_active_pct"] = sum(f(r, "tensor_pipe_active_pct") * f(r, "us_total") for r in fl) / uf
+        ev["flash_l2_bytes_per_launch"] = sum(f(r, "l2_mb_per_launch") * int(r["launches"]) for r in fl) / sum(int(r["launches"]) for r in fl) * 1e6
+    return ev
 
 
 # --------------------------------------------------------------------------------------------- CPU arms
@@ -364,24 +411,34 @@ def reference_arm(args):
     print(json.dumps(line))
 
 
-FRAMES_OVERRIDE = 0   # --frames L: other BASELINE configs on one GPU (e.g. 96 = configs[2]); not the headline line
+FRAMES_OVERRIDE = 0   # --frames L: the other BASELINE configs (96 = configs[2] on 1 GPU, 384 = configs[3] on 8); not the headline
+LATENT = 64           # --size 768 -> 96 (configs[4])
+DDIM_STEPS = 25       # --ddim-steps 50 (configs[4])
 
 
 def workload_config(n):
     L = 16 if n == 1 else 8 * n + 8
-    if FRAMES_OVERRIDE and n == 1:
-        L = FRAMES_OVERRIDE
-        nw = (L - 16) // 8 + 1
-        return dict(workload=f"512x512, {L} frames via context scheduler (window 16, overlap 8 -> {nw} windows), 25 DDIM steps, "
-                             f"CFG 3.5, bf16, 1 GPU", video_length=L, context_frames=16, context_overlap=8,
-                    num_inference_steps=25, guidance_scale=3.5, l2="working set >> 126 MB L2", parallelism="windows-dp1")
-    return dict(workload=("BASELINE configs[1]: 512x512, single 16-frame context window, 25 DDIM steps, CFG 3.5, bf16"
-                          if n == 1 else
-                          f"512x512, {L} frames = {n} context windows (window 16, overlap 8), one window per rank, 25 DDIM "
-                          f"steps, CFG 3.5, bf16, NCCL all-reduce of overlap noise-pred per step, VAE decode sharded by frame"),
-                video_length=L, context_frames=16, context_overlap=8, num_inference_steps=25, guidance_scale=3.5,
+    res = LATENT * 8
+    base = dict(context_frames=16, context_overlap=8, num_inference_steps=DDIM_STEPS, guidance_scale=3.5,
                 l2="inputs+weights per step (2.7 GB weights, >10 GB activations) far exceed the 126 MB L2; no flush needed",
                 parallelism=f"windows-dp{n}")
+    if FRAMES_OVERRIDE:
+        L = FRAMES_OVERRIDE
+        nw = (L - 16) // 8 + 1
+        per = [len(range(r * (nw // n) + min(r, nw % n), (r + 1) * (nw // n) + min(r + 1, nw % n))) for r in range(n)]
+        return dict(workload=f"{res}x{res}, {L} frames via context scheduler (window 16, overlap 8 -> {nw} windows"
+                             + (f", sharded {'/'.join(map(str, per))} over {n} GPUs, NCCL all-reduce of the overlap noise-pred "
+                                f"sums per step, VAE decode sharded by frame" if n > 1 else "")
+                             + f"), {DDIM_STEPS} DDIM steps, CFG 3.5, bf16, {n} GPU" + ("s" if n > 1 else ""),
+                    video_length=L, windows=nw, **base)
+    if n == 1:
+        name = ("BASELINE configs[1]: 512x512, single 16-frame context window, 25 DDIM steps, CFG 3.5, bf16"
+                if (res, DDIM_STEPS) == (512, 25) else
+                f"BASELINE configs[4]-style: {res}x{res}, single 16-frame context window, {DDIM_STEPS} DDIM steps, CFG 3.5, bf16")
+        return dict(workload=name, video_length=L, windows=1, **base)
+    return dict(workload=f"{res}x{res}, {L} frames = {n} context windows (window 16, overlap 8), one window per rank, "
+                         f"{DDIM_STEPS} DDIM steps, CFG 3.5, bf16, NCCL all-reduce of overlap noise-pred per step, VAE decode "
+                         f"sharded by frame", video_length=L, windows=n, **base)
 
 
 # --------------------------------------------------------------------------------------------- our arm
@@ -397,7 +454,7 @@ def ours(args):
         torch.distributed.init_process_group("nccl", device_id=dev)
     n = world
     cfgw = workload_config(n)
-    L, h, steps_ddim, gs = cfgw["video_length"], 64, 25, 3.5
+    L, h, steps_ddim, gs = cfgw["video_length"], LATENT, DDIM_STEPS, 3.5
     from vexpress_b200 import _ffi
     pipe, host, banks = build_ours(L, h, dev)
     from vexpress_b200.modules import ReferenceAttentionControl
@@ -418,7 +475,7 @@ def ours(args):
         return pipe_decode_device(pipe, lat, dist)
 
     def e2e_pass():
-        return pipe(reference_image=None, kps_images=None, audio_waveform=None, width=512, height=512, video_length=L,
+        return pipe(reference_image=None, kps_images=None, audio_waveform=None, width=8 * h, height=8 * h, video_length=L,
                     num_inference_steps=steps_ddim, guidance_scale=gs, context_frames=16, context_overlap=8,
                     reference_attention_weight=0.95, audio_attention_weight=3.0, do_multi_devices_inference=dist)
 
@@ -483,17 +540,24 @@ def ours(args):
             op_table(pipe, host, L, h, "vae")
         fps = L * args.steps / sec
         e2e_fps = L * args.steps / e2e_wall
-        windows = n if not (FRAMES_OVERRIDE and n == 1) else (L - 16) // 8 + 1
-        work_tflop = steps_ddim * windows * 32 * UNET_TFLOP_PER_FRAME_EVAL + L * VAE_TFLOP_PER_FRAME
+        windows = cfgw["windows"]
+        s768 = LATENT == 96      # canonical work per frame-eval / decoded frame at 768x768
+        work_tflop = steps_ddim * windows * 32 * (3.5616 if s768 else UNET_TFLOP_PER_FRAME_EVAL) \
+            + L * (5.754 if s768 else VAE_TFLOP_PER_FRAME)
         line = dict(metric="frames_per_sec_512x512_25step", value=fps, unit="frames/s", n_gpus=n, steps=args.steps,
-                    warmup=args.warmup, ms_per_step=sec / args.steps * 1e3, higher_is_better=True, scaling="weak",
+                    warmup=args.warmup, ms_per_step=sec / args.steps * 1e3, higher_is_better=True,
+                    scaling="strong" if FRAMES_OVERRIDE else "weak",
                     vs_baseline=None, dtype="bf16", data="synthetic (random-init weights, dummy audio/kps/bank tensors)",
                     config=cfgw, clocks=clocks,
                     e2e=dict(value=e2e_fps, unit="frames/s",
                              h2d_bytes_per_step=int(sum(v.numel() * v.element_size() for v in host.values())),
-                             d2h_bytes_per_step=int(L * 3 * 512 * 512 * 4)),
+                             d2h_bytes_per_step=int(L * 3 * (8 * h) * (8 * h) * 4)),
                     gpu_launches=int(launches_direct),
                     unet_ms_per_step=unet_ms_per_step, vae_decode_ms=vae_ms,
+                    window_forwards_per_s=windows * steps_ddim * args.steps / sec,
+                    # weak scaling gives every rank ONE 16-frame window at overlap 8: N windows cover 8N + 8 frames, so
+                    # frames/s per GPU can reach at most (8N + 8) / (16 N) of the 1-GPU figure even with zero overhead
+                    scaling_ceiling=(1.0 if (n == 1 or FRAMES_OVERRIDE) else (8 * n + 8) / (16.0 * n)),
                     whole_path=dict(tflop_per_pass=work_tflop, achieved_tflops=work_tflop * args.steps / sec / n,
                                     frac_of_sustained_peak=work_tflop * args.steps / sec / n / pk["tf_sustained"]))
         if n == 1 and os.environ.get("VX_BENCH_REFNET"):
@@ -505,15 +569,28 @@ def ours(args):
                     for kk in ("seconds", "launches", "flop"):
                         dom[kk] += roof_k[k][kk]
             ach = dom["flop"] / dom["seconds"] / 1e12
-            traffic = None
-            tp = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
-            if os.path.exists(tp):
-                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            ev = ncu_evidence() or {}
+            fa = dict(roof_k.get("flash") or {})
+            if fa:
+                fa.update(bound="softmax instruction stream (MUFU ex2 16/clk/SM) -> tensor pipe <= 40 % at hd 40",
+                          frac_of_sustained_tensor_peak=fa["tflops"] / pk["tf_sustained"],
+                          tensor_pipe_active_pct=ev.get("flash_tensor_pipe_active_pct"))
+            hbm = {}
+            for k in ("groupnorm", "layernorm"):
+                if k in roof_k:
+                    hbm[k] = dict(bound="hbm", achieved=roof_k[k]["algorithmic_gbs"], peak=pk["hbm_gbs"], unit="GB/s",
+                                  frac=roof_k[k]["algorithmic_gbs"] / pk["hbm_gbs"], seconds_per_forward=roof_k[k]["seconds"],
+                                  calls_per_forward=roof_k[k]["calls"],
+                                  algorithmic_bytes_per_forward=roof_k[k]["algorithmic_bytes"])
             line["roofline"] = dict(bound="tensor", kernel="gemm_tcgen05_kernel (GEMM + implicit-GEMM 3x3 conv)",
                                     achieved=ach, peak=pk["tf_sustained"], unit="TFLOP/s", frac=ach / pk["tf_sustained"],
-                                    traffic=traffic, peak_source=pk["source"] + " (sustained cuBLAS bf16)",
+                                    traffic=ev.get("dram_bytes_per_launch"),
+                                    algorithmic_bytes=ev.get("algorithmic_bytes_per_launch"),
+                                    l2_bytes=ev.get("l2_bytes_per_launch"),
+                                    tensor_pipe_active_pct=ev.get("tensor_pipe_active_pct"), traffic_source=ev.get("source"),
+                                    peak_source=pk["source"] + " (sustained cuBLAS bf16)",
                                     launches_per_forward=dom["launches"], seconds_per_forward=dom["seconds"],
-                                    flash_attention=roof_k.get("flash"))
+                                    flash_attention=fa or None, **hbm)
         print(json.dumps(line))
     if dist:
         torch.distributed.destroy_process_group()
@@ -557,10 +634,12 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--frames", type=int, default=0, help="video length override for N=1 (multiple of 8, >= 16)")
+    ap.add_argument("--frames", type=int, default=0, help="video length override (multiple of 8, >= 16): 96 = configs[2], 384 = configs[3]")
+    ap.add_argument("--size", type=int, default=512, help="video side in pixels (512, or 768 = configs[4])")
+    ap.add_argument("--ddim-steps", type=int, default=25)
     args = ap.parse_args()
-    global FRAMES_OVERRIDE
-    FRAMES_OVERRIDE = args.frames
+    global FRAMES_OVERRIDE, LATENT, DDIM_STEPS
+    FRAMES_OVERRIDE, LATENT, DDIM_STEPS = args.frames, args.size // 8, args.ddim_steps
     if args.impl == "reference":
         reference_arm(args)
         return

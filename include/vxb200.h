@@ -154,8 +154,9 @@ int vx_upconv3x3_bf16(const void* X, int NB, int H, int W, int C, const void* Wt
 
 /* ---- conditioning prologue: im2col of a 3x3 conv (stride 1 or 2, pad 1, NHWC bf16) with an
  * optional SiLU on the gathered input; VKpsGuider's narrow conv -> SiLU chain (modules/v_kps_guider.py:35-45) runs as
- * im2col(SiLU(x)) + vx_gemm_bf16.  out [NB*Ho*Wo, 9*C], K order (tap, channel). */
-int vx_im2col3x3(const void* x, int NB, int H, int W, int C, int stride, int silu, void* out, void* stream);
+ * im2col(SiLU(x)) + vx_gemm_bf16.  out [NB*Ho*Wo, 9*C], K order (tap, channel).  pad_lo = 1: pad 1 all round;
+ * pad_lo = 0 (stride 2 only): pad (0,1,0,1), the Downsample2D(padding=0) of the VAE encoder. */
+int vx_im2col3x3(const void* x, int NB, int H, int W, int C, int stride, int silu, int pad_lo, void* out, void* stream);
 
 #ifdef __cplusplus
 }

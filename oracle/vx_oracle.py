@@ -765,6 +765,74 @@ def vae_decode(sd, cfg, z: Tensor) -> Tensor:
     return conv(sd, d + ".conv_out", x)
 
 
+def vae_encode_mean(sd, cfg, x: Tensor) -> Tensor:
+    """AutoencoderKL.encode(x).latent_dist.mean (diffusers 0.29.2 Encoder, sd-vae-ft-mse layout; the call the reference
+    makes at pipelines/v_express_pipeline.py:346): conv_in -> DownEncoderBlock2D x len(boc) (resnets, then
+    Downsample2D(padding=0): F.pad (0,1,0,1) + conv3x3 stride 2) -> UNetMidBlock2D -> GroupNorm -> SiLU -> conv_out ->
+    quant_conv; mean = first latent_channels channels.  x (n,3,H,W) in [-1,1] -> (n,4,H/8,W/8)."""
+    g = cfg["norm_num_groups"]
+    boc = cfg["block_out_channels"]
+    e = "encoder"
+    h = conv(sd, e + ".conv_in", x)
+    for i in range(len(boc)):
+        for j in range(cfg["layers_per_block"]):
+            h = _vae_resnet(sd, f"{e}.down_blocks.{i}.resnets.{j}", h, g)
+        if i < len(boc) - 1:
+            h = F.pad(h, (0, 1, 0, 1), mode="constant", value=0)
+            h = conv(sd, f"{e}.down_blocks.{i}.downsamplers.0.conv", h, stride=2, padding=0)
+    h = _vae_resnet(sd, e + ".mid_block.resnets.0", h, g)
+    h = _vae_attn(sd, e + ".mid_block.attentions.0", h, g)
+    h = _vae_resnet(sd, e + ".mid_block.resnets.1", h, g)
+    h = F.silu(group_norm(sd, e + ".conv_norm_out", h, g, 1e-6))
+    moments = conv(sd, "quant_conv", conv(sd, e + ".conv_out", h), padding=0)
+    return moments[:, :cfg["latent_channels"]]
+
+
+def vae_encoder_param_shapes(cfg) -> Dict[str, tuple]:
+    """``encoder.*`` + ``quant_conv.*`` keys of diffusers' AutoencoderKL."""
+    boc = cfg["block_out_channels"]
+    S: Dict[str, tuple] = {}
+
+    def conv_(p, co, ci, k):
+        S[p + ".weight"] = (co, ci, k, k)
+        S[p + ".bias"] = (co,)
+
+    def norm_(p, c):
+        S[p + ".weight"] = (c,)
+        S[p + ".bias"] = (c,)
+
+    def res_(p, ci, co):
+        norm_(p + ".norm1", ci)
+        conv_(p + ".conv1", co, ci, 3)
+        norm_(p + ".norm2", co)
+        conv_(p + ".conv2", co, co, 3)
+        if ci != co:
+            conv_(p + ".conv_shortcut", co, ci, 1)
+
+    lc = cfg["latent_channels"]
+    e = "encoder"
+    conv_(e + ".conv_in", boc[0], 3, 3)
+    out_c = boc[0]
+    for i, ch in enumerate(boc):
+        in_c, out_c = out_c, ch
+        for j in range(cfg["layers_per_block"]):
+            res_(f"{e}.down_blocks.{i}.resnets.{j}", in_c if j == 0 else out_c, out_c)
+        if i < len(boc) - 1:
+            conv_(f"{e}.down_blocks.{i}.downsamplers.0.conv", out_c, out_c, 3)
+    top = boc[-1]
+    res_(e + ".mid_block.resnets.0", top, top)
+    a = e + ".mid_block.attentions.0"
+    norm_(a + ".group_norm", top)
+    for n in ("to_q", "to_k", "to_v", "to_out.0"):
+        S[f"{a}.{n}.weight"] = (top, top)
+        S[f"{a}.{n}.bias"] = (top,)
+    res_(e + ".mid_block.resnets.1", top, top)
+    norm_(e + ".conv_norm_out", top)
+    conv_(e + ".conv_out", 2 * lc, top, 3)
+    conv_("quant_conv", 2 * lc, 2 * lc, 1)
+    return S
+
+
 def decode_latents(vae_sd, vae_cfg, latents: Tensor) -> Tensor:
     """pipelines/v_express_pipeline.py:152-166: z/0.18215, per-frame decode, (x/2+.5).clamp, fp32."""
     f = latents.shape[2]

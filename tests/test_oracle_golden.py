@@ -4,6 +4,7 @@ import json
 import os
 
 import numpy as np
+import pytest
 import torch
 
 from oracle import vx_oracle as O
@@ -238,3 +239,27 @@ def test_vae_decoder_against_independent_module_restatement():
         b = O.vae_decode(vsd, vcfg, z)
     assert a.shape == (2, 3, 128, 128)
     np.testing.assert_allclose(a.numpy(), b.numpy(), atol=2e-5, rtol=1e-5)
+
+
+def test_vae_encoder_against_independent_module_restatement():
+    """the oracle's functional VAE encoder (posterior mean) vs the library-structured nn.Module in the
+    shim; the strict load pins the encoder's state_dict layout, which the product mirrors (vexpress_b200 AutoencoderKL)."""
+    d = _shim()
+    vcfg = O.small_vae_cfg()
+    vsd = O.synth_state_dict({**O.vae_param_shapes(vcfg), **O.vae_encoder_param_shapes(vcfg)}, 1236)
+    vae = d.AutoencoderKL(vsd, vcfg)
+    x = torch.rand(2, 3, 64, 48, generator=torch.Generator().manual_seed(9)) * 2 - 1
+    with torch.no_grad():
+        a = vae.encode(x).latent_dist.mean
+        b = O.vae_encode_mean(vsd, vcfg, x)
+    assert a.shape == (2, 4, 8, 6)
+    np.testing.assert_allclose(a.numpy(), b.numpy(), atol=2e-5, rtol=1e-5)
+    from vexpress_b200.modules.vae import AutoencoderKL as Prod
+    p = Prod(block_out_channels=vcfg["block_out_channels"], layers_per_block=vcfg["layers_per_block"])
+    p.load_state_dict(vsd, strict=True)
+    assert set(p.state_dict()) == set(vsd)
+    p2 = Prod(block_out_channels=vcfg["block_out_channels"], layers_per_block=vcfg["layers_per_block"])
+    p2.load_state_dict(O.synth_state_dict(O.vae_param_shapes(vcfg), 1235), strict=True)      # decoder-only checkpoint
+    assert set(p2.state_dict()) == set(O.vae_param_shapes(vcfg))
+    with pytest.raises(RuntimeError):
+        p2.encode(x)

@@ -153,3 +153,30 @@ def test_pipeline_non_tiling_length_follows_reference_bookkeeping(golden_dir):
     e_ref = _rel(captured["latents"], g["final_latents"])
     print(f"non-tiling L=20: final latents rel {e:.3e} vs oracle, worst frame {worst:.3e}; vs reference golden {e_ref:.3e}")
     assert e < 5e-2 and worst < 8e-2 and e_ref < 6e-2
+
+
+def test_vae_encode_reference_latent_vs_oracle():
+    """Row f4: ``prepare_reference_latent`` = VAE posterior mean x 0.18215 on the decoder's kernels vs the oracle."""
+    from oracle import vx_oracle as O
+    from vexpress_b200.modules.vae import AutoencoderKL
+    from vexpress_b200.pipelines.scheduler import DDIMScheduler
+    from vexpress_b200.pipelines.v_express_pipeline import VExpressPipeline
+    vcfg = O.small_vae_cfg()
+    vsd = O.synth_state_dict({**O.vae_param_shapes(vcfg), **O.vae_encoder_param_shapes(vcfg)}, 1236)
+    vae = AutoencoderKL(block_out_channels=vcfg["block_out_channels"], layers_per_block=vcfg["layers_per_block"])
+    vae.load_state_dict(vsd, strict=True)
+    vae = vae.to(torch.bfloat16).to("cuda")
+    img = torch.rand(1, 3, 128, 128, generator=torch.Generator().manual_seed(11)) * 2 - 1
+    r = lambda t: t.bfloat16().float()
+    with torch.no_grad():
+        ref = O.vae_encode_mean({k: r(v) for k, v in vsd.items()}, vcfg, r(img)) * 0.18215
+    pipe = VExpressPipeline(vae=vae, reference_net=None, denoising_unet=vae, v_kps_guider=None, audio_processor=None,
+                            audio_encoder=None, audio_projection=None, scheduler=DDIMScheduler())
+    lat = pipe.prepare_reference_latent(img, 128, 128)
+    e = _rel(lat.float().cpu(), ref)
+    print(f"VAE encode (reference latent) rel-L2 vs oracle {e:.3e}")
+    assert lat.shape == (1, 4, 16, 16) and e < 2e-2
+    # a uint8 HWC image goes through the same preprocessing as the reference's VaeImageProcessor (x / 255 * 2 - 1)
+    u8 = ((img[0].permute(1, 2, 0) + 1) * 127.5).round().clamp(0, 255).to(torch.uint8).numpy()
+    lat2 = pipe.prepare_reference_latent(u8, 128, 128)
+    assert _rel(lat2.float().cpu(), ref) < 3e-2

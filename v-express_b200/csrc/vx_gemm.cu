@@ -786,8 +786,8 @@ extern "C" int vx_conv3x3_bf16(const void* X, int NB, int H, int W, int C, const
   // pixel rectangle of <= 128 output rows that is contiguous in NHWC row order
   int wbox, hbox = 1, nbox = 1;
   if (W >= kBlockM) {
-    VX_REQUIRE(W % kBlockM == 0, "vx_conv3x3_bf16: W=%d must be a multiple of 128 when >= 128", W);
-    wbox = kBlockM;
+    wbox = kBlockM;                 // widest divisor of W that fits a tile (192 -> 96 at the 768x768 VAE level)
+    while (W % wbox) --wbox;
   } else {
     wbox = W;
     hbox = kBlockM / W;
@@ -855,8 +855,8 @@ extern "C" int vx_upconv3x3_bf16(const void* X, int NB, int H, int W, int C, con
   VX_REQUIRE(ldc % 8 == 0, "vx_upconv3x3_bf16: ldc must be %%8");
   int wbox, hbox = 1, nbox = 1;
   if (W >= kBlockM) {
-    VX_REQUIRE(W % kBlockM == 0, "vx_upconv3x3_bf16: W=%d must be a multiple of 128 when >= 128", W);
-    wbox = kBlockM;
+    wbox = kBlockM;                 // widest divisor of W that fits a tile (192 -> 96 at the 768x768 VAE level)
+    while (W % wbox) --wbox;
   } else {
     wbox = W;
     hbox = kBlockM / W;

@@ -81,7 +81,9 @@ __global__ void __launch_bounds__(256) median3d_kernel(const float* __restrict__
 // implicit-GEMM conv (C % 64); they run as im2col(SiLU(x)) + tensor-core GEMM instead.  K order = (tap, channel), the
 // order of pack_conv3x3_weight.  Same structure as im2col_s2_kernel (vx_misc.cu).
 __global__ void im2col3x3_kernel(const __nv_bfloat16* __restrict__ x, int NB, int H, int W, int C, int stride, int silu,
-                                 __nv_bfloat16* __restrict__ out) {
+                                 int pad_lo, __nv_bfloat16* __restrict__ out) {
+  // pad_lo = 1: pad 1 on every side (nn.Conv2d(padding=1)); pad_lo = 0: pad (0, 1, 0, 1) -- right/bottom only, the
+  // diffusers Downsample2D(padding=0) of the VAE encoder -- same output size for even H, W at stride 2
   const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1, V = C / 8;
   const long long total = (long long)NB * Ho * Wo * 9 * V;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -91,7 +93,7 @@ __global__ void im2col3x3_kernel(const __nv_bfloat16* __restrict__ x, int NB, in
     const long long opix = idx / ((long long)V * 9);
     const int ox = (int)(opix % Wo), oy = (int)((opix / Wo) % Ho);
     const long long n = opix / ((long long)Wo * Ho);
-    const int yy = oy * stride + t / 3 - 1, xx = ox * stride + t % 3 - 1;
+    const int yy = oy * stride + t / 3 - pad_lo, xx = ox * stride + t % 3 - pad_lo;
     uint4 val = make_uint4(0, 0, 0, 0);
     if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
       val = *reinterpret_cast<const uint4*>(x + ((n * H + yy) * W + xx) * C + v * 8);
@@ -113,13 +115,15 @@ __global__ void im2col3x3_kernel(const __nv_bfloat16* __restrict__ x, int NB, in
 
 using namespace vx;
 
-extern "C" int vx_im2col3x3(const void* x, int NB, int H, int W, int C, int stride, int silu, void* out, void* stream) {
+extern "C" int vx_im2col3x3(const void* x, int NB, int H, int W, int C, int stride, int silu, int pad_lo, void* out,
+                            void* stream) {
   VX_REQUIRE(C % 8 == 0 && (stride == 1 || stride == 2), "vx_im2col3x3: C=%d stride=%d", C, stride);
+  VX_REQUIRE(pad_lo == 1 || (pad_lo == 0 && stride == 2 && H % 2 == 0 && W % 2 == 0), "vx_im2col3x3: pad_lo=%d needs stride 2, even H/W", pad_lo);
   const long long total = (long long)NB * ((H - 1) / stride + 1) * ((W - 1) / stride + 1) * 9 * (C / 8);
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   im2col3x3_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, NB, H, W, C, stride, silu,
-                                                                      (__nv_bfloat16*)out);
+                                                                      pad_lo, (__nv_bfloat16*)out);
   VX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

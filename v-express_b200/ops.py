@@ -481,13 +481,14 @@ def median3d_u8(video, want_filtered=False):
     return (frames, filt) if want_filtered else frames
 
 
-def im2col3x3(x, NB, H, W, stride=1, silu=False, out=None):
-    """x [NB*H*W, C] NHWC bf16 -> [NB*Ho*Wo, 9*C] (pad 1), optionally SiLU(x) while gathering."""
+def im2col3x3(x, NB, H, W, stride=1, silu=False, out=None, pad_lo=1):
+    """x [NB*H*W, C] NHWC bf16 -> [NB*Ho*Wo, 9*C] (pad 1; pad_lo=0: pad (0,1,0,1) at stride 2), optionally SiLU(x) while
+    gathering."""
     _chk_bf16(x, out)
     C = x.shape[1]
     Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
     if out is None:
         out = torch.empty((NB * Ho * Wo, 9 * C), device=x.device, dtype=BF16)
     check(_ffi.lib().vx_im2col3x3(ptr(x), c_int(NB), c_int(H), c_int(W), c_int(C), c_int(stride), c_int(int(silu)),
-                                  ptr(out), stream_ptr()), "vx_im2col3x3")
+                                  c_int(pad_lo), ptr(out), stream_ptr()), "vx_im2col3x3")
     return out

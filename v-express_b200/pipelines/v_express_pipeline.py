@@ -142,9 +142,33 @@ class VExpressPipeline:
         return tqdm(iterable, total=total, disable=True)
 
     # ------------------------------------------------------------------ prologue hooks (outside the hot path)
+    @staticmethod
+    def _reference_image_to_tensor(image, height, width):
+        """The reference's ``reference_image_processor.preprocess`` (VaeImageProcessor(do_convert_rgb=True), default
+        do_normalize: [0,1] -> [-1,1], resample "lanczos"; pipelines/v_express_pipeline.py:112-114,344): a PIL image, an HWC
+        uint8 array, or a (1,3,H,W) tensor already in [-1,1] -> (1,3,height,width) fp32 in [-1,1]."""
+        import numpy as np
+        if torch.is_tensor(image):
+            if image.dim() == 3:
+                image = image.unsqueeze(0)
+            if image.shape[-2:] != (height, width):
+                raise ValueError(f"reference image tensor must be (1,3,{height},{width}), got {tuple(image.shape)}")
+            return image.float()
+        if hasattr(image, "convert"):
+            image = image.convert("RGB")
+            if image.size != (width, height):
+                from PIL import Image
+                image = image.resize((width, height), resample=Image.LANCZOS)
+        arr = np.asarray(image)
+        if arr.shape[:2] != (height, width):
+            raise ValueError(f"reference image of size {arr.shape[:2]} needs resampling to {(height, width)}: pass a PIL image")
+        t = torch.from_numpy(arr.astype(np.float32) / 255.0).permute(2, 0, 1).unsqueeze(0)
+        return 2.0 * t - 1.0
+
     def prepare_reference_latent(self, reference_image, height, width):
-        raise NotImplementedError("prologue hook: VAE encode of the reference image is outside the hot path "
-                                  "(SURVEY.md 8f-f4); override or pass precomputed banks")
+        """Reference pipelines/v_express_pipeline.py:343-348: VAE posterior mean of the reference image x 0.18215."""
+        x = self._reference_image_to_tensor(reference_image, height, width).to(device=self.device, dtype=self.dtype)
+        return self.vae.encode(x).latent_dist.mean * 0.18215
 
     @staticmethod
     def _condition_images_to_tensor(images, height, width):
