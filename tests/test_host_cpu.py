@@ -843,3 +843,103 @@ def test_denoise_sharded_over_ranks_equals_single_rank(L, S, Ov, world):
         assert p.exitcode == 0
     single = _run_fake_denoise(L, S, Ov, 3)
     assert torch.equal(got, single.float())
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Drop-in boundary: the mirrored entry points keep the reference's parameter names, order and defaults.  Runs where the
+# reference tree is present (the build container); on the GPU box the committed snapshot below is checked instead.
+# ----------------------------------------------------------------------------------------------------------------------
+_REF = os.environ.get("VX_REFERENCE", "/root/reference")
+_BOUNDARY = [  # (reference file, class, function, product object path)
+    ("pipelines/v_express_pipeline.py", "VExpressPipeline", "__call__", "vexpress_b200.pipelines.v_express_pipeline:VExpressPipeline.__call__"),
+    ("pipelines/v_express_pipeline.py", "VExpressPipeline", "mean_overlap", "vexpress_b200.pipelines.v_express_pipeline:VExpressPipeline.mean_overlap"),
+    ("pipelines/v_express_pipeline.py", "VExpressPipeline", "__init__", "vexpress_b200.pipelines.v_express_pipeline:VExpressPipeline.__init__"),
+    ("pipelines/v_express_pipeline.py", "VExpressPipeline", "prepare_reference_latent", "vexpress_b200.pipelines.v_express_pipeline:VExpressPipeline.prepare_reference_latent"),
+    ("pipelines/v_express_pipeline.py", "VExpressPipeline", "prepare_kps_feature", "vexpress_b200.pipelines.v_express_pipeline:VExpressPipeline.prepare_kps_feature"),
+    ("pipelines/v_express_pipeline.py", "VExpressPipeline", "prepare_audio_embeddings", "vexpress_b200.pipelines.v_express_pipeline:VExpressPipeline.prepare_audio_embeddings"),
+    ("modules/unet_3d.py", "UNet3DConditionModel", "forward", "vexpress_b200.modules.unet_3d:UNet3DConditionModel.forward"),
+    ("modules/unet_3d.py", "UNet3DConditionModel", "from_config_2d", "vexpress_b200.modules.unet_3d:UNet3DConditionModel.from_config_2d"),
+    ("modules/unet_3d.py", "UNet3DConditionModel", "__init__", "vexpress_b200.modules.unet_3d:UNet3DConditionModel.__init__"),
+    ("modules/mutual_self_attention.py", "ReferenceAttentionControl", "__init__", "vexpress_b200.modules.mutual_self_attention:ReferenceAttentionControl.__init__"),
+    ("modules/mutual_self_attention.py", "ReferenceAttentionControl", "update", "vexpress_b200.modules.mutual_self_attention:ReferenceAttentionControl.update"),
+    ("modules/mutual_self_attention.py", "ReferenceAttentionControl", "clear", "vexpress_b200.modules.mutual_self_attention:ReferenceAttentionControl.clear"),
+    ("pipelines/context.py", None, "uniform", "vexpress_b200.pipelines.context:uniform"),
+    ("pipelines/context.py", None, "get_context_scheduler", "vexpress_b200.pipelines.context:get_context_scheduler"),
+    ("pipelines/context.py", None, "ordered_halving", "vexpress_b200.pipelines.context:ordered_halving"),
+]
+
+
+def _ast_signature(path, cls, fn):
+    """[(name, default-or-'<required>')] of a function in a source file, without importing it."""
+    import ast
+    tree = ast.parse(open(path).read())
+    body = tree.body
+    if cls is not None:
+        body = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == cls).body
+    f = next(n for n in body if isinstance(n, (ast.FunctionDef, ast.AsyncFunctionDef)) and n.name == fn)
+    a = f.args
+    pos = a.posonlyargs + a.args
+    defaults = [None] * (len(pos) - len(a.defaults)) + list(a.defaults)
+    out = []
+    for arg, d in zip(pos, defaults):
+        out.append((arg.arg, "<required>" if d is None else ast.unparse(d)))
+    for arg, d in zip(a.kwonlyargs, a.kw_defaults):
+        out.append((arg.arg, "<required>" if d is None else ast.unparse(d)))
+    if a.kwarg is not None:
+        out.append(("**" + a.kwarg.arg, ""))
+    return out
+
+
+def _product_signature(spec):
+    import importlib
+    import inspect
+    mod, path = spec.split(":")
+    obj = importlib.import_module(mod)
+    for part in path.split("."):
+        obj = getattr(obj, part)
+    out = []
+    for name, p in inspect.signature(obj).parameters.items():
+        if p.kind == p.VAR_KEYWORD:
+            out.append(("**" + name, ""))
+        elif p.default is p.empty:
+            out.append((name, "<required>"))
+        else:
+            out.append((name, p.default))
+    return out
+
+
+def _same_default(ref_src, val):
+    if ref_src == "<required>" or val == "<required>":
+        return ref_src == val
+    try:
+        import ast
+        ref_val = ast.literal_eval(ref_src)
+    except Exception:
+        if ref_src == "float('inf')":
+            return val == float("inf")
+        return ref_src.replace("torch.", "") in repr(val) or ref_src == "..."      # e.g. torch.float16, Ellipsis defaults
+    if isinstance(ref_val, (list, tuple)) and isinstance(val, (list, tuple)):
+        return list(ref_val) == list(val)
+    if ref_val == {} and val is None:
+        return True          # a mutable `{}` default of the reference is an immutable None here (same meaning)
+    return ref_val == val
+
+
+@pytest.mark.skipif(not os.path.isdir(_REF), reason="reference tree not present (GPU box)")
+@pytest.mark.parametrize("ref_file,cls,fn,spec", _BOUNDARY)
+def test_boundary_signatures_match_reference(ref_file, cls, fn, spec):
+    ref = _ast_signature(os.path.join(_REF, ref_file), cls, fn)
+    ours = _product_signature(spec)
+    if cls is not None:
+        ref = [r for r in ref if r[0] not in ("self", "cls")]
+        ours = [o for o in ours if o[0] not in ("self", "cls")]
+    ref_names = [n for n, _ in ref if not n.startswith("**")]
+    our_names = [n for n, _ in ours if not n.startswith("**")]
+    # every reference parameter exists, in the same order (the product may append optional extras at the end)
+    assert our_names[:len(ref_names)] == ref_names, (fn, ref_names, our_names)
+    for (n, d_ref), (_, d_our) in zip(ref, ours):
+        if n.startswith("**"):
+            continue
+        assert _same_default(d_ref, d_our), (fn, n, d_ref, d_our)
+    for n, d in ours[len(ref):]:
+        assert n.startswith("**") or d != "<required>", f"{fn}: extra parameter {n} must be optional"
