@@ -83,7 +83,9 @@ def build_ours(L, h, device):
     vae = vae.to(torch.bfloat16)
     g = torch.Generator().manual_seed(42)
     lat = torch.randn(1, 4, L, h, h, generator=g).to(torch.bfloat16)
-    kps = torch.cat([torch.zeros(1, 320, L, h, h), 0.1 * torch.randn(1, 320, L, h, h, generator=g)]).to(torch.bfloat16)
+    kps = torch.zeros(2, 320, L, h, h, dtype=torch.bfloat16)                 # [uncond zeros | cond]; bf16 from the start:
+    for f0 in range(0, L, 32):                                             # a 384-frame fp32 copy would be 4 GB per rank
+        kps[1, :, f0:f0 + 32] = (0.1 * torch.randn(320, min(32, L - f0), h, h, generator=g)).to(torch.bfloat16)
     audio = ln_rows(torch.randn(1, L, 5, 768, generator=g))
     audio = torch.cat([torch.zeros_like(audio), audio]).to(torch.bfloat16)
     mods = dict(unet.named_modules())

@@ -822,13 +822,15 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
     const uint32_t to = tmem_o + lane_addr;
     float m_used = -INFINITY, l = 0.f;
     const float c = p.scale_log2;
+    uint32_t v[2][32];
+    // S(0) into registers; inside the loop the load of S(j+1) is issued right behind the store of P(j), so that its latency
+    // (and the barrier round trip in front of it) overlaps the wait for that store instead of opening the next iteration
+    mbar_wait(&s_full[0], 0);
+    tc_fence_after();
+    tmem_ld32(tmem_base + lane_addr, v[0]);
+    tmem_ld32(tmem_base + lane_addr + 32, v[1]);
     for (int j = 0; j < T; ++j) {
       const uint32_t ts = tmem_base + lane_addr + (uint32_t)((j & 1) * 64);
-      mbar_wait(&s_full[j & 1], (uint32_t)((j >> 1) & 1));
-      tc_fence_after();
-      uint32_t v[2][32];
-      tmem_ld32(ts, v[0]);
-      tmem_ld32(ts + 32, v[1]);
       tmem_ld_wait();
       // row max of the 64 scores: 3-input max (sm_100), four independent chains
 #define VX_SV(k) __uint_as_float(v[(k) >> 5][(k) & 31])
@@ -881,6 +883,13 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
       }
       if (!ONES) l += (ls[0] + ls[1]) + (ls[2] + ls[3]);
       tmem_st32(ts, pk);        // P(j): 64 keys = 32 packed columns over the S columns this thread has consumed
+      if (j + 1 < T) {          // S(j+1) was issued an iteration ago: normally complete, the wait is a formality
+        mbar_wait(&s_full[(j + 1) & 1], (uint32_t)(((j + 1) >> 1) & 1));
+        tc_fence_after();
+        const uint32_t tn = tmem_base + lane_addr + (uint32_t)(((j + 1) & 1) * 64);
+        tmem_ld32(tn, v[0]);
+        tmem_ld32(tn + 32, v[1]);
+      }
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&p_ready[j & 1]);
