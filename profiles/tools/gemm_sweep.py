@@ -2,7 +2,7 @@
 usage: python profiles/tools/gemm_sweep.py            (run on a B200; prints TFLOP/s per shape and setting)"""
 import os, sys, torch
 sys.path.insert(0, os.getcwd())
-from vexpress_b200 import ops
+from vexpress_b200 import _ffi, ops
 torch.manual_seed(0)
 dev = 'cuda'
 
@@ -54,6 +54,7 @@ for name, flop, fn in cases:
     for _, env in settings:
         for k in keys: os.environ.pop(k, None)
         os.environ.update(env)
+        _ffi.lib().vx_gemm_reload_env()          # the library reads its switches once; the sweep asks it to re-read them
         try:
             row += f"{flop / t_ms(fn) * 1e-9:12.0f}"
         except Exception as e:

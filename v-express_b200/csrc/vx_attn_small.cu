@@ -399,7 +399,8 @@ extern "C" int vx_temporal_attention(const void* q, const void* k, const void* v
   TemporalArgs a{(const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, ld, (__nv_bfloat16*)out,
                  ldo, b, f, HW, heads, hd, 1.0f / sqrtf((float)hd)};
   auto st = (cudaStream_t)stream;
-  if (f <= 16 && !getenv("VX_TEMPORAL_V1")) {
+  static const bool temporal_v1 = getenv("VX_TEMPORAL_V1") != nullptr;   // A/B switch, read once
+  if (f <= 16 && !temporal_v1) {
     const long long warps = (long long)b * HW * heads;
     const unsigned grid_m = (unsigned)((warps + 3) / 4);
     switch (hd) {
@@ -452,7 +453,8 @@ extern "C" int vx_smallkv_attention(const void* q, long long ldq, const void* k,
   SmallKvArgs a{(const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, ldkv,
                 (__nv_bfloat16*)out, ldo, rows, rows_per_frame, heads, hd, Lk, 1.0f / sqrtf((float)hd)};
   auto st = (cudaStream_t)stream;
-  if (rows_per_frame % 16 == 0 && rows % 16 == 0 && !getenv("VX_SMALLKV_V1") &&
+  static const bool smallkv_v1 = getenv("VX_SMALLKV_V1") != nullptr;     // A/B switch, read once
+  if (rows_per_frame % 16 == 0 && rows % 16 == 0 && !smallkv_v1 &&
       (hd == 8 || hd == 40 || hd == 80 || hd == 160)) {
     const long long warps = rows / 16 * heads;
     const unsigned grid_m = (unsigned)((warps + 3) / 4);

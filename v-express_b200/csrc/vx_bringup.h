@@ -15,6 +15,7 @@ int vx_probe_tma(const void* base, int rank, const unsigned long long* dims, con
                  const unsigned* box, int swizzle, const int* coords, int nbytes, void* out, void* stream);
 
 void vx_flash_reload_env(void);
+void vx_gemm_reload_env(void);
 #ifdef __cplusplus
 }
 #endif

@@ -519,9 +519,27 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   }
 }
 
-static int env_int(const char* name, int dflt) {
-  const char* s = getenv(name);
-  return s ? atoi(s) : dflt;
+// A/B switches (bring-up only) are read ONCE per process: the launch path never touches the environment
+// (the sweep tools re-read them through vx_gemm_reload_env).
+struct GemmEnv {
+  int cg, cg_minkb, pairs, stages, nbuf, bn, verbose;
+  static int geti(const char* name, int dflt) {
+    const char* s = getenv(name);
+    return s ? atoi(s) : dflt;
+  }
+  GemmEnv() {
+    cg = geti("VX_GEMM_CG", 0);
+    cg_minkb = geti("VX_GEMM_CG_MINKB", 12);
+    pairs = geti("VX_GEMM_PAIRS", 0);
+    stages = geti("VX_GEMM_STAGES", 0);
+    nbuf = geti("VX_GEMM_NBUF", 0);
+    bn = geti("VX_GEMM_BN", 0);
+    verbose = geti("VX_GEMM_VERBOSE", 0);
+  }
+};
+static GemmEnv& gemm_env() {
+  static GemmEnv e;
+  return e;
 }
 
 static int num_sms() {
@@ -535,15 +553,14 @@ static int num_sms() {
   return n;
 }
 
-static int env_int(const char* name, int dflt);
 
 static bool pair_ok(int out_f32, int block_n, long long tiles_m, int total_kb) {
   // CTA pairs need an even split of the W tile into 8-row swizzle groups and at least two row tiles.  They pay off
   // once the K loop is long enough to be MMA/operand bound; short K loops (K <= 640) are bound by the epilogue and
   // the output stores, where two independent CTAs overlap better (profiles/tools/gemm_sweep.py).
-  const int mode = env_int("VX_GEMM_CG", 0);   // 0 = auto, 1 = never, 2 = whenever legal
+  const int mode = gemm_env().cg;   // 0 = auto, 1 = never, 2 = whenever legal
   if (out_f32 || block_n % 32 != 0 || tiles_m < 2 || mode == 1) return false;
-  return mode == 2 || total_kb >= env_int("VX_GEMM_CG_MINKB", 12);   // threshold from profiles/tools/gemm_sweep.py
+  return mode == 2 || total_kb >= gemm_env().cg_minkb;   // threshold from profiles/tools/gemm_sweep.py
 }
 
 // resident CTA pairs of the persistent cta_group::2 kernel (GPCs with an odd SM count strand one SM)
@@ -597,8 +614,8 @@ static int num_pairs() {
       cudaGetLastError();
       c = num_sms() / 2;
     }
-    n = env_int("VX_GEMM_PAIRS", c);
-    if (getenv("VX_GEMM_VERBOSE")) fprintf(stderr, "[vx_gemm] resident CTA pairs: %d (occupancy query %d)\n", n, c);
+    n = gemm_env().pairs > 0 ? gemm_env().pairs : c;
+    if (gemm_env().verbose) fprintf(stderr, "[vx_gemm] resident CTA pairs: %d (occupancy query %d)\n", n, c);
   }
   return n;
 }
@@ -612,7 +629,7 @@ static int launch(const CUtensorMap& mA, const CUtensorMap& mA2, const CUtensorM
   const int total_kb = a.taps * a.kblocks1 + a.kblocks2;
   const size_t cap = 227 * 1024 - 2048;
   // deep TMA rings only pay off for long K loops; short K loops need the second staging tile instead
-  int want_stages = env_int("VX_GEMM_STAGES", 0);
+  int want_stages = gemm_env().stages;
   if (want_stages <= 0) want_stages = total_kb < 6 ? (total_kb < 3 ? 3 : total_kb) : 6;
   int nbuf = (!a.out_f32 && (size_t)3 * stage_bytes + 2 * buf_bytes <= cap) ? 2 : 1;
   if (cg == 2 && nbuf == 2) {
@@ -621,14 +638,14 @@ static int launch(const CUtensorMap& mA, const CUtensorMap& mA2, const CUtensorM
     const int st2 = (int)((cap - 2 * (size_t)buf_bytes) / stage_bytes);
     if (st2 < 5 && (!a.has_residual || total_kb >= 40)) nbuf = 1;
   }
-  const int force_nbuf = env_int("VX_GEMM_NBUF", 0);
+  const int force_nbuf = gemm_env().nbuf;
   if (force_nbuf == 1 || (force_nbuf == 2 && (size_t)2 * stage_bytes + 2 * buf_bytes <= cap)) nbuf = force_nbuf;
   int stages = want_stages;
   while (stages > 2 && (size_t)stages * stage_bytes + (size_t)nbuf * buf_bytes > cap) --stages;
   a.stages = stages;
   a.nbuf = nbuf;
   const size_t smem = (size_t)stages * stage_bytes + (size_t)nbuf * buf_bytes + 2048;
-  if (getenv("VX_GEMM_VERBOSE"))
+  if (gemm_env().verbose)
     fprintf(stderr, "[vx_gemm] M=%d N=%d kb=%d taps=%d cg=%d bn=%d stages=%d nbuf=%d tiles=%dx%d\n", a.M, a.N, total_kb,
             a.taps, cg, a.block_n, stages, nbuf, a.tiles_m, a.tiles_n);
   static bool configured = false;
@@ -688,6 +705,8 @@ static int make_out_maps(CUtensorMap* mR, CUtensorMap* mC, const void* residual,
 
 using namespace vx;
 
+extern "C" void vx_gemm_reload_env() { gemm_env() = GemmEnv(); }   // sweep-tool hook (csrc/vx_bringup.h), not product ABI
+
 // epilogue: 0 = linear (bias, bias2, scale, residual); 1 = GEGLU (W / bias packed per tile as value|gate halves,
 // see vx_geglu_pack_rows; out has N/2 columns)
 static int gemm_entry(const void* A, long long lda, int K1, const void* A2, long long lda2, int K2, const void* Wt,
@@ -706,7 +725,7 @@ static int gemm_entry(const void* A, long long lda, int K1, const void* A2, long
   VX_REQUIRE(!geglu || (!bias2 && scale == 1.0f), "vx_gemm_bf16: GEGLU epilogue takes only the packed bias");
   const int tiles_m = (M + kBlockM - 1) / kBlockM;
   const int total_kb = (K1 + kBlockK - 1) / kBlockK + (K2 + kBlockK - 1) / kBlockK;
-  if (block_n <= 0) block_n = env_int("VX_GEMM_BN", 0);
+  if (block_n <= 0) block_n = gemm_env().bn;
   if (block_n <= 0) block_n = pick_block_n(tiles_m, N, gran, out_f32, total_kb);
   VX_REQUIRE(block_n >= gran && block_n % gran == 0 && block_n <= 256 && N % block_n == 0,
              "vx_gemm_bf16: block_n=%d invalid for N=%d", block_n, N);
@@ -806,7 +825,7 @@ extern "C" int vx_conv3x3_bf16(const void* X, int NB, int H, int W, int C, const
   VX_REQUIRE(M % rows_valid == 0, "vx_conv3x3_bf16: NB*H*W=%lld not tileable by %d", M, rows_valid);
   const long long tiles_m = M / rows_valid;
   const int total_kb = 9 * (C / kBlockK);
-  if (block_n <= 0) block_n = env_int("VX_GEMM_BN", 0);
+  if (block_n <= 0) block_n = gemm_env().bn;
   if (block_n <= 0) block_n = pick_block_n(tiles_m, Cout, 32, 0, total_kb);
   VX_REQUIRE(block_n % 32 == 0 && block_n >= 32 && block_n <= 256 && Cout % block_n == 0,
              "vx_conv3x3_bf16: block_n=%d invalid for Cout=%d", block_n, Cout);
@@ -875,7 +894,7 @@ extern "C" int vx_upconv3x3_bf16(const void* X, int NB, int H, int W, int C, con
   VX_REQUIRE(M % rows_valid == 0, "vx_upconv3x3_bf16: NB*H*W=%lld not tileable by %d", M, rows_valid);
   const long long tiles_m = M / rows_valid;
   const int total_kb = 4 * (C / kBlockK);
-  if (block_n <= 0) block_n = env_int("VX_GEMM_BN", 0);
+  if (block_n <= 0) block_n = gemm_env().bn;
   if (block_n <= 0) block_n = pick_block_n(tiles_m * 4, Cout, 32, 0, total_kb);
   VX_REQUIRE(block_n % 32 == 0 && block_n >= 32 && block_n <= 256 && Cout % block_n == 0,
              "vx_upconv3x3_bf16: block_n=%d invalid for Cout=%d", block_n, Cout);

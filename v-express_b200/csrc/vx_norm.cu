@@ -55,7 +55,7 @@ __device__ __forceinline__ void gn_stats_body(const GnStatsArgs& p, float* sm, c
   const __nv_bfloat16* base = second ? p.x2 + (long long)n * p.HW * p.ld2 + (c0 - p.C1)
                                      : p.x1 + (long long)n * p.HW * p.ld1 + c0;
   const long long ld = second ? p.ld2 : p.ld1;
-#pragma unroll 4
+#pragma unroll 8
   for (int px = p0 + r; px < p1; px += p.R) {
     float f[8];
     load8(base + px * ld, f);
@@ -183,10 +183,19 @@ __device__ __forceinline__ void gn_apply_body(const GnApplyArgs& p, float* sm, c
                                     : p.x1 + (long long)n * p.HW * p.ld1 + c0;
   const long long lds = second ? p.ld2 : p.ld1;
   __nv_bfloat16* dst = p.out + (long long)n * p.HW * p.ldo + c0;
-#pragma unroll 4
-  for (int px = p0 + r; px < p1; px += R) {
+  // back to front: in the one-launch kernel the tail of the chunk is what the statistics pass read last, i.e. what the L2
+  // still holds; the output goes out with evict-first stores so that it does not push the input out.  The loads of U pixels
+  // are issued before the first store: the compiler may not hoist a load above a store through possibly aliasing pointers,
+  // so a plain unrolled loop keeps ONE 16-byte load in flight per thread (ncu r02_gn_fused: 37 % of the DRAM peak).
+  auto emit = [&](const uint4& raw, int px) {
+    const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
     float f[8];
-    load8(src + px * lds, f);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 t = unpack_bf16(w4[i]);
+      f[2 * i] = t.x;
+      f[2 * i + 1] = t.y;
+    }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       float y = fmaf(f[i], sc[i], sh[i]);
@@ -198,8 +207,19 @@ __device__ __forceinline__ void gn_apply_body(const GnApplyArgs& p, float* sm, c
       }
       f[i] = y;
     }
-    store8(dst + px * p.ldo, f);
+    __stcs(reinterpret_cast<uint4*>(dst + (long long)px * p.ldo),
+           make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7])));
+  };
+  constexpr int U = 6;
+  int px = p1 - 1 - r;
+  for (; px - (U - 1) * R >= p0; px -= U * R) {
+    uint4 raw[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) raw[u] = *reinterpret_cast<const uint4*>(src + (long long)(px - u * R) * lds);
+#pragma unroll
+    for (int u = 0; u < U; ++u) emit(raw[u], px - u * R);
   }
+  for (; px >= p0; px -= R) emit(*reinterpret_cast<const uint4*>(src + (long long)px * lds), px);
 }
 
 __global__ void gn_apply_kernel(const GnApplyArgs p) {
@@ -368,27 +388,27 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restri
 // five 16-byte vectors per lane (no idle lanes, 128-byte coalesced segments), 32 / LPR rows per warp pass.  gamma and
 // beta live in registers for the whole grid-stride loop: the per-row version above spends four parameter loads per
 // data load on them.
-template <int LPR>
-__global__ void __launch_bounds__(256) layernorm5_kernel(const __nv_bfloat16* __restrict__ x, long long ldx,
-                                                         long long rows, const float* __restrict__ gamma,
-                                                         const float* __restrict__ beta, float eps,
-                                                         const float* __restrict__ pe, int pe_rows_per_frame,
-                                                         int pe_frames, __nv_bfloat16* __restrict__ out, long long ldo) {
+template <int LPR, int MINB>
+__global__ void __launch_bounds__(256, MINB) layernorm5_kernel(const __nv_bfloat16* __restrict__ x, long long ldx,
+                                                            long long rows, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, float eps,
+                                                            const float* __restrict__ pe, int pe_rows_per_frame,
+                                                            int pe_frames, __nv_bfloat16* __restrict__ out, long long ldo) {
   constexpr int RPW = 32 / LPR;
   constexpr int C = LPR * 40;
+  // gamma / beta live in shared memory (2.5 - 10 KB): in registers they cost 80 registers per thread, i.e. ONE resident
+  // block per SM and 40 KB of loads in flight -- the kernel then sits at 40 % of the HBM peak on latency (ncu r02_ln5:
+  // 195 registers, 11.8 % warps active).  Two blocks per SM double the bytes in flight.
+  __shared__ __align__(16) float sg[C], sb[C];
+  for (int c = threadIdx.x; c < C; c += 256) {
+    sg[c] = gamma[c];
+    sb[c] = beta[c];
+  }
+  __syncthreads();
   const int lane = threadIdx.x & 31;
   const int sub = lane / LPR, l = lane % LPR;
   const long long nwarps = (long long)gridDim.x * 8;
   const long long ngroups = (rows + RPW - 1) / RPW;
-  float g[5][8], b[5][8];
-#pragma unroll
-  for (int i = 0; i < 5; ++i) {
-    const int c = (l + i * LPR) * 8;
-    const float4 g0 = *reinterpret_cast<const float4*>(gamma + c), g1 = *reinterpret_cast<const float4*>(gamma + c + 4);
-    const float4 b0 = *reinterpret_cast<const float4*>(beta + c), b1 = *reinterpret_cast<const float4*>(beta + c + 4);
-    g[i][0] = g0.x; g[i][1] = g0.y; g[i][2] = g0.z; g[i][3] = g0.w; g[i][4] = g1.x; g[i][5] = g1.y; g[i][6] = g1.z; g[i][7] = g1.w;
-    b[i][0] = b0.x; b[i][1] = b0.y; b[i][2] = b0.z; b[i][3] = b0.w; b[i][4] = b1.x; b[i][5] = b1.y; b[i][6] = b1.z; b[i][7] = b1.w;
-  }
   // two row sets per iteration (rows r and r + RPW): twice the bytes in flight for the same parameter registers
   const long long npairs = (ngroups + 1) / 2;
   for (long long grp = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); grp < npairs; grp += nwarps) {
@@ -440,10 +460,17 @@ __global__ void __launch_bounds__(256) layernorm5_kernel(const __nv_bfloat16* __
         const uint32_t w4[4] = {u[r][i].x, u[r][i].y, u[r][i].z, u[r][i].w};
         float y[8];
 #pragma unroll
+        int c = (l + i * LPR) * 8;
+        asm volatile("" : "+r"(c));     // opaque to the optimiser: or it hoists all 80 parameter loads out of the row loop again
+        const float4 g0 = *reinterpret_cast<const float4*>(sg + c), g1 = *reinterpret_cast<const float4*>(sg + c + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(sb + c), b1 = *reinterpret_cast<const float4*>(sb + c + 4);
+        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
         for (int t = 0; t < 4; ++t) {
           const float2 v = unpack_bf16(w4[t]);
-          y[2 * t] = (v.x - mean) * rstd * g[i][2 * t] + b[i][2 * t];
-          y[2 * t + 1] = (v.y - mean) * rstd * g[i][2 * t + 1] + b[i][2 * t + 1];
+          y[2 * t] = (v.x - mean) * rstd * gg[2 * t] + bb[2 * t];
+          y[2 * t + 1] = (v.y - mean) * rstd * gg[2 * t + 1] + bb[2 * t + 1];
         }
         if (perow) {
           const float4 p0 = *reinterpret_cast<const float4*>(perow + i * LPR * 8);
@@ -672,15 +699,23 @@ extern "C" int vx_layernorm(const void* x, long long ldx, long long rows, int C,
   auto st = (cudaStream_t)stream;
   if (pe && (rows_per_frame <= 0 || pe_frames <= 0)) return fail("vx_layernorm: bad pe args");
   // (with a positional-encoding row to fetch per row the one-warp-per-row kernel, with its 8x occupancy, is as fast)
-  if ((C == 320 || C == 640 || C == 1280) && !pe && ldx % 8 == 0 && ldo % 8 == 0 && !getenv("VX_LN_V1")) {
+  static const bool ln_v1 = getenv("VX_LN_V1") != nullptr;   // A/B switch, read once
+  if ((C == 320 || C == 640 || C == 1280) && !pe && ldx % 8 == 0 && ldo % 8 == 0 && !ln_v1) {
     const int lpr = C / 40;
     const long long groups = (rows + 32 / lpr - 1) / (32 / lpr);
     long long nb = ((groups + 1) / 2 + 7) / 8;
-    if (nb > 148 * 4) nb = 148 * 4;   // one 256-thread block is resident per SM (parameter registers); 4 waves balance the tail
+    static const int minb = getenv("VX_LN_BLOCKS") ? atoi(getenv("VX_LN_BLOCKS")) : 3;   // read once (A/B switch)
+    if (nb > 148 * minb * 2) nb = 148 * minb * 2;   // `minb` 256-thread blocks are resident per SM; two waves balance the tail
     if (nb < 1) nb = 1;
-#define LN5_LAUNCH(LPR)                                                                                            \
-  layernorm5_kernel<LPR><<<(unsigned)nb, 256, 0, st>>>((const __nv_bfloat16*)x, ldx, rows, gamma, beta, eps, pe,  \
-                                                       rows_per_frame, pe_frames, (__nv_bfloat16*)out, ldo)
+#define LN5_LAUNCH(LPR)                                                                                               \
+  do {                                                                                                               \
+    if (minb == 2)                                                                                                   \
+      layernorm5_kernel<LPR, 2><<<(unsigned)nb, 256, 0, st>>>((const __nv_bfloat16*)x, ldx, rows, gamma, beta, eps, pe, \
+                                                              rows_per_frame, pe_frames, (__nv_bfloat16*)out, ldo);  \
+    else                                                                                                             \
+      layernorm5_kernel<LPR, 3><<<(unsigned)nb, 256, 0, st>>>((const __nv_bfloat16*)x, ldx, rows, gamma, beta, eps, pe, \
+                                                              rows_per_frame, pe_frames, (__nv_bfloat16*)out, ldo);  \
+  } while (0)
     if (lpr == 8) LN5_LAUNCH(8);
     else if (lpr == 16) LN5_LAUNCH(16);
     else LN5_LAUNCH(32);
