@@ -1,4 +1,4 @@
-"""A/B of the flash-attention kernels on the UNet's shapes: v3 (one query tile per CTA, double-buffered S, 2 CTAs per SM; default) against
+"""A/B of the flash-attention kernels on the UNet's shapes: v4 / v3 (one query tile per CTA, double-buffered S, 2 CTAs per SM) against
 v2 (two tiles per CTA, 16 softmax warps), plus v3's knobs (share of exponentials on the FMA pipe, K/V ring depth).
 Every variant is checked against fp32 SDPA on the first shape.   usage: python profiles/tools/fa_sweep.py"""
 import os, sys, torch
@@ -6,7 +6,7 @@ import torch.nn.functional as F
 sys.path.insert(0, os.getcwd())
 from vexpress_b200 import _ffi, ops
 torch.manual_seed(0)
-KNOBS = ("VX_FA_V2", "VX_FA_POLY", "VX_FA3_STAGES", "VX_FA_NOONES")
+KNOBS = ("VX_FA_V2", "VX_FA_V3", "VX_FA_POLY", "VX_FA3_STAGES", "VX_FA_NOONES")
 
 
 def setenv(**kw):
@@ -42,9 +42,9 @@ def run(B, N, Nk, heads, hd, kv_div, label, check=False):
         vf = v.float().reshape(B // kv_div, Nk, heads, hd).transpose(1, 2).repeat_interleave(kv_div, 0)
         ref = F.scaled_dot_product_attention(qf, kf, vf).transpose(1, 2).reshape(B * N, C)
     print(label)
-    for name, kw in (("v3 (default)", {}), ("v3 poly 1/4", dict(VX_FA_POLY=4)), ("v3 poly 1/2", dict(VX_FA_POLY=2)),
-                     ("v3 no ones column", dict(VX_FA_NOONES=1)), ("v3 3 stages", dict(VX_FA3_STAGES=3)),
-                     ("v3 4 stages", dict(VX_FA3_STAGES=4)), ("v2", dict(VX_FA_V2=1))):
+    for name, kw in (("default (v4 hd<=64 / v3)", {}), ("poly 1/4", dict(VX_FA_POLY=4)), ("no ones column", dict(VX_FA_NOONES=1)),
+                     ("4 stages", dict(VX_FA3_STAGES=4)), ("v3", dict(VX_FA_V3=1)), ("v3 4 stages", dict(VX_FA_V3=1, VX_FA3_STAGES=4)),
+                     ("v2", dict(VX_FA_V2=1))):
         setenv(**kw)
         try:
             ms, o = t_ms()

@@ -31,7 +31,10 @@ def _gen(seed):
                                                     # BASELINE configs[4] (768x768: 96x96 latents): N = 9216 / 2304 / 576 / 144
                                                     (2, 9216, 8, 40, 1, 9216), (4, 9216, 8, 40, 2, 9216),
                                                     (2, 2304, 8, 80, 1, 2304), (2, 576, 8, 160, 1, 576),
-                                                    (4, 144, 8, 160, 1, 144), (4, 144, 8, 160, 2, 144)])
+                                                    (4, 144, 8, 160, 1, 144), (4, 144, 8, 160, 2, 144),
+                                                    # head dims of the 8-softmax-warp kernel (hd <= 64), incl. padded ones
+                                                    (2, 128, 4, 64, 1, 192), (1, 256, 2, 48, 1, 128), (2, 128, 8, 8, 1, 64),
+                                                    (3, 384, 8, 40, 3, 320), (2, 128, 8, 24, 1, 64)])
 def test_flash_attention(ops, B, N, heads, hd, kv_div, Nk):
     g = _gen(B * N + hd)
     C = heads * hd
