@@ -6,7 +6,7 @@ import torch.nn.functional as F
 sys.path.insert(0, os.getcwd())
 from vexpress_b200 import _ffi, ops
 torch.manual_seed(0)
-KNOBS = ("VX_FA_V2", "VX_FA_V3", "VX_FA_POLY", "VX_FA3_STAGES", "VX_FA_NOONES")
+KNOBS = ("VX_FA_V2", "VX_FA_V4", "VX_FA_POLY", "VX_FA3_STAGES", "VX_FA_NOONES", "VX_FA3_NOLOAD")
 
 
 def setenv(**kw):
@@ -42,17 +42,17 @@ def run(B, N, Nk, heads, hd, kv_div, label, check=False):
         vf = v.float().reshape(B // kv_div, Nk, heads, hd).transpose(1, 2).repeat_interleave(kv_div, 0)
         ref = F.scaled_dot_product_attention(qf, kf, vf).transpose(1, 2).reshape(B * N, C)
     print(label)
-    for name, kw in (("default (v4 hd<=64 / v3)", {}), ("poly 1/4", dict(VX_FA_POLY=4)), ("no ones column", dict(VX_FA_NOONES=1)),
-                     ("4 stages", dict(VX_FA3_STAGES=4)), ("v3", dict(VX_FA_V3=1)), ("v3 4 stages", dict(VX_FA_V3=1, VX_FA3_STAGES=4)),
-                     ("v2", dict(VX_FA_V2=1))):
+    for name, kw in (("v3 (default)", {}), ("v3 4 stages", dict(VX_FA3_STAGES=4)),
+                     ("v3, K/V traffic removed (timing experiment, wrong results)", dict(VX_FA3_NOLOAD=1)),
+                     ("v4 (8 softmax warps)", dict(VX_FA_V4=1)), ("v2", dict(VX_FA_V2=1))):
         setenv(**kw)
         try:
             ms, o = t_ms()
         except Exception as e:
-            print(f"  {name:20s} failed: {e}")
+            print(f"  {name:62s} failed: {e}")
             continue
-        err = "" if ref is None else f"  rel-L2 vs fp32 SDPA {((o.float() - ref).norm() / ref.norm()).item():.2e}"
-        print(f"  {name:20s} {ms:7.3f} ms  {flops / ms / 1e9:7.1f} TFLOP/s{err}", flush=True)
+        err = "" if (ref is None or "NOLOAD" in str(kw)) else f"  rel-L2 vs fp32 SDPA {((o.float() - ref).norm() / ref.norm()).item():.2e}"
+        print(f"  {name:62s} {ms:7.3f} ms  {flops / ms / 1e9:7.1f} TFLOP/s{err}", flush=True)
     setenv()
 
 

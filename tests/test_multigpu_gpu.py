@@ -71,6 +71,8 @@ def test_two_ranks_nccl_equals_single_gpu(L):
     pipe, _ = _build(0, L)
     lat1, vid1 = _call(pipe, L, False)
     assert got_vid.shape == vid1.shape == (1, 3, L, 128, 128)
+    d = (got_lat - lat1).abs().amax(dim=(0, 1, 3, 4))
+    print(f"L={L}: per-frame max |latents(2 ranks) - latents(1 rank)| = {[round(x, 4) for x in d.tolist()]}")
     assert torch.equal(got_lat, lat1)                       # the denoising trajectory: bit-identical
     # the decode is sharded by FRAME: a rank's batch has fewer frames, GroupNorm splits a frame into a different number of
     # partial sums (fp32 merge order) -> equal to bf16 rounding, not bitwise

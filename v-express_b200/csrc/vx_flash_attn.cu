@@ -673,6 +673,7 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
 constexpr int kFa3Threads = 192;
 
 struct Fa3Args {
+  int noload;                // experiment (VX_FA3_NOLOAD): K/V tiles are loaded for the first ring pass only -> time without K/V traffic
   int Nq, Nk, hd, hdp, kv_div, stages;
   float scale_log2;
   __nv_bfloat16* out;
@@ -764,9 +765,13 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
     for (int j = 0; j < T; ++j) {
       mbar_wait(&kv_empty[stage], phase ^ 1);
       if (leader) {
-        mbar_expect_tx(&kv_full[stage], 2 * 64 * p.hd * 2);
-        tma_load_3d(sK + stage * p.kv_bytes, &mapK, &kv_full[stage], 0, kv_row0 + j * 64, col_chunk);
-        tma_load_3d(sV + stage * p.kv_bytes, &mapV, &kv_full[stage], 0, kv_row0 + j * 64, col_chunk);
+        if (p.noload && j >= p.stages) {
+          mbar_arrive(&kv_full[stage]);          // timing experiment: reuse what the ring already holds
+        } else {
+          mbar_expect_tx(&kv_full[stage], 2 * 64 * p.hd * 2);
+          tma_load_3d(sK + stage * p.kv_bytes, &mapK, &kv_full[stage], 0, kv_row0 + j * 64, col_chunk);
+          tma_load_3d(sV + stage * p.kv_bytes, &mapV, &kv_full[stage], 0, kv_row0 + j * 64, col_chunk);
+        }
       }
       __syncwarp();
       if (++stage == p.stages) {
@@ -1273,7 +1278,7 @@ using namespace vx;
 // A/B switches (bring-up only), read ONCE per process: the launch path itself never touches the environment.
 namespace {
 struct FaEnv {
-  int v1, v2, v3, psmem, noones, stages, stagger, pairsync, latewait, baton, poly, v3_stages;
+  int v1, v2, v4, v3_noload, psmem, noones, stages, stagger, pairsync, latewait, baton, poly, v3_stages;
   long long* trace;
   static int geti(const char* n, int d) {
     const char* e = getenv(n);
@@ -1291,7 +1296,8 @@ struct FaEnv {
     baton = geti("VX_FA_BATON", 0);
     poly = geti("VX_FA_POLY", 8);
     v3_stages = geti("VX_FA3_STAGES", 0);
-    v3 = geti("VX_FA_V3", 0);
+    v4 = geti("VX_FA_V4", 0);
+    v3_noload = geti("VX_FA3_NOLOAD", 0);
     const char* t = getenv("VX_FA_TRACE");
     trace = t ? (long long*)strtoull(t, nullptr, 10) : nullptr;
   }
@@ -1328,6 +1334,7 @@ extern "C" int vx_flash_attention(const void* q, long long ldq, const void* k, l
   if (hdp <= 128 && Nq % 128 == 0 && Nk % 64 == 0 && !env.v1 && !env.v2) {
     // ---- v3: one query tile per CTA, 64 keys per step, 2-3 CTAs per SM
     Fa3Args a{};
+    a.noload = env.v3_noload;
     a.Nq = Nq; a.Nk = Nk; a.hd = hd; a.hdp = hdp; a.kv_div = kv_div;
     a.scale_log2 = 1.4426950408889634f / sqrtf((float)hd);
     a.out = (__nv_bfloat16*)out; a.ldo = ldo;
@@ -1364,8 +1371,9 @@ extern "C" int vx_flash_attention(const void* q, long long ldq, const void* k, l
     dim3 grid3(Nq / 128, heads, Bq);
     const bool ones = hdp > hd && !env.noones;
     auto st3 = (cudaStream_t)stream;
-    if (hdp <= 64 && !env.v3) {
-      // ---- v4: eight softmax warps (two independent key halves per step); scratch for the final merge lives in Q + K ring
+    if (hdp <= 64 && env.v4) {
+      // ---- v4 (A/B only: measured SLOWER than v3, 1.56 vs 1.49 ms at level 0 -- profiles/r02_flash_notes.md): eight softmax
+      // warps (two independent key halves per step); scratch for the final merge lives in Q + K ring
       VX_REQUIRE((size_t)a.q_bytes + (size_t)a.stages * a.kv_bytes >= (size_t)(256 + (hd + 1) * 128) * 4,
                  "vx_flash_attention: merge scratch does not fit (hd=%d stages=%d)", hd, a.stages);
       static bool cfg4 = false;

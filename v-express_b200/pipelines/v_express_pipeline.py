@@ -21,6 +21,7 @@ pass; they run whatever torch modules the caller registered.
 from __future__ import annotations
 
 import math
+import os
 from typing import Callable, List, Optional, Union
 
 import torch
@@ -32,6 +33,7 @@ from .context import overlap_plan, window_table
 from .scheduler import ddim_coefficients
 
 BF16 = torch.bfloat16
+_ALLREDUCE_FP32 = os.environ.get("VX_ALLREDUCE_FP32") == "1"     # A/B switch: reduce the fp32 accumulator instead of its bf16 copy
 
 
 def retrieve_timesteps(scheduler, num_inference_steps=None, device=None, timesteps=None, **kwargs):
@@ -349,9 +351,12 @@ class VExpressPipeline:
             if world > 1:
                 # every frame has at most two non-zero bf16 contributions across the ranks (its windows live on one rank
                 # or on two neighbours), so the bf16 sum is the reference's own bf16 add -- half the bytes of fp32
-                acc_x.copy_(acc)
-                torch.distributed.all_reduce(acc_x, op=torch.distributed.ReduceOp.SUM)
-                acc.copy_(acc_x)
+                if _ALLREDUCE_FP32:
+                    torch.distributed.all_reduce(acc, op=torch.distributed.ReduceOp.SUM)
+                else:
+                    acc_x.copy_(acc)
+                    torch.distributed.all_reduce(acc_x, op=torch.distributed.ReduceOp.SUM)
+                    acc.copy_(acc_x)
             sa, sb, sap, sbp = ddim_coefficients(self.scheduler, int(t))
             ops.ddim_step(lat, acc, sa, sb, sap, sbp)
             if callback is not None and i % callback_steps == 0:
