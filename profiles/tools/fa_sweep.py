@@ -6,7 +6,7 @@ import torch.nn.functional as F
 sys.path.insert(0, os.getcwd())
 from vexpress_b200 import _ffi, ops
 torch.manual_seed(0)
-KNOBS = ("VX_FA_V2", "VX_FA_V4", "VX_FA_POLY", "VX_FA3_STAGES", "VX_FA_NOONES", "VX_FA3_NOLOAD")
+KNOBS = ("VX_FA_V2", "VX_FA_POLY", "VX_FA3_STAGES", "VX_FA_NOONES", "VX_FA3_NOLOAD")
 
 
 def setenv(**kw):
@@ -44,7 +44,7 @@ def run(B, N, Nk, heads, hd, kv_div, label, check=False):
     print(label)
     for name, kw in (("v3 (default)", {}), ("v3 4 stages", dict(VX_FA3_STAGES=4)),
                      ("v3, K/V traffic removed (timing experiment, wrong results)", dict(VX_FA3_NOLOAD=1)),
-                     ("v4 (8 softmax warps)", dict(VX_FA_V4=1)), ("v2", dict(VX_FA_V2=1))):
+                     ("v3 poly 1/4", dict(VX_FA_POLY=4)), ("v2", dict(VX_FA_V2=1))):
         setenv(**kw)
         try:
             ms, o = t_ms()

@@ -871,19 +871,22 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
       const float mc = m_used * c;
       float ls[4] = {0.f, 0.f, 0.f, 0.f};
       uint32_t pk[32];
+      // Software-pipelined exponentials: the scale FMA of element k + 4 is issued between the MUFU ops of elements k and
+      // k + 1 (volatile asm pins the order).  Left alone the compiler issues all 64 FMAs (half-rate pipe: 128 clk), then
+      // 56 MUFU ops back to back (448 clk), then the packs -- with two softmax warps per sub-partition nothing hides the
+      // FMA / pack blocks, and the MUFU pipe, the binding resource, idles through them (ncu: 61 % busy).
+      {
+        float xx[64], e[64];
 #pragma unroll
-      for (int g = 0; g < 2; ++g) {
-#pragma unroll
-        for (int h = 0; h < 4; ++h) {
-          float e[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float xx = fmaf(__uint_as_float(v[g][h * 8 + i]), c, -mc);
-            e[i] = ((i & PMASK) == PMASK) ? ex2_poly(xx) : ex2_approx(xx);
-            if (!ONES) ls[i & 3] += e[i];
+        for (int k = 0; k < 64 + 4; ++k) {
+          if (k < 64) asm volatile("fma.rn.f32 %0, %1, %2, %3;" : "=f"(xx[k]) : "f"(__uint_as_float(v[k >> 5][k & 31])), "f"(c), "f"(-mc));
+          if (k >= 4) {
+            const int q = k - 4;
+            if (((q & 7) & PMASK) == PMASK) e[q] = ex2_poly(xx[q]);
+            else asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(e[q]) : "f"(xx[q]));
+            if (!ONES) ls[q & 3] += e[q];
+            if (q & 1) pk[q >> 1] = pack_bf16(e[q - 1], e[q]);
           }
-#pragma unroll
-          for (int i = 0; i < 4; ++i) pk[g * 16 + h * 4 + i] = pack_bf16(e[2 * i], e[2 * i + 1]);
         }
       }
       if (!ONES) l += (ls[0] + ls[1]) + (ls[2] + ls[3]);
@@ -937,281 +940,9 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
   }
 }
 
-// ------------------------------------------------------------------------------------------------------------
-// v4 = v3 with EIGHT softmax warps per CTA (four per SM sub-partition with the two resident CTAs) for head dims <= 64.
-// ncu of v3 at hd 40 (profiles/r02_ncu_full_notes.md): MUFU pipe 61 % busy, issue slots 47 %, warp stalls = `wait` +
-// `long_scoreboard` (tcgen05.ld / .st round trips, mbarrier try_wait): with two softmax warps per sub-partition nobody is
-// left to issue while both sit in one of those latencies.  The 64 keys of a step are split into two halves of 32 that
-// run as independent online-softmax streams (own running max, own row sum, own O accumulator in tensor memory:
-// 2 x 64 S + 2 x hdp O <= 256 columns), so the extra warps need no exchange with their row partners until the very end:
-//   warp w: lane quadrant w & 3, key half w >> 2; P(j, half) = 16 packed columns over its own S columns;
-//   P.V(j, half) = two K = 16 TS-MMAs against V rows [32 half, 32 half + 32) into O_half, issued as soon as that half's
-//   four warps have stored their P (one mbarrier per (S buffer, half));
-//   epilogue: O = (O_0 2^(m_0 - m) + O_1 2^(m_1 - m)) / (l_0 2^(m_0 - m) + l_1 2^(m_1 - m)) through shared memory.
-constexpr int kFa4Threads = 320;   // warps 0..7 softmax, 8 TMA, 9 MMA
-
-__device__ __forceinline__ void fa4_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
-
-template <bool ONES, int PMASK>
-__global__ void __maxnreg__(96)      // 2 resident CTAs x 320 threads within the 64 K registers of an SM
-flash_attn4_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
-                   const __grid_constant__ CUtensorMap mapV, const Fa3Args p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + p.q_bytes;
-  uint8_t* sV = sK + p.stages * p.kv_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + p.stages * p.kv_bytes);
-  uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;          // [<= 8]
-  uint64_t* kv_empty = kv_full + 8;      // [8]
-  uint64_t* s_full = kv_empty + 8;       // [2]
-  uint64_t* p_ready = s_full + 2;        // [2 S buffers][2 halves]
-  uint64_t* pv_done = p_ready + 4;       // [2 halves]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q_tile = blockIdx.x, head = blockIdx.y, bq = blockIdx.z;
-  const int T = p.Nk / 64;
-  if (p.hdp > p.hd) {
-    const int total16 = (p.q_bytes + 2 * p.stages * p.kv_bytes) / 16;
-    uint4* z = reinterpret_cast<uint4*>(sQ);
-    for (int i = threadIdx.x; i < total16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
-    if (ONES) {
-      __syncthreads();
-      for (int i = threadIdx.x; i < p.stages * 64; i += blockDim.x) {
-        const int st = i / 64, key = i % 64;
-        reinterpret_cast<__nv_bfloat16*>(sV + st * p.kv_bytes + (p.hd / 8) * 1024 + key * 16)[p.hd % 8] = __float2bfloat16(1.0f);
-      }
-    }
-  }
-  if (threadIdx.x == 0) {
-    mbar_init(q_full, 1);
-    for (int s = 0; s < 8; ++s) {
-      mbar_init(&kv_full[s], 1);
-      mbar_init(&kv_empty[s], 1);
-    }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&s_full[s], 1);
-      mbar_init(&p_ready[2 * s], 128);
-      mbar_init(&p_ready[2 * s + 1], 128);
-      mbar_init(&pv_done[s], 1);
-    }
-    fence_barrier_init();
-  }
-  if (warp == 9) {
-    tmem_alloc(tmem_slot, 256);
-    tmem_relinquish();
-  }
-  fence_proxy_async_smem();
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 8) {
-    // ------------------------------------------------------------ TMA producer
-    const bool leader = elect_one();
-    const int col_chunk = head * p.hd / 8;
-    const int kv_row0 = (bq / p.kv_div) * p.Nk;
-    if (leader) {
-      tma_prefetch_desc(&mapQ);
-      tma_prefetch_desc(&mapK);
-      tma_prefetch_desc(&mapV);
-      mbar_expect_tx(q_full, 128 * p.hd * 2);
-      tma_load_3d(sQ, &mapQ, q_full, 0, bq * p.Nq + q_tile * 128, col_chunk);
-    }
-    __syncwarp();
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int j = 0; j < T; ++j) {
-      mbar_wait(&kv_empty[stage], phase ^ 1);
-      if (leader) {
-        mbar_expect_tx(&kv_full[stage], 2 * 64 * p.hd * 2);
-        tma_load_3d(sK + stage * p.kv_bytes, &mapK, &kv_full[stage], 0, kv_row0 + j * 64, col_chunk);
-        tma_load_3d(sV + stage * p.kv_bytes, &mapV, &kv_full[stage], 0, kv_row0 + j * 64, col_chunk);
-      }
-      __syncwarp();
-      if (++stage == p.stages) {
-        stage = 0;
-        phase ^= 1;
-      }
-    }
-  } else if (warp == 9) {
-    // ------------------------------------------------------------ MMA issuer
-    const bool leader = elect_one();
-    const uint32_t idesc_s = make_idesc_bf16(128, 64, 0, 0);
-    const uint32_t idesc_o = make_idesc_bf16(128, (uint32_t)p.hdp, 0, 1);   // B = V is MN-major
-    const uint64_t dq = make_smem_desc(smem_u32(sQ), 2048, 128, SWZ_NONE);
-    const int ksteps = p.hdp / 16;
-    mbar_wait(q_full, 0);
-    auto issue_s = [&](int t) {
-      const int st = t % p.stages;
-      mbar_wait(&kv_full[st], (uint32_t)((t / p.stages) & 1));
-      tc_fence_after();
-      const uint64_t dk = make_smem_desc(smem_u32(sK + st * p.kv_bytes), 1024, 128, SWZ_NONE);
-      const uint32_t d_s = tmem_base + (uint32_t)((t & 1) * 64);
-      if (leader) {
-        for (int k = 0; k < ksteps; ++k)
-          umma_ss(d_s, dq + (uint64_t)(k * 256), dk + (uint64_t)(k * 128), idesc_s, k ? 1u : 0u);
-        umma_commit(&s_full[t & 1]);
-      }
-      __syncwarp();
-    };
-    issue_s(0);
-    if (T > 1) issue_s(1);
-    for (int j = 0; j < T; ++j) {
-      const int stage = j % p.stages;
-      const uint64_t dv = make_smem_desc(smem_u32(sV + stage * p.kv_bytes), 128, 1024, SWZ_NONE);
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        mbar_wait(&p_ready[2 * (j & 1) + h], (uint32_t)((j >> 1) & 1));
-        tc_fence_after();
-        const uint32_t t_p = tmem_base + (uint32_t)((j & 1) * 64 + h * 32);
-        const uint32_t d_o = tmem_base + 128u + (uint32_t)(h * p.hdp);
-        if (leader) {
-#pragma unroll
-          for (int k = 0; k < 2; ++k)   // 16 keys = 8 packed P columns; V rows 32 h + 16 k: +256 B (= +16) per 16 keys
-            umma_ts(d_o, t_p + (uint32_t)(k * 8), dv + (uint64_t)(h * 32 + k * 16), idesc_o, (j | k) ? 1u : 0u);
-          umma_commit(&pv_done[h]);
-        }
-        __syncwarp();
-      }
-      if (leader) umma_commit(&kv_empty[stage]);
-      __syncwarp();
-      if (j + 2 < T) issue_s(j + 2);
-    }
-  } else {
-    // ------------------------------------------------------------ softmax: warp = (key half, TMEM lane quadrant)
-    const int qd = warp & 3, half = warp >> 2;
-    const int row = qd * 32 + lane;
-    const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
-    const uint32_t to = tmem_base + lane_addr + 128u + (uint32_t)(half * p.hdp);
-    const uint32_t ts0 = tmem_base + lane_addr + (uint32_t)(half * 32);
-    float m_used = -INFINITY, l = 0.f;
-    const float c = p.scale_log2;
-    uint32_t v[32];
-    mbar_wait(&s_full[0], 0);
-    tc_fence_after();
-    tmem_ld32(ts0, v);
-    for (int j = 0; j < T; ++j) {
-      const uint32_t ts = ts0 + (uint32_t)((j & 1) * 64);
-      tmem_ld_wait();
-#define VX_SV(k) __uint_as_float(v[k])
-      float mxs[4] = {VX_SV(0), VX_SV(1), VX_SV(2), VX_SV(3)};
-#pragma unroll
-      for (int k = 4; k < 28; k += 8)
-#pragma unroll
-        for (int u = 0; u < 4; ++u) mxs[u] = fmax3(mxs[u], VX_SV(k + u), VX_SV(k + 4 + u));
-#pragma unroll
-      for (int u = 0; u < 4; ++u) mxs[u] = fmaxf(mxs[u], VX_SV(28 + u));
-#undef VX_SV
-      const float mx = fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3]));
-      const float m_new = fmaxf(m_used, mx);
-      const bool need = (m_new - m_used) * c > 8.0f;
-      if (__any_sync(0xffffffffu, need)) {
-        const float alpha = (m_used == -INFINITY) ? 0.f : ex2_approx((m_used - m_new) * c);
-        l *= alpha;
-        m_used = m_new;
-        if (j > 0) {
-          mbar_wait(&pv_done[half], (uint32_t)((j - 1) & 1));
-          tc_fence_after();
-          for (int cb = 0; cb < p.hdp; cb += 16) {
-            uint32_t o[16];
-            tmem_ld16(to + cb, o);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st16(to + cb, o);
-          }
-          tmem_st_wait();
-        }
-      }
-      const float mc = m_used * c;
-      float ls[4] = {0.f, 0.f, 0.f, 0.f};
-      uint32_t pk[16];
-#pragma unroll
-      for (int h = 0; h < 4; ++h) {
-        float e[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float xx = fmaf(__uint_as_float(v[h * 8 + i]), c, -mc);
-          e[i] = ((i & PMASK) == PMASK) ? ex2_poly(xx) : ex2_approx(xx);
-          if (!ONES) ls[i & 3] += e[i];
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) pk[h * 4 + i] = pack_bf16(e[2 * i], e[2 * i + 1]);
-      }
-      if (!ONES) l += (ls[0] + ls[1]) + (ls[2] + ls[3]);
-      tmem_st16(ts, pk);        // P(j, half): 32 keys = 16 packed columns over the S columns this thread has consumed
-      if (j + 1 < T) {
-        mbar_wait(&s_full[(j + 1) & 1], (uint32_t)(((j + 1) >> 1) & 1));
-        tc_fence_after();
-        tmem_ld32(ts0 + (uint32_t)(((j + 1) & 1) * 64), v);
-      }
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(&p_ready[2 * (j & 1) + half]);
-    }
-    mbar_wait(&pv_done[half], (uint32_t)((T - 1) & 1));
-    tc_fence_after();
-    if (ONES) {
-      uint32_t o[16];
-      tmem_ld16(to + (p.hd / 16) * 16, o);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 16; ++i)
-        if (i == (p.hd & 15)) l = __uint_as_float(o[i]);
-    }
-    // ---- merge the two key halves of every row.  Scratch = the Q tile + K ring (all S MMAs have completed: both halves
-    // have seen s_full of the last step), laid out [column][row] so that a warp's 32 rows hit 32 banks.
-    float* xm = reinterpret_cast<float*>(sQ);            // [2][128] running max of each half
-    float* xo = xm + 256;                                // [hd + 1][128]: O_1 scaled, then its row sum
-    xm[half * 128 + row] = m_used;
-    fa4_bar_sync();
-    const float m = fmaxf(xm[row], xm[128 + row]);
-    const float fs = ex2_approx((m_used - m) * c);       // this half's weights are 2^(s c - m_used c): rescale to the common max
-    if (half == 1) {
-      for (int cb = 0; cb < p.hdp; cb += 16) {
-        uint32_t o[16];
-        tmem_ld16(to + cb, o);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-          if (cb + i < p.hd) xo[(cb + i) * 128 + row] = __uint_as_float(o[i]) * fs;
-      }
-      xo[p.hd * 128 + row] = l * fs;
-    }
-    fa4_bar_sync();
-    if (half == 0) {
-      const float inv = 1.f / (l * fs + xo[p.hd * 128 + row]);
-      const int qrow = q_tile * 128 + row;
-      __nv_bfloat16* op = p.out + ((long long)bq * p.Nq + qrow) * p.ldo + head * p.hd;
-      for (int cb = 0; cb < p.hdp; cb += 16) {
-        uint32_t o[16];
-        tmem_ld16(to + cb, o);
-        tmem_ld_wait();
-        float f[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) f[i] = (cb + i < p.hd) ? (__uint_as_float(o[i]) * fs + xo[(cb + i) * 128 + row]) * inv : 0.f;
-#pragma unroll
-        for (int h8 = 0; h8 < 2; ++h8) {
-          if (cb + h8 * 8 < p.hd) {
-            const int b8 = h8 * 8;
-            *reinterpret_cast<uint4*>(op + cb + b8) = make_uint4(pack_bf16(f[b8], f[b8 + 1]), pack_bf16(f[b8 + 2], f[b8 + 3]),
-                                                                 pack_bf16(f[b8 + 4], f[b8 + 5]), pack_bf16(f[b8 + 6], f[b8 + 7]));
-          }
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 9) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
-  }
-}
+// (A v4 with EIGHT softmax warps per CTA -- the 64 keys of a step split into two independent 32-key online-softmax
+// streams with their own O accumulators, merged in the epilogue -- was built and measured this round: 1.56 ms vs 1.49 ms at
+// level 0, and its 2-rank run was not bit-reproducible; it was removed again.  profiles/r02_flash_notes.md has the numbers.)
 
 // Fallback for key counts the tensor-core tiling cannot express (Nk < 16 or Nk % 16 != 0, e.g. the 2x2 / 12x12
 // maps of reduced test resolutions): one warp per (batch, head, query), exact softmax, CUDA cores.
@@ -1278,7 +1009,7 @@ using namespace vx;
 // A/B switches (bring-up only), read ONCE per process: the launch path itself never touches the environment.
 namespace {
 struct FaEnv {
-  int v1, v2, v4, v3_noload, psmem, noones, stages, stagger, pairsync, latewait, baton, poly, v3_stages;
+  int v1, v2, v3_noload, psmem, noones, stages, stagger, pairsync, latewait, baton, poly, v3_stages;
   long long* trace;
   static int geti(const char* n, int d) {
     const char* e = getenv(n);
@@ -1296,7 +1027,6 @@ struct FaEnv {
     baton = geti("VX_FA_BATON", 0);
     poly = geti("VX_FA_POLY", 8);
     v3_stages = geti("VX_FA3_STAGES", 0);
-    v4 = geti("VX_FA_V4", 0);
     v3_noload = geti("VX_FA3_NOLOAD", 0);
     const char* t = getenv("VX_FA_TRACE");
     trace = t ? (long long*)strtoull(t, nullptr, 10) : nullptr;
@@ -1371,24 +1101,6 @@ extern "C" int vx_flash_attention(const void* q, long long ldq, const void* k, l
     dim3 grid3(Nq / 128, heads, Bq);
     const bool ones = hdp > hd && !env.noones;
     auto st3 = (cudaStream_t)stream;
-    if (hdp <= 64 && env.v4) {
-      // ---- v4 (A/B only: measured SLOWER than v3, 1.56 vs 1.49 ms at level 0 -- profiles/r02_flash_notes.md): eight softmax
-      // warps (two independent key halves per step); scratch for the final merge lives in Q + K ring
-      VX_REQUIRE((size_t)a.q_bytes + (size_t)a.stages * a.kv_bytes >= (size_t)(256 + (hd + 1) * 128) * 4,
-                 "vx_flash_attention: merge scratch does not fit (hd=%d stages=%d)", hd, a.stages);
-      static bool cfg4 = false;
-      if (!cfg4) {
-        VX_CHECK_CUDA(cudaFuncSetAttribute(flash_attn4_kernel<true, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
-        VX_CHECK_CUDA(cudaFuncSetAttribute(flash_attn4_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
-        VX_CHECK_CUDA(cudaFuncSetAttribute(flash_attn4_kernel<false, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
-        cfg4 = true;
-      }
-      if (ones && env.poly == 4) flash_attn4_kernel<true, 3><<<grid3, kFa4Threads, smem3, st3>>>(mQ, mK, mV, a);
-      else if (ones) flash_attn4_kernel<true, 7><<<grid3, kFa4Threads, smem3, st3>>>(mQ, mK, mV, a);
-      else flash_attn4_kernel<false, 7><<<grid3, kFa4Threads, smem3, st3>>>(mQ, mK, mV, a);
-      VX_CHECK_CUDA(cudaGetLastError());
-      return 0;
-    }
     if (ones && env.poly == 4) flash_attn3_kernel<true, 3, 2><<<grid3, kFa3Threads, smem3, st3>>>(mQ, mK, mV, a);
     else if (ones && env.poly == 2) flash_attn3_kernel<true, 1, 2><<<grid3, kFa3Threads, smem3, st3>>>(mQ, mK, mV, a);
     else if (ones) flash_attn3_kernel<true, 7, 2><<<grid3, kFa3Threads, smem3, st3>>>(mQ, mK, mV, a);
