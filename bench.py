@@ -361,6 +361,7 @@ def cpu_sample(threads=None):
     lat, kps, audio, banks = O.synth_inputs(cfg, C1_FRAMES, 64, 64, True, 42)
 
     def run():
+        """one full configs[0] pass: (t_denoise over C1_STEPS steps, t_decode of C1_FRAMES frames)"""
         with torch.no_grad():
             t0 = time.perf_counter()
             final = O.denoise(sd, cfg, lat, kps, audio, banks, C1_STEPS, 3.5, 24, 4, ref_w=0.95, audio_w=3.0)
@@ -368,7 +369,17 @@ def cpu_sample(threads=None):
             O.decode_latents(vsd, vcfg, final)
             t2 = time.perf_counter()
         return t1 - t0, t2 - t1
-    return run, threads
+
+    def run_reduced():
+        """one CFG denoise step of configs[0] + the decode of ONE frame, normalised to the units of run()"""
+        with torch.no_grad():
+            t0 = time.perf_counter()
+            final = O.denoise(sd, cfg, lat, kps, audio, banks, 1, 3.5, 24, 4, ref_w=0.95, audio_w=3.0)
+            t1 = time.perf_counter()
+            O.decode_latents(vsd, vcfg, final[:, :, :1])
+            t2 = time.perf_counter()
+        return (t1 - t0) * C1_STEPS, (t2 - t1) * C1_FRAMES
+    return run, run_reduced, threads
 
 
 C1_FRAMES, C1_STEPS = 4, 2      # BASELINE configs[0], the reference's own CPU-runnable case
@@ -382,31 +393,44 @@ def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    run, threads = cpu_sample()
-    for _ in range(args.warmup):
-        run()
-    tu = tv = 0.0
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        a, b = run()
-        tu += a
-        tv += b
-    wall = time.perf_counter() - t0
-    tu /= args.steps
-    tv /= args.steps
+    run, run_reduced, threads = cpu_sample()
+    # one COMPLETE configs[0] pass is always measured first (it is also the first warm-up).  If warm-up + timed steps of
+    # that size would exceed the time budget (the driver runs --steps 20 --warmup 5: ~15 min of host time), the remaining
+    # steps time half a pass each -- one CFG denoise step + one decoded frame -- and are scaled to the same units.
+    c1_u, c1_v = run()
+    budget = float(os.environ.get("VX_REF_BUDGET_S", 300))
+    reduced = (args.steps + args.warmup) * (c1_u + c1_v) > budget
+    step_fn = run_reduced if reduced else run
+    for _ in range(max(args.warmup - 1, 0)):
+        step_fn()
+    if args.warmup == 0 and args.steps == 1:       # the cpu_baseline leg of our arm: that first complete pass IS the sample
+        tu, tv, wall = c1_u, c1_v, c1_u + c1_v
+    else:
+        tu = tv = 0.0
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            a, b = step_fn()
+            tu += a
+            tv += b
+        wall = time.perf_counter() - t0
+        tu /= args.steps
+        tv /= args.steps
     fps_c1 = C1_FRAMES / (tu + tv)
     fps = C1_FRAMES / (25.0 / C1_STEPS * tu + tv)
-    sample = (f"per step: one full BASELINE configs[0] pass on the host (512x512, {C1_FRAMES} frames, {C1_STEPS} DDIM steps, CFG 3.5, "
-              f"fp32): denoise {tu:.2f}s + VAE decode of {C1_FRAMES} frames {tv:.2f}s = {fps_c1:.4f} frames/s measured; "
-              f"25-step figure = {C1_FRAMES}/(12.5*t_denoise + t_decode)")
+    what = ("one CFG denoise step of configs[0] + the VAE decode of one frame (x2 / x4 to the units of a pass)" if reduced else
+            "one full BASELINE configs[0] pass")
+    sample = (f"first a complete configs[0] pass on the host (512x512, {C1_FRAMES} frames, {C1_STEPS} DDIM steps, CFG 3.5, fp32): "
+              f"denoise {c1_u:.2f}s + decode {c1_v:.2f}s; then per step: {what}: denoise {tu:.2f}s + decode {tv:.2f}s per pass = "
+              f"{fps_c1:.4f} frames/s at configs[0]; 25-step figure = {C1_FRAMES}/(12.5*t_denoise + t_decode)")
     cfgw = workload_config(args.gpus)
     cfgw["extrapolated_from"] = (f"measured configs[0] pass ({C1_FRAMES} frames, {C1_STEPS} DDIM steps) scaled to 25 steps; a full "
                                  "configs[1] pass on the host takes ~30 min")
     line = dict(metric="frames_per_sec_512x512_25step", value=fps, unit="frames/s", n_gpus=args.gpus, steps=args.steps,
                 warmup=args.warmup, ms_per_step=wall / args.steps * 1e3, higher_is_better=True, scaling="weak",
                 vs_baseline=None, dtype="f32", data="synthetic", impl="reference", config=cfgw,
-                c1_measured=dict(seconds_per_pass=tu + tv, denoise_s=tu, vae_decode_s=tv, frames_per_s=fps_c1,
-                                 frames=C1_FRAMES, ddim_steps=C1_STEPS),
+                c1_measured=dict(seconds_per_pass=c1_u + c1_v, denoise_s=c1_u, vae_decode_s=c1_v,
+                                 frames_per_s=C1_FRAMES / (c1_u + c1_v), frames=C1_FRAMES, ddim_steps=C1_STEPS,
+                                 timed_steps_use="half passes (1 denoise step + 1 frame decode)" if reduced else "full passes"),
                 cpu_baseline=dict(value=fps, unit="frames/s", cores=threads, kind="port", sample=sample),
                 e2e=dict(value=fps, unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 unet_ms_per_step=tu / C1_STEPS * 1e3 * (16 / C1_FRAMES))
