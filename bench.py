@@ -174,8 +174,8 @@ def op_table(pipe, host, L, h, which="unet"):
     during an eager forward is replayed 8x back-to-back and timed with CUDA events (so host launch overhead overlaps)."""
     from vexpress_b200 import ops
     recs = []
-    names = ["gemm", "conv3x3", "flash_attention", "temporal_attention", "smallkv_attention", "groupnorm", "layernorm",
-             "conv_in", "conv_out", "im2col_s2", "upsample2x", "skinny_linear", "timestep_embed", "softmax_rows"]
+    names = ["gemm", "gemm_ln", "conv3x3", "upconv3x3", "flash_attention", "temporal_attention", "smallkv_attention", "groupnorm",
+             "layernorm", "conv_in", "conv_out", "im2col_s2", "upsample2x", "skinny_linear", "timestep_embed", "softmax_rows"]
     orig = {n: getattr(ops, n) for n in names}
 
     def wrap(n, fn):
@@ -239,8 +239,8 @@ def kernel_roofline(pipe, host, L, h):
     CUDA events on the launching stream; achieved = sum(2*M*N*K) / sum(duration)."""
     from vexpress_b200 import ops
     recs = []
-    orig = dict(gemm=ops.gemm, conv3x3=ops.conv3x3, flash_attention=ops.flash_attention, upconv3x3=ops.upconv3x3,
-                groupnorm=ops.groupnorm, layernorm=ops.layernorm)
+    orig = dict(gemm=ops.gemm, gemm_ln=ops.gemm_ln, conv3x3=ops.conv3x3, flash_attention=ops.flash_attention,
+                upconv3x3=ops.upconv3x3, groupnorm=ops.groupnorm, layernorm=ops.layernorm)
 
     def timed(name, fn, flops_of):
         def w(*a, **k):
@@ -273,6 +273,7 @@ def kernel_roofline(pipe, host, L, h):
         return 2.0 * (a[0].numel() + (x2.numel() if x2 is not None else 0)) + 2.0 * out.numel()
 
     ops.gemm = timed("gemm", orig["gemm"], f_gemm)
+    ops.gemm_ln = timed("gemm", orig["gemm_ln"], f_gemm)     # LayerNorm -> Linear in one launch: the GEMM's FLOPs
     ops.conv3x3 = timed("conv3x3", orig["conv3x3"], f_conv)
     ops.upconv3x3 = timed("conv3x3", orig["upconv3x3"], f_upconv)
     ops.flash_attention = timed("flash", orig["flash_attention"], f_fa)

@@ -44,6 +44,16 @@ int vx_gemm_lnfold_bf16(const void* A, long long lda, int K, const void* Wt, lon
                         float scale, const void* residual, long long ldr, void* out, long long ldc, int geglu,
                         int block_n, void* stream);
 
+/* nn.LayerNorm -> nn.Linear in ONE kernel for K <= 512 (the UNet's 320-wide level): same folded parameters as
+ * vx_gemm_lnfold_bf16, but the (mean, rstd) of a row tile are computed inside the kernel from the shared-memory resident
+ * 128 x K tile of A (two-pass variance, eps as nn.LayerNorm), which also serves every column tile of that row tile, so
+ * only W streams through the TMA ring.  Neither LayerNorm(A) nor a statistics array is written to HBM.  Replaces the
+ * norm1/norm1_5/norm2/norm3 -> to_q/to_k/to_v/ff.net.0 pairs of modules/attention.py:329-375 and the norms -> qkv / ff_norm
+ * -> ff pairs of modules/motion_module.py:228-234,300-321 at K = 320. */
+int vx_gemm_ln_bf16(const void* A, long long lda, int K, const void* Wt, long long ldw, int M, int N,
+                    const float* colsum, const float* bias, float eps, const float* bias2, int bias2_div, float scale,
+                    const void* residual, long long ldr, void* out, long long ldc, int geglu, int block_n, void* stream);
+
 /* ---- tcgen05 implicit-GEMM 3x3 convolution, stride 1, pad 1, NHWC.  X [NB,H,W,C]; W [Cout, 9*C].
  * Replaces InflatedConv3d / nn.Conv2d 3x3 (modules/resnet.py:9-17,165-167,194-196; Upsample3D conv :51) and the
  * VAE decoder convs (diffusers AutoencoderKL).  bias2 = per-sample bias (time embedding,

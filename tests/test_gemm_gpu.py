@@ -49,18 +49,24 @@ def test_gemm_epilogue_and_splitk(ops):
 
 @pytest.mark.parametrize("NB,H,W,C,Cout", [(2, 64, 64, 64, 64), (4, 32, 32, 128, 256), (4, 16, 16, 256, 320),
                                            (6, 8, 8, 128, 128), (32, 64, 64, 320, 320), (1, 256, 256, 128, 128),
-                                           (2, 8, 8, 2560, 1280)])
+                                           (2, 8, 8, 2560, 1280),
+                                           # row-reuse staging (tile = 2 / 4 / 8 whole image rows of one frame)
+                                           (3, 32, 32, 640, 640), (2, 16, 16, 1280, 1280), (1, 64, 64, 960, 320),
+                                           (5, 16, 16, 256, 64), (2, 64, 64, 512, 512)])
 def test_conv3x3(ops, NB, H, W, C, Cout):
     g = torch.Generator(device="cuda").manual_seed(NB * H + C)
     x = torch.randn(NB, H, W, C, device="cuda", generator=g).bfloat16()
     w = (torch.randn(Cout, C, 3, 3, device="cuda", generator=g) / (9 * C) ** 0.5).bfloat16()
     bias = torch.randn(Cout, device="cuda", generator=g)
+    res = torch.randn(NB * H * W, Cout, device="cuda", generator=g).bfloat16()
     out = ops.conv3x3(x, ops.pack_conv3x3_weight(w), bias)
+    out_r = ops.conv3x3(x, ops.pack_conv3x3_weight(w), bias, residual=res, scale=0.5)
     ref = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2).float(), w.float(), bias, padding=1)
     ref = ref.permute(0, 2, 3, 1).reshape(-1, Cout)
     err = _rel(out, ref)
-    print(f"conv {NB}x{H}x{W}x{C}->{Cout} rel={err:.3e}")
-    assert err < 5e-3
+    err_r = _rel(out_r, ref * 0.5 + res.float())
+    print(f"conv {NB}x{H}x{W}x{C}->{Cout} rel={err:.3e} (+scale, residual: {err_r:.3e})")
+    assert err < 5e-3 and err_r < 5e-3
 
 
 @pytest.mark.parametrize("M,C", [(1024, 64), (4096, 320), (2048, 1280), (300, 128)])

@@ -208,6 +208,8 @@ def _cpu_engine(cls, model):
 class _ShapeOps:
     """Stands in for vexpress_b200.ops: checks operand shapes like the real wrappers and returns empty outputs."""
 
+    LN_GEMM_MAX_K = 512
+
     def __init__(self):
         self.calls = []
 
@@ -218,6 +220,15 @@ class _ShapeOps:
             self.calls.append(op)
             if op == "row_stats":
                 return torch.zeros(a[0].shape[0], 2)
+            if op == "gemm_ln":
+                x, wf, cs, bf, eps = a[:5]
+                M, K = x.shape
+                N = wf.shape[0]
+                assert wf.shape[1] == K and cs.shape == (N,) and bf.shape == (N,) and eps == 1e-5
+                assert K % 64 == 0 and K <= self.LN_GEMM_MAX_K
+                if k.get("bias2") is not None:
+                    assert k["bias2"].shape == (M // k["bias2_div"], N) and M % k["bias2_div"] == 0
+                return torch.zeros(M, N // 2 if k.get("geglu") else N)
             if op == "gemm_lnfold":
                 x, wf, st, cs, bf = a[:5]
                 M, K = x.shape
@@ -283,15 +294,16 @@ class _ShapeOps:
         return f
 
 
-@pytest.mark.parametrize("fold", ["0", "1"])
-def test_transformer_block_schedules_dry_run(monkeypatch, fold):
-    """Host logic of UNetEngine._spatial / _motion with shape-checking fake ops: the default schedule and the
-    VX_LN_FOLD=1 one (every LayerNorm -> Linear pair becomes row_stats + gemm_lnfold, incl. the positional-encoding
-    bias of the motion modules) run through without touching a GPU."""
+@pytest.mark.parametrize("fold,one_kernel", [("0", "0"), ("1", "0"), ("0", "1")])
+def test_transformer_block_schedules_dry_run(monkeypatch, fold, one_kernel):
+    """Host logic of UNetEngine._spatial / _motion with shape-checking fake ops, without touching a GPU: the three
+    LayerNorm -> Linear schedules -- LayerNorm kernel + GEMM (VX_LN_GEMM=0), row_stats + gemm_lnfold (VX_LN_FOLD=1), and the
+    default one-kernel gemm_ln for K <= 512 (incl. the positional-encoding bias of the motion modules)."""
     import torch
     from oracle import vx_oracle as O
     from vexpress_b200.modules import UNet3DConditionModel, unet_3d
     monkeypatch.setenv("VX_LN_FOLD", fold)
+    monkeypatch.setenv("VX_LN_GEMM", one_kernel)
     cfg = O.small_cfg()
     m = UNet3DConditionModel(
         block_out_channels=cfg["block_out_channels"], cross_attention_dim=cfg["cross_attention_dim"],
@@ -302,7 +314,7 @@ def test_transformer_block_schedules_dry_run(monkeypatch, fold):
                                   temporal_attention_dim_div=1))
     m.load_state_dict(O.synth_state_dict(O.unet_param_shapes(cfg), 1234), strict=True)
     eng = _cpu_engine(unet_3d.UNetEngine, m.to(torch.bfloat16))
-    assert eng.ln_fold == (fold == "1") and len(eng.F) == (127 if fold == "1" else 0)
+    assert eng.ln_fold == (fold == "1") and len(eng.F) == (127 if "1" in (fold, one_kernel) else 0)
     fake = _ShapeOps()
     monkeypatch.setattr(unet_3d, "ops", fake)
     C, HW, f, b = 64, 256, 4, 2
@@ -313,7 +325,9 @@ def test_transformer_block_schedules_dry_run(monkeypatch, fold):
     assert eng._spatial("down_blocks.0.attentions.0", x, NB, HW, f, enc).shape == x.shape
     assert eng._motion("down_blocks.0.motion_modules.0", x, NB, HW, b, f).shape == x.shape
     n_ln = 7                                   # norm1, norm1_5, norm2, norm3 + norms.0, norms.1, ff_norm
-    if fold == "1":
+    if one_kernel == "1":
+        assert fake.calls.count("gemm_ln") == n_ln and not {"layernorm", "row_stats", "gemm_lnfold"} & set(fake.calls)
+    elif fold == "1":
         assert fake.calls.count("row_stats") == n_ln and fake.calls.count("gemm_lnfold") == n_ln
         assert "layernorm" not in fake.calls
     else:
@@ -570,6 +584,11 @@ class _EmuOps:
             acc = acc + residual.float()
         return self._ret(acc.to(torch.bfloat16), out)
 
+    def gemm_ln(self, a, wf, colsum, bias, eps=1e-5, **k):
+        """vx_gemm_ln_bf16: the statistics come from the same bf16 rows the GEMM multiplies (two-pass variance)."""
+        assert a.shape[1] % 64 == 0 and a.shape[1] <= self.real.LN_GEMM_MAX_K
+        return self.gemm_lnfold(a, wf, self.row_stats(a, eps), colsum, bias, **k)
+
 
 import torch  # noqa: E402  (used by the emulation above)
 
@@ -602,15 +621,16 @@ def test_prologue_modules_compose_correctly(monkeypatch, golden_dir):
     assert ya.shape == a["tokens"].shape and rel(ya, a["tokens"]) < 2e-2, rel(ya, a["tokens"])
 
 
-@pytest.mark.parametrize("fold", ["0", "1"])
-def test_unet_engine_matches_oracle_with_emulated_kernels(monkeypatch, golden_dir, fold):
+@pytest.mark.parametrize("fold,one_kernel", [("0", "0"), ("1", "0"), ("0", "1")])
+def test_unet_engine_matches_oracle_with_emulated_kernels(monkeypatch, golden_dir, fold, one_kernel):
     """The whole UNetEngine.forward_frames host schedule (weight packing, split-K concat, time-embedding bias, banks,
     CFG uncond-half skip, GEGLU packing, ...) with every kernel replaced by a functional CPU emulation, against the
-    oracle -- in the default mode and with VX_LN_FOLD=1 (LayerNorm folded into the GEMM epilogue, positional encoding
-    as a per-frame bias)."""
+    oracle -- with the LayerNorm kernel, with VX_LN_FOLD=1 (LayerNorm folded into the GEMM epilogue, positional encoding
+    as a per-frame bias) and with the default one-kernel LayerNorm GEMM."""
     from oracle import vx_oracle as O
     from vexpress_b200.modules import ReferenceAttentionControl, UNet3DConditionModel, unet_3d
     monkeypatch.setenv("VX_LN_FOLD", fold)
+    monkeypatch.setenv("VX_LN_GEMM", one_kernel)
     cfg = O.small_cfg()
     m = UNet3DConditionModel(
         block_out_channels=cfg["block_out_channels"], cross_attention_dim=cfg["cross_attention_dim"],
@@ -640,7 +660,7 @@ def test_unet_engine_matches_oracle_with_emulated_kernels(monkeypatch, golden_di
     with torch.no_grad():
         ref = O.unet_forward(sd, cfg, x, 499, enc, kps, banks, 0.95, 3.0)
     err = ((out - ref).norm() / ref.norm()).item()
-    print(f"emulated engine vs oracle (VX_LN_FOLD={fold}): rel-L2 {err:.3e}")
+    print(f"emulated engine vs oracle (VX_LN_FOLD={fold}, VX_LN_GEMM={one_kernel}): rel-L2 {err:.3e}")
     assert err < 3e-2, err
 
 

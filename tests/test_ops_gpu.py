@@ -54,7 +54,54 @@ def test_flash_attention(ops, B, N, heads, hd, kv_div, Nk):
     torch.cuda.synchronize()
     err = _rel(out, ref)
     print(f"flash B={B} N={N} hd={hd} kv_div={kv_div} Nk={Nk} rel={err:.3e} nan={torch.isnan(out.float()).any().item()}")
-    assert err < 1e-2, err
+    # bf16 P and bf16 output put a correct kernel at 2.3e-3 on this data; the hd 80 ordering hazard of round 2 (S(t) issued
+    # behind a P.V(t-2) that had not completed) sat at 5e-3 .. 8e-3 -- under the 1e-2 this assertion used to allow
+    assert err < 4e-3, err
+
+
+@pytest.mark.parametrize("B,N,heads,hd", [(8, 1024, 8, 80), (4, 1024, 8, 96), (2, 4096, 8, 40), (4, 1024, 8, 64), (2, 2048, 8, 128),
+                                          (4, 256, 8, 160)])
+def test_flash_attention_is_deterministic(ops, B, N, heads, hd):
+    """Identical inputs -> identical bits, run after run, with unrelated kernels in between (a tensor-memory or ring race shows
+    up as run-to-run differences long before it moves the error against fp32 past a tolerance)."""
+    g = torch.Generator(device="cuda").manual_seed(B * N + hd)
+    C = heads * hd
+    qkv = torch.randn(B * N, 3 * C, device="cuda", generator=g).bfloat16()
+    first = None
+    for i in range(12):
+        out = ops.flash_attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], heads, N, N)
+        if i % 2 == 0:
+            torch.empty(1 << 24, device="cuda").normal_()
+        if first is None:
+            first = out.clone()
+        else:
+            assert torch.equal(out, first), f"run {i} differs from run 0 by {(out.float() - first.float()).abs().max().item():.3e}"
+
+
+@pytest.mark.parametrize("B,N,heads,hd", [(2, 128, 4, 40), (2, 256, 4, 40), (2, 1024, 4, 40), (2, 1024, 4, 64), (2, 128, 4, 80),
+                                          (2, 1024, 4, 80), (2, 1024, 2, 128)])
+def test_flash_attention_with_a_late_mma_warp(ops, B, N, heads, hd, monkeypatch):
+    """Fault injection (bring-up switch VX_FA3_DBG bit 5): the MMA warp idles 3000 clocks in front of every P.V, so the
+    softmax warps run as far ahead of the tensor core as the protocol lets them.  Every wait in the kernel must still mean what
+    it says -- round 2's first v3 read O after a parity wait that had silently skipped a phase in exactly this situation
+    (which the K/V-load-bound hd 80 shape produced on its own)."""
+    from vexpress_b200 import _ffi
+    g = torch.Generator(device="cuda").manual_seed(N + hd)
+    C = heads * hd
+    qkv = torch.randn(B * N, 3 * C, device="cuda", generator=g).bfloat16()
+    ref = F.scaled_dot_product_attention(*[qkv[:, i * C:(i + 1) * C].float().view(B, N, heads, hd).transpose(1, 2) for i in range(3)])
+    ref = ref.transpose(1, 2).reshape(B * N, C)
+    errs = {}
+    try:
+        for dbg in ("0", "32", "34"):      # 34: additionally every S(t) completes before anything else is issued
+            monkeypatch.setenv("VX_FA3_DBG", dbg)
+            _ffi.lib().vx_flash_reload_env()
+            errs[dbg] = _rel(ops.flash_attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], heads, N, N), ref)
+    finally:
+        monkeypatch.delenv("VX_FA3_DBG")
+        _ffi.lib().vx_flash_reload_env()
+    print(f"flash hd={hd} N={N}: rel err normal {errs['0']:.3e}, MMA warp delayed {errs['32']:.3e}, delayed + serialised {errs['34']:.3e}")
+    assert max(errs.values()) < 4e-3, errs
 
 
 def test_flash_attention_zero_kv(ops):

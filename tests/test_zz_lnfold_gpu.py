@@ -48,6 +48,57 @@ def test_gemm_lnfold_matches_layernorm_then_linear(M, K, N, geglu, residual):
     assert err < 6e-3, err
 
 
+@pytest.mark.parametrize("M,K,N,geglu,residual,pe", [(4096, 320, 960, False, False, False), (4096, 320, 320, False, False, False),
+                                                     (2048, 320, 2560, True, False, False), (4096, 320, 960, False, False, True),
+                                                     (1000, 320, 960, False, True, False), (384, 320, 320, False, False, False),
+                                                     (128, 320, 960, False, False, False), (100, 64, 64, False, False, False),
+                                                     (2048, 512, 1024, False, True, False), (3072, 128, 512, True, False, False),
+                                                     (40960, 320, 960, False, False, False), (20000, 320, 2560, True, False, False)])
+def test_gemm_ln_matches_layernorm_then_linear(M, K, N, geglu, residual, pe):
+    """vx_gemm_ln_bf16: LayerNorm -> Linear with the row tile resident in shared memory and the statistics computed in the
+    kernel; against fp32 torch and, bit for bit run to run, against itself (row tiles walk all their column tiles: one, two
+    and many row-tile groups per CTA pair, odd row-tile counts, ragged last tile, the single-CTA path at M <= 128)."""
+    from vexpress_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(M + K + N)
+    x = (torch.randn(M, K, device="cuda", generator=g) * 2 + 0.7).bfloat16()
+    x[::7] *= 8.0           # rows of very different scale: the statistics are per row
+    x[3::11] += 30.0        # large mean against the spread: E[x^2] - mean^2 would lose bits here, the two-pass form does not
+    w = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).bfloat16()
+    b = torch.randn(N, device="cuda", generator=g)
+    gamma = 1 + 0.1 * torch.randn(K, device="cuda", generator=g)
+    beta = 0.1 * torch.randn(K, device="cuda", generator=g)
+    res = torch.randn(M, N, device="cuda", generator=g).bfloat16() if residual else None
+    f_, rows = 16, 64
+    bias2 = torch.randn((M + rows - 1) // rows, N, device="cuda", generator=g) if pe else None
+    wf, cs, bf = ops.fold_layernorm(w, b, gamma, beta, geglu=geglu)
+    out = ops.gemm_ln(x, wf, cs, bf, 1e-5, bias2=bias2, bias2_div=rows, residual=res, geglu=geglu)
+    ref = F.layer_norm(x.float(), (K,), gamma, beta, 1e-5) @ w.float().t() + b
+    if pe:
+        ref = ref + bias2.repeat_interleave(rows, 0)[:M]
+    if geglu:
+        h, gate = ref.chunk(2, dim=-1)
+        ref = h * F.gelu(gate)
+    if residual:
+        ref = ref + res.float()
+    err = _rel(out, ref)
+    # the two-kernel path on the same data, for scale
+    n = ops.layernorm(x, gamma, beta)
+    if geglu:
+        wg, bg, _ = ops.pack_geglu(w, b)
+        two = ops.gemm(n, wg, bg, geglu=True)
+    else:
+        two = ops.gemm(n, w, b, residual=res)
+        if pe:
+            two = None
+    e2 = _rel(two, ref) if two is not None else float("nan")
+    print(f"gemm_ln M={M} K={K} N={N} geglu={geglu} res={residual} pe={pe}: rel={err:.3e} (layernorm kernel + gemm: {e2:.3e})")
+    assert err < 6e-3, err
+    for _ in range(3):
+        torch.empty(1 << 22, device="cuda").normal_()
+        again = ops.gemm_ln(x, wf, cs, bf, 1e-5, bias2=bias2, bias2_div=rows, residual=res, geglu=geglu)
+        assert torch.equal(again, out)
+
+
 def test_unet_with_ln_fold_vs_oracle(golden_dir, monkeypatch):
     """Whole small UNet with VX_LN_FOLD=1 against the fp32 oracle on the same bf16-rounded weights: same bound as the
     default LayerNorm-kernel path (two bf16 evaluation orders of the same network sit ~sqrt(2) x 1.6e-2 apart from each

@@ -673,6 +673,7 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
 constexpr int kFa3Threads = 192;
 
 struct Fa3Args {
+  int dbg;                   // bring-up switches (VX_FA3_DBG), see the kernel
   int noload;                // experiment (VX_FA3_NOLOAD): K/V tiles are loaded for the first ring pass only -> time without K/V traffic
   int Nq, Nk, hd, hdp, kv_div, stages;
   float scale_log2;
@@ -703,8 +704,9 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
   uint64_t* kv_empty = kv_full + 8;      // [8]
   uint64_t* s_full = kv_empty + 8;       // [2]
   uint64_t* p_ready = s_full + 2;        // [2]
-  uint64_t* pv_done = p_ready + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
+  uint64_t* pv_done = p_ready + 2;       // one phase per step: P.V(j) complete
+  uint64_t* o_full = pv_done + 1;        // single phase: the LAST P.V complete -> O final
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q_tile = blockIdx.x, head = blockIdx.y, bq = blockIdx.z;
@@ -734,6 +736,7 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
       mbar_init(&p_ready[s], 128);
     }
     mbar_init(pv_done, 1);
+    mbar_init(o_full, 1);
     fence_barrier_init();
   }
   if (warp == 5) {
@@ -787,8 +790,11 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
     const uint64_t dq = make_smem_desc(smem_u32(sQ), 2048, 128, SWZ_NONE);
     const int ksteps = p.hdp / 16;
     mbar_wait(q_full, 0);
-    // S(t) = Q K_t^T into S buffer t & 1.  Tensor-core operations of one CTA execute in issue order, so S(t) -- issued
-    // after P.V(t-2) -- overwrites that buffer only once P(t-2) has been consumed out of it.
+    // S(t) = Q K_t^T into S buffer t & 1, the buffer P(t-2) was stored into: S(t) is issued once P.V(t-2) has COMPLETED
+    // (pv_done), not merely been issued -- S (D = S buffer, N = 64) and P.V (D = O, N = hdp, A = P in tensor memory) differ in
+    // accumulator and shape, and only same-accumulator, same-shape MMAs are documented to execute in issue order.  The wait
+    // costs nothing measurable (the softmax of step t - 1 runs in between) and also pins pv_done's phase for the softmax
+    // warps' parity wait below.
     auto issue_s = [&](int t) {
       const int st = t % p.stages;
       mbar_wait(&kv_full[st], (uint32_t)((t / p.stages) & 1));
@@ -801,6 +807,7 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
         umma_commit(&s_full[t & 1]);
       }
       __syncwarp();
+      if (p.dbg & 2) mbar_wait(&s_full[t & 1], (uint32_t)((t >> 1) & 1));   // S(t) complete before anything else is issued
     };
     issue_s(0);
     if (T > 1) issue_s(1);
@@ -808,17 +815,31 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
       const int stage = j % p.stages;
       mbar_wait(&p_ready[j & 1], (uint32_t)((j >> 1) & 1));
       tc_fence_after();
+      if (p.dbg & 32) {   // bring-up: let the P stores settle
+        const long long t0 = clock64();
+        while (clock64() - t0 < 3000) {
+        }
+      }
       const uint64_t dv = make_smem_desc(smem_u32(sV + stage * p.kv_bytes), 128, 1024, SWZ_NONE);
       const uint32_t t_p = tmem_base + (uint32_t)((j & 1) * 64);
       if (leader) {
 #pragma unroll
         for (int k = 0; k < 4; ++k)   // A = P from tensor memory (8 packed columns per 16 keys); V: +256 B (= +16) per 16 keys
           umma_ts(tmem_o, t_p + (uint32_t)(k * 8), dv + (uint64_t)(k * 16), idesc_o, (j | k) ? 1u : 0u);
-        umma_commit(&kv_empty[stage]);
+        if (p.dbg & 16) {   // bring-up: release the K/V stage one step late (after P.V(j), free the stage of step j - 1)
+          if (j > 0) umma_commit(&kv_empty[(j - 1) % p.stages]);
+          if (j == T - 1) umma_commit(&kv_empty[stage]);
+        } else {
+          umma_commit(&kv_empty[stage]);
+        }
         umma_commit(pv_done);
+        if (j == T - 1) umma_commit(o_full);
       }
       __syncwarp();
-      if (j + 2 < T) issue_s(j + 2);
+      if (j + 2 < T) {
+        mbar_wait(pv_done, (uint32_t)(j & 1));   // P(j) has been consumed out of S buffer j & 1
+        issue_s(j + 2);
+      }
     }
   } else {
     // ------------------------------------------------------------ softmax: warp = TMEM lane quadrant, thread = query row
@@ -836,7 +857,17 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
     tmem_ld32(tmem_base + lane_addr + 32, v[1]);
     for (int j = 0; j < T; ++j) {
       const uint32_t ts = tmem_base + lane_addr + (uint32_t)((j & 1) * 64);
+      if ((p.dbg & 1) && j > 0) {   // no prefetch: S(j) is loaded here
+        mbar_wait(&s_full[j & 1], (uint32_t)((j >> 1) & 1));
+        tc_fence_after();
+        tmem_ld32(ts, v[0]);
+        tmem_ld32(ts + 32, v[1]);
+      }
       tmem_ld_wait();
+      if ((p.dbg & 4) && j > 0) {
+        mbar_wait(pv_done, (uint32_t)((j - 1) & 1));
+        tc_fence_after();
+      }
       // row max of the 64 scores: 3-input max (sm_100), four independent chains
 #define VX_SV(k) __uint_as_float(v[(k) >> 5][(k) & 31])
       float mxs[4] = {VX_SV(0), VX_SV(1), VX_SV(2), VX_SV(3)};
@@ -855,7 +886,9 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
         l *= alpha;
         m_used = m_new;
         if (j > 0) {
-          mbar_wait(pv_done, (uint32_t)((j - 1) & 1));   // P.V(j-1) has landed in O
+          // P.V(j-1) has landed in O.  The parity is unambiguous here: S(j), which this thread has already seen complete,
+          // was issued after P.V(j-2) had completed, so pv_done is in phase j - 1 or j.
+          mbar_wait(pv_done, (uint32_t)((j - 1) & 1));
           tc_fence_after();
           for (int cb = 0; cb < p.hdp; cb += 16) {
             uint32_t o[16];
@@ -890,7 +923,11 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
       }
       if (!ONES) l += (ls[0] + ls[1]) + (ls[2] + ls[3]);
       tmem_st32(ts, pk);        // P(j): 64 keys = 32 packed columns over the S columns this thread has consumed
-      if (j + 1 < T) {          // S(j+1) was issued an iteration ago: normally complete, the wait is a formality
+      if (p.dbg & 8) {
+        tmem_st_wait();
+        tc_fence_before();
+      }
+      if (j + 1 < T && !(p.dbg & 1)) {          // S(j+1) was issued an iteration ago: normally complete, the wait is a formality
         mbar_wait(&s_full[(j + 1) & 1], (uint32_t)(((j + 1) >> 1) & 1));
         tc_fence_after();
         const uint32_t tn = tmem_base + lane_addr + (uint32_t)(((j + 1) & 1) * 64);
@@ -901,7 +938,11 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
       tc_fence_before();
       mbar_arrive(&p_ready[j & 1]);
     }
-    mbar_wait(pv_done, (uint32_t)((T - 1) & 1));
+    // The last P.V has its own single-phase barrier.  (Waiting for phase T - 1 of pv_done by parity is only meaningful when
+    // that barrier is at most ONE phase behind; a thread that has stored P(T-1) only knows that P.V(T-3) has completed, so
+    // with a late MMA warp the parity test passed while P.V(T-2) was still pending and O was read half-accumulated: the
+    // run-to-run differences at hd >= 80, where the K/V loads keep the MMA warp waiting -- profiles/r02_flash_notes.md 5.)
+    mbar_wait(o_full, 0);
     tc_fence_after();
     const int qrow = q_tile * 128 + row;
     __nv_bfloat16* op = p.out + ((long long)bq * p.Nq + qrow) * p.ldo + head * p.hd;
@@ -1008,7 +1049,7 @@ using namespace vx;
 // A/B switches (bring-up only), read ONCE per process: the launch path itself never touches the environment.
 namespace {
 struct FaEnv {
-  int v1, v2, v3_noload, psmem, noones, stages, stagger, pairsync, latewait, baton, poly, v3_stages;
+  int v1, v2, v3_noload, v3_dbg, psmem, noones, stages, stagger, pairsync, latewait, baton, poly, v3_stages;
   long long* trace;
   static int geti(const char* n, int d) {
     const char* e = getenv(n);
@@ -1027,6 +1068,7 @@ struct FaEnv {
     poly = geti("VX_FA_POLY", 8);
     v3_stages = geti("VX_FA3_STAGES", 0);
     v3_noload = geti("VX_FA3_NOLOAD", 0);
+    v3_dbg = geti("VX_FA3_DBG", 0);
     const char* t = getenv("VX_FA_TRACE");
     trace = t ? (long long*)strtoull(t, nullptr, 10) : nullptr;
   }
@@ -1064,6 +1106,7 @@ extern "C" int vx_flash_attention(const void* q, long long ldq, const void* k, l
     // ---- v3: one query tile per CTA, 64 keys per step, 2-3 CTAs per SM
     Fa3Args a{};
     a.noload = env.v3_noload;
+    a.dbg = env.v3_dbg;
     a.Nq = Nq; a.Nk = Nk; a.hd = hd; a.hdp = hdp; a.kv_div = kv_div;
     a.scale_log2 = 1.4426950408889634f / sqrtf((float)hd);
     a.out = (__nv_bfloat16*)out; a.ldo = ldo;

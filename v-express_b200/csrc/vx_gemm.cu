@@ -27,6 +27,7 @@ namespace vx {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
 constexpr int kThreads = 352;   // + warp 10: TMA-store / residual-prefetch warp
+constexpr int kStatThreads = 128;   // LNF instantiations: + warps 11..14, row statistics of the resident A tile (`ares`)
 constexpr int kEpiThreads = 256;
 constexpr int kPanelCols = 32;                         // staging panel: 32 bf16 = 64 B rows, 64B swizzle
 constexpr int kPanelBytes = kBlockM * kPanelCols * 2;  // 8 KB
@@ -36,6 +37,8 @@ struct GemmArgs {
   int kblocks1;    // 64-wide K blocks taken from A (per tap for conv)
   int kblocks2;    // ... then from A2 (plain mode only)
   int taps;        // 1 = plain GEMM, 9 = 3x3 conv, 4 = nearest-2x upsample folded into the 3x3 conv (see `ups`)
+  int rr;          // 3x3 conv "row reuse": one A box of hbox + 2 image rows per (dx, channel block) feeds the three dy taps
+  int a_bytes;     // bytes of one A stage tile (128 rows x 128 B, or (hbox + 2) * W rows x 128 B with rr)
   int ups;         // 1: output parity classes (py, px) of conv3x3(upsample2x(x)) as four 2x2 convolutions on x (vx_upconv3x3_bf16)
   int block_n;     // UMMA N (multiple of 32, <= 256)
   int stages;
@@ -54,8 +57,14 @@ struct GemmArgs {
   long long ldc;
   // LayerNorm folded into the epilogue (LNF instantiations only): out = rstd[m] * (acc - mean[m] * colsum[n]) + bias[n]
   // with W pre-multiplied by gamma, colsum[n] = sum_k W'[n,k], bias[n] = sum_k beta[k] W[n,k] + b[n]
-  const float* ln_stats;    // [M][2] = (mean, rstd) of the un-normalised rows of A
+  const float* ln_stats;    // [M][2] = (mean, rstd) of the un-normalised rows of A (null with `ares`)
   const float* ln_colsum;   // [N]
+  // A-resident LayerNorm GEMM (LNF instantiations, K <= 512): a CTA (pair) keeps the K blocks of ONE 128-row tile of A in
+  // shared memory while it walks ALL column tiles of that row tile (only W streams through the TMA ring), and four extra warps
+  // compute the row statistics from the resident tile -- no statistics pass, no LayerNorm pass, 1/tiles_n of the A traffic.
+  int ares;
+  int ares_bytes;           // kblocks1 x 16 KB
+  float ln_eps;
 };
 
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
@@ -150,19 +159,22 @@ __device__ __forceinline__ float gelu_erf(float g) {
 // half of B from its shared memory -- the 1-CTA kernel is bound by the SS-MMA operand fetch (A 4 KB + B 8 KB per
 // 128x256x16 MMA at ~64 B/clk = 192 clk vs 128 clk of math, profiles/r01e_final_ncu.md).
 template <int CG, bool LNF>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(LNF ? kThreads + kStatThreads : kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapA2,
                     const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapR,
                     const __grid_constant__ CUtensorMap mapC, const GemmArgs p) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment required by the 128B swizzle atom
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int a_bytes = kBlockM * kBlockK * 2;
-  const int b_bytes = (p.block_n / CG) * kBlockK * 2;   // this CTA's share of the W tile
-  const int stage_bytes = a_bytes + b_bytes;
+  const int a_bytes = p.a_bytes;
+  const int b_bytes = (p.block_n / CG) * kBlockK * 2;   // this CTA's share of one W tile
+  const int nbt = p.rr ? 3 : 1;                         // W tiles per stage (rr: the three dy taps of one dx)
+  const int stage_bytes = a_bytes + nbt * b_bytes;
   const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
   const bool pair_leader = cta_rank == 0;
-  uint8_t* sC = smem + p.stages * stage_bytes;  // staging: (block_n or block_n/2)/32 panels of 8 KB
+  uint8_t* ring = smem;                         // TMA ring (behind the resident A tile in `ares` mode)
+  if constexpr (LNF) ring += p.ares ? p.ares_bytes : 0;
+  uint8_t* sC = ring + p.stages * stage_bytes;  // staging: (block_n or block_n/2)/32 panels of 8 KB
   const int out_cols = p.geglu ? p.block_n / 2 : p.block_n;
   const int npanels = out_cols / kPanelCols;
   const int buf_bytes = npanels * kPanelBytes;
@@ -173,14 +185,36 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   uint64_t* c_ready = tmem_empty + 2;          // [2] staging tile b free (+ residual landed)
   uint64_t* staged = c_ready + 2;              // [2] staging tile b fully written by the epilogue warps
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(staged + 2);
+  // `ares` only: per K block of the resident tile -- landed in THIS CTA / usable by the MMA (both CTAs landed, on the pair
+  // leader) / released (MMAs of the last column tile done + statistics warps done); statistics double buffer
+  uint64_t* a_land = staged + 3;          // [8]
+  uint64_t* a_full = a_land + 8;          // [8]
+  uint64_t* a_empty = a_full + 8;         // [8]
+  uint64_t* stats_full = a_empty + 8;     // [2]
+  uint64_t* stats_empty = stats_full + 2; // [2]
+  float2* s_stats = reinterpret_cast<float2*>(stats_empty + 2);   // [2][128] (mean, rstd)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_kb = p.taps * p.kblocks1 + p.kblocks2;
+  const int total_kb = p.rr ? 3 * p.kblocks1 : p.taps * p.kblocks1 + p.kblocks2;   // ring stages per output tile
   // work items are (row-tile group of CG tiles, column tile); every CTA of a pair walks the same sequence
   const int tiles_per_par = ((p.tiles_m + CG - 1) / CG) * p.tiles_n;
   const int num_tiles = tiles_per_par * (p.ups ? 4 : 1);   // ups: (parity, row-tile group, column tile), parity slowest
   const int first_item = blockIdx.x / CG, item_stride = gridDim.x / CG;
+  // the it-th output tile of this CTA (pair) as a flat (row-tile group, column tile) index, or -1 past the end.  Default:
+  // tiles strided over the grid, n fastest.  `ares`: row-tile groups strided over the grid, each walked through all its
+  // column tiles.
+  const int groups = (p.tiles_m + CG - 1) / CG;
+  auto item_at = [&](int it) -> int {
+    if constexpr (LNF) {
+      if (p.ares) {
+        const int g = first_item + (it / p.tiles_n) * item_stride;
+        return g < groups ? g * p.tiles_n + it % p.tiles_n : -1;
+      }
+    }
+    const int t = first_item + it * item_stride;
+    return t < num_tiles ? t : -1;
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA);
@@ -197,6 +231,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       mbar_init(&tmem_empty[s], CG * kEpiThreads / 32);
       mbar_init(&c_ready[s], 1);
       mbar_init(&staged[s], kEpiThreads);
+    }
+    if constexpr (LNF) {
+      if (p.ares) {
+        for (int s = 0; s < 8; ++s) {
+          mbar_init(&a_land[s], 1);
+          mbar_init(&a_full[s], CG);                    // one arrival per CTA of the pair (its statistics warp 0)
+          mbar_init(&a_empty[s], 1 + kStatThreads / 32); // MMA commit + the four statistics warps
+        }
+        for (int s = 0; s < 2; ++s) {
+          mbar_init(&stats_full[s], kStatThreads);
+          mbar_init(&stats_empty[s], kEpiThreads / 32);
+        }
+      }
     }
     fence_barrier_init();
   }
@@ -221,7 +268,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     const bool leader = elect_one();
     int stage = 0;
     uint32_t phase = 0;
-    for (int t = first_item; t < num_tiles; t += item_stride) {
+    for (int it = 0, t = item_at(0); t >= 0; t = item_at(++it)) {
       const int par = t / tiles_per_par, tt = t - par * tiles_per_par;
       const int tile_n = tt % p.tiles_n, tile_m = (tt / p.tiles_n) * CG + (int)cta_rank;
       int n0 = 0, y0 = 0, x0 = 0;
@@ -234,14 +281,69 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         x0 = rem % p.W;
       }
       // the pair's loads all complete on the LEADER's full barrier (it alone waits for the operands)
-      const uint32_t tx_bytes = (uint32_t)(CG * (p.rows_valid * kBlockK * 2 + b_bytes));
+      const uint32_t tx_bytes = (uint32_t)(CG * ((p.rr ? a_bytes : p.rows_valid * kBlockK * 2) + nbt * b_bytes));
       const int b_row = par * p.N + tile_n * p.block_n + (int)cta_rank * (p.block_n / CG);
       for (int kb = 0; kb < total_kb; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* sa = smem + stage * stage_bytes;
+        uint8_t* sa = ring + stage * stage_bytes;
         uint8_t* sb = sa + a_bytes;
-        const int tap = p.taps != 1 ? kb / p.kblocks1 : 0;
+        const int tap = p.taps != 1 ? kb / p.kblocks1 : 0;     // rr: tap = dx index (0..2)
         const int cb = kb - tap * p.kblocks1;
+        if constexpr (LNF) {
+          if (p.ares) {
+            // resident A: K block kb of this row tile is loaded once, in front of the first column tile, into its own slot
+            // (completing on THIS CTA's a_land: the statistics warps of each CTA read their own rows)
+            if (tile_n == 0) {
+              mbar_wait(&a_empty[kb], (uint32_t)(((it / p.tiles_n) & 1) ^ 1));
+              if (leader) {
+                mbar_expect_tx(&a_land[kb], (uint32_t)(kBlockM * kBlockK * 2));
+                tma_load_2d(smem + kb * (kBlockM * kBlockK * 2), &mapA, &a_land[kb], kb * kBlockK, (int)m0);
+              }
+            }
+            if (leader) {
+              if (CG == 2) {
+                const uint32_t fb = mapa_rank(smem_u32(&full_bar[stage]), 0);
+                if (pair_leader) mbar_expect_tx(&full_bar[stage], (uint32_t)(CG * b_bytes));
+                tma_load_2d_cg2(ring + stage * stage_bytes, &mapB, fb, kb * kBlockK, b_row);
+              } else {
+                mbar_expect_tx(&full_bar[stage], (uint32_t)b_bytes);
+                tma_load_2d(ring + stage * stage_bytes, &mapB, &full_bar[stage], kb * kBlockK, b_row);
+              }
+            }
+            __syncwarp();
+            if (++stage == p.stages) {
+              stage = 0;
+              phase ^= 1;
+            }
+            continue;
+          }
+        }
+        if (p.rr) {
+          // A: image rows y0 - 1 .. y0 + hbox of the column window shifted by dx (zero-filled outside the image = padding);
+          // W: the three taps (dy, dx), dy = 0..2, of this channel block
+          if (leader) {
+            if (CG == 2) {
+              const uint32_t fb = mapa_rank(smem_u32(&full_bar[stage]), 0);
+              if (pair_leader) mbar_expect_tx(&full_bar[stage], tx_bytes);
+              tma_load_4d_cg2(sa, &mapA, fb, cb * kBlockK, x0 + tap - 1, y0 - 1, n0);
+#pragma unroll
+              for (int dyi = 0; dyi < 3; ++dyi)
+                tma_load_2d_cg2(sb + dyi * b_bytes, &mapB, fb, ((dyi * 3 + tap) * p.kblocks1 + cb) * kBlockK, b_row);
+            } else {
+              mbar_expect_tx(&full_bar[stage], tx_bytes);
+              tma_load_4d(sa, &mapA, &full_bar[stage], cb * kBlockK, x0 + tap - 1, y0 - 1, n0);
+#pragma unroll
+              for (int dyi = 0; dyi < 3; ++dyi)
+                tma_load_2d(sb + dyi * b_bytes, &mapB, &full_bar[stage], ((dyi * 3 + tap) * p.kblocks1 + cb) * kBlockK, b_row);
+            }
+          }
+          __syncwarp();
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+          continue;
+        }
         // 3x3: taps (dy, dx) in {-1, 0, 1}^2.  Folded upsample: output pixel (2i + py, 2j + px) reads the 2x2 input
         // neighbourhood rows i + py - 1 + {0, 1}, columns j + px - 1 + {0, 1} (weights pre-summed per parity on the host).
         const int dy = p.ups ? (tap >> 1) + (par >> 1) - 1 : tap / 3 - 1;
@@ -283,27 +385,55 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     const uint32_t idesc = make_idesc_bf16(kBlockM * CG, (uint32_t)p.block_n, 0, 0);
     int stage = 0;
     uint32_t phase = 0;
-    int it = 0;
     if (pair_leader)
-    for (int t = first_item; t < num_tiles; t += item_stride, ++it) {
+    for (int it = 0, t = item_at(0); t >= 0; t = item_at(++it)) {
       const int as = it & 1;
       mbar_wait(&tmem_empty[as], (uint32_t)(((it >> 1) & 1) ^ 1));
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(as * 256);
       for (int kb = 0; kb < total_kb; ++kb) {
+        bool a_last = false;   // ares: last column tile of the row tile -> its MMAs release the resident K block
+        if constexpr (LNF) {
+          if (p.ares) {
+            const int tn = t % p.tiles_n;
+            if (tn == 0) mbar_wait(&a_full[kb], (uint32_t)((it / p.tiles_n) & 1));
+            a_last = tn == p.tiles_n - 1;
+          }
+        }
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+        uint32_t sa = smem_u32(ring + stage * stage_bytes);
         const uint32_t sb = sa + a_bytes;
+        if constexpr (LNF) {
+          if (p.ares) sa = smem_u32(smem + kb * (kBlockM * kBlockK * 2));
+        }
         const uint64_t da = make_smem_desc(sa, 16, 1024, SWZ_128B);
         const uint64_t db = make_smem_desc(sb, 16, 1024, SWZ_128B);
         if (leader) {
+          if (p.rr) {
+            // tap dy reads the 128 tile rows that start dy image rows (W x 128 B, a multiple of the 1024-B swizzle atom)
+            // into the A box, against its own W tile
+            const uint32_t a_step = (uint32_t)(p.W * 128) >> 4, b_step = (uint32_t)b_bytes >> 4;
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {  // +32 bytes per K step = +2 in the (addr >> 4) field
-            if (CG == 2) umma_ss_cg2(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
-            else umma_ss(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int dyi = 0; dyi < 3; ++dyi) {
+#pragma unroll
+              for (int k = 0; k < kBlockK / 16; ++k) {
+                const uint64_t a = da + (uint64_t)(dyi * a_step + k * 2), b = db + (uint64_t)(dyi * b_step + k * 2);
+                if (CG == 2) umma_ss_cg2(d_tmem, a, b, idesc, (kb | dyi | k) != 0 ? 1u : 0u);
+                else umma_ss(d_tmem, a, b, idesc, (kb | dyi | k) != 0 ? 1u : 0u);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k) {  // +32 bytes per K step = +2 in the (addr >> 4) field
+              if (CG == 2) umma_ss_cg2(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+              else umma_ss(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+            }
           }
           if (CG == 2) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
+          if (a_last) {
+            if (CG == 2) umma_commit_pair(&a_empty[kb]); else umma_commit(&a_empty[kb]);
+          }
         }
         __syncwarp();
         if (++stage == p.stages) {
@@ -332,9 +462,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         }
       };
       for (int b = 0; b < p.nbuf; ++b)
-        if (first_item + b * item_stride < num_tiles) arm(first_item + b * item_stride, b);
-      int it = 0;
-      for (int t = first_item; t < num_tiles; t += item_stride, ++it) {
+        if (item_at(b) >= 0) arm(item_at(b), b);
+      for (int it = 0, t = item_at(0); t >= 0; t = item_at(++it)) {
         const int b = it % p.nbuf;
         const int par = t / tiles_per_par, tt = t - par * tiles_per_par;
         const int tile_n = tt % p.tiles_n, tile_m = (tt / p.tiles_n) * CG + (int)cta_rank;
@@ -355,8 +484,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                          tile_m * p.rows_valid);
         }
         tma_store_commit();
-        const int tnext = t + p.nbuf * item_stride;
-        if (tnext < num_tiles) {
+        const int tnext = item_at(it + p.nbuf);
+        if (tnext >= 0) {
           tma_store_wait_read();  // the store has finished reading tile b
           arm(tnext, b);
         }
@@ -372,10 +501,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     const int nchunks = out_cols / 16;
     const int c_begin = half ? (nchunks + 1) / 2 : 0;
     const int c_end = half ? nchunks : (nchunks + 1) / 2;
-    int it = 0;
     const uint32_t te_leader0 = CG == 2 ? mapa_rank(smem_u32(&tmem_empty[0]), 0) : 0u;
     const uint32_t te_leader1 = CG == 2 ? mapa_rank(smem_u32(&tmem_empty[1]), 0) : 0u;
-    for (int t = first_item; t < num_tiles; t += item_stride, ++it) {
+    for (int it = 0, t = item_at(0); t >= 0; t = item_at(++it)) {
       const int tt = t % tiles_per_par;
       const int tile_n = tt % p.tiles_n, tile_m = (tt / p.tiles_n) * CG + (int)cta_rank;
       const int as = it & 1;
@@ -390,7 +518,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       const float* b2 = p.bias2 ? p.bias2 + (row_ok ? (m / p.bias2_div) : 0) * (long long)p.N : nullptr;
       float ln_mean = 0.f, ln_rstd = 1.f;
       if constexpr (LNF) {
-        if (row_ok) {
+        if (p.ares) {
+          // statistics of this row tile, computed by warps 11..14 from the resident tile (double-buffered by row tile)
+          const int item = it / p.tiles_n, sbuf = item & 1;
+          mbar_wait(&stats_full[sbuf], (uint32_t)((item >> 1) & 1));
+          const float2 st = s_stats[sbuf * kBlockM + row];
+          ln_mean = st.x;
+          ln_rstd = st.y;
+          if (tile_n == p.tiles_n - 1) {   // last use of this buffer: hand it back
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&stats_empty[sbuf]);
+          }
+        } else if (row_ok) {
           const float2 st = *reinterpret_cast<const float2*>(p.ln_stats + 2 * m);
           ln_mean = st.x;
           ln_rstd = st.y;
@@ -511,6 +650,64 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       }
     }
   }
+  if constexpr (LNF) {
+    if (warp >= 11 && p.ares) {
+      // ---------------------------------------------------------- row statistics of the resident A tile (thread = row)
+      // The tile sits in the 128B-swizzled K-major layout: row r of K block kb = 128 bytes at kb * 16 KB + r * 128, its eight
+      // 16-byte chunks permuted by r & 7 -- sums do not care.  Chunk (j + r) & 7 at step j keeps the eight rows of a
+      // quarter-warp on eight different bank groups.  Two passes (mean, then centred squares): the tile is in shared
+      // memory anyway, and the result is the textbook variance rather than E[x^2] - mean^2.
+      const int sw = warp - 11, r = sw * 32 + lane;
+      const uint32_t a_full_leader = CG == 2 ? mapa_rank(smem_u32(&a_full[0]), 0) : 0u;
+      const int K = p.kblocks1 * kBlockK;
+      for (int item = 0; item_at(item * p.tiles_n) >= 0; ++item) {
+        const int sbuf = item & 1;
+        const uint32_t a_phase = (uint32_t)(item & 1);
+        mbar_wait(&stats_empty[sbuf], (uint32_t)(((item >> 1) & 1) ^ 1));
+        float sum = 0.f;
+        for (int kb = 0; kb < p.kblocks1; ++kb) {
+          mbar_wait(&a_land[kb], a_phase);
+          if (sw == 0 && lane == 0) {   // this CTA's K block has landed: tell the MMA warp (of the pair leader)
+            if (CG == 2) mbar_arrive_cluster(a_full_leader + (uint32_t)(kb * 8));
+            else mbar_arrive(&a_full[kb]);
+          }
+          const uint8_t* rowp = smem + kb * (kBlockM * kBlockK * 2) + r * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint4 q = *reinterpret_cast<const uint4*>(rowp + (((j + r) & 7) << 4));
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 f2 = unpack_bf16(w[i]);
+              sum += f2.x + f2.y;
+            }
+          }
+        }
+        const float mean = sum / (float)K;
+        float ssq = 0.f;
+        for (int kb = 0; kb < p.kblocks1; ++kb) {
+          const uint8_t* rowp = smem + kb * (kBlockM * kBlockK * 2) + r * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint4 q = *reinterpret_cast<const uint4*>(rowp + (((j + r) & 7) << 4));
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 f2 = unpack_bf16(w[i]);
+              const float d0 = f2.x - mean, d1 = f2.y - mean;
+              ssq = fmaf(d0, d0, ssq);
+              ssq = fmaf(d1, d1, ssq);
+            }
+          }
+        }
+        s_stats[sbuf * kBlockM + r] = make_float2(mean, rsqrtf(ssq / (float)K + p.ln_eps));
+        __syncwarp();
+        if (lane == 0)
+          for (int kb = 0; kb < p.kblocks1; ++kb) mbar_arrive(&a_empty[kb]);   // this warp has finished reading the tile
+        mbar_arrive(&stats_full[sbuf]);
+      }
+    }
+  }
   tc_fence_before();
   if (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
@@ -522,7 +719,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
 // A/B switches (bring-up only) are read ONCE per process: the launch path never touches the environment
 // (the sweep tools re-read them through vx_gemm_reload_env).
 struct GemmEnv {
-  int cg, cg_minkb, pairs, stages, nbuf, bn, verbose;
+  int cg, cg_minkb, pairs, stages, nbuf, bn, verbose, conv_rr;
   static int geti(const char* name, int dflt) {
     const char* s = getenv(name);
     return s ? atoi(s) : dflt;
@@ -535,6 +732,7 @@ struct GemmEnv {
     nbuf = geti("VX_GEMM_NBUF", 0);
     bn = geti("VX_GEMM_BN", 0);
     verbose = geti("VX_GEMM_VERBOSE", 0);
+    conv_rr = geti("VX_CONV_RR", 1);
   }
 };
 static GemmEnv& gemm_env() {
@@ -591,8 +789,11 @@ static int pick_block_n(long long tiles_m, int N, int gran, int out_f32, int tot
 }
 
 static bool use_pair(const GemmArgs& a) {
+  if (a.ares) return a.tiles_m >= 2;   // resident A: the pair halves the W stream, the only operand left in the ring
   return pair_ok(a.out_f32, a.block_n, a.tiles_m, a.taps * a.kblocks1 + a.kblocks2);
 }
+
+constexpr size_t kAresExtra = 2560;   // ares barriers + the statistics double buffer behind the ordinary barrier block
 
 static int num_pairs() {
   static int n = 0;
@@ -623,11 +824,13 @@ static int num_pairs() {
 static int launch(const CUtensorMap& mA, const CUtensorMap& mA2, const CUtensorMap& mB, const CUtensorMap& mR,
                   const CUtensorMap& mC, GemmArgs& a, cudaStream_t st) {
   const int cg = use_pair(a) ? 2 : 1;
-  const int stage_bytes = kBlockM * kBlockK * 2 + (a.block_n / cg) * kBlockK * 2;
+  if (a.ares) a.a_bytes = 0;   // A lives in its own resident slots, the ring stages hold W only
+  else if (a.a_bytes <= 0) a.a_bytes = kBlockM * kBlockK * 2;
+  const int stage_bytes = a.a_bytes + (a.rr ? 3 : 1) * (a.block_n / cg) * kBlockK * 2;
   const int out_cols = a.geglu ? a.block_n / 2 : a.block_n;
   const int buf_bytes = a.out_f32 ? 0 : out_cols / kPanelCols * kPanelBytes;
-  const int total_kb = a.taps * a.kblocks1 + a.kblocks2;
-  const size_t cap = 227 * 1024 - 2048;
+  const int total_kb = a.rr ? 3 * a.kblocks1 : a.taps * a.kblocks1 + a.kblocks2;
+  const size_t cap = 227 * 1024 - 2048 - (a.ares ? kAresExtra + (size_t)a.ares_bytes : 0);
   // deep TMA rings only pay off for long K loops; short K loops need the second staging tile instead
   int want_stages = gemm_env().stages;
   if (want_stages <= 0) want_stages = total_kb < 6 ? (total_kb < 3 ? 3 : total_kb) : 6;
@@ -638,13 +841,25 @@ static int launch(const CUtensorMap& mA, const CUtensorMap& mA2, const CUtensorM
     const int st2 = (int)((cap - 2 * (size_t)buf_bytes) / stage_bytes);
     if (st2 < 5 && (!a.has_residual || total_kb >= 40)) nbuf = 1;
   }
+  if (a.rr) {
+    // a row-reuse stage is 3 taps deep (12 MMAs): three stages when they fit beside ONE staging tile, else two beside two
+    nbuf = ((size_t)3 * stage_bytes + buf_bytes <= cap) ? 1 : 2;
+    want_stages = nbuf == 1 ? 3 : 2;
+    if ((size_t)want_stages * stage_bytes + (size_t)nbuf * buf_bytes > cap) nbuf = 1;
+  }
+  if (a.ares) {   // every column tile of a row tile streams the whole W panel: a deep ring, two staging tiles when they fit
+    nbuf = ((size_t)4 * stage_bytes + 2 * (size_t)buf_bytes <= cap) ? 2 : 1;
+    want_stages = 8;
+  }
   const int force_nbuf = gemm_env().nbuf;
   if (force_nbuf == 1 || (force_nbuf == 2 && (size_t)2 * stage_bytes + 2 * buf_bytes <= cap)) nbuf = force_nbuf;
   int stages = want_stages;
   while (stages > 2 && (size_t)stages * stage_bytes + (size_t)nbuf * buf_bytes > cap) --stages;
   a.stages = stages;
   a.nbuf = nbuf;
-  const size_t smem = (size_t)stages * stage_bytes + (size_t)nbuf * buf_bytes + 2048;
+  const size_t smem = (size_t)stages * stage_bytes + (size_t)nbuf * buf_bytes + 2048 + (a.ares ? kAresExtra + (size_t)a.ares_bytes : 0);
+  VX_REQUIRE(smem <= (size_t)227 * 1024, "vx_gemm: %zu bytes of shared memory needed (bn=%d, K blocks=%d)", smem, a.block_n,
+             a.kblocks1);
   if (gemm_env().verbose)
     fprintf(stderr, "[vx_gemm] M=%d N=%d kb=%d taps=%d cg=%d bn=%d stages=%d nbuf=%d tiles=%dx%d\n", a.M, a.N, total_kb,
             a.taps, cg, a.block_n, stages, nbuf, a.tiles_m, a.tiles_n);
@@ -657,17 +872,19 @@ static int launch(const CUtensorMap& mA, const CUtensorMap& mA2, const CUtensorM
     configured = true;
   }
   const int npar = a.ups ? 4 : 1;
+  const bool lnf = a.ln_stats != nullptr || a.ares;
+  const int threads = a.ares ? kThreads + kStatThreads : kThreads;
   if (cg == 1) {
-    const int tiles = a.tiles_m * a.tiles_n * npar;
+    const int tiles = a.ares ? a.tiles_m : a.tiles_m * a.tiles_n * npar;
     const int grid = tiles < num_sms() ? tiles : num_sms();
-    if (a.ln_stats) gemm_tcgen05_kernel<1, true><<<grid, kThreads, smem, st>>>(mA, mA2, mB, mR, mC, a);
+    if (lnf) gemm_tcgen05_kernel<1, true><<<grid, threads, smem, st>>>(mA, mA2, mB, mR, mC, a);
     else gemm_tcgen05_kernel<1, false><<<grid, kThreads, smem, st>>>(mA, mA2, mB, mR, mC, a);
   } else {
-    const int items = ((a.tiles_m + 1) / 2) * a.tiles_n * npar;
+    const int items = a.ares ? (a.tiles_m + 1) / 2 : ((a.tiles_m + 1) / 2) * a.tiles_n * npar;
     const int pairs = items < num_pairs() ? items : num_pairs();
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(2 * pairs);
-    cfg.blockDim = dim3(kThreads);
+    cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -677,7 +894,7 @@ static int launch(const CUtensorMap& mA, const CUtensorMap& mA2, const CUtensorM
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (a.ln_stats) VX_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<2, true>, mA, mA2, mB, mR, mC, a));
+    if (lnf) VX_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<2, true>, mA, mA2, mB, mR, mC, a));
     else VX_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<2, false>, mA, mA2, mB, mR, mC, a));
   }
   VX_CHECK_CUDA(cudaGetLastError());
@@ -712,8 +929,9 @@ extern "C" void vx_gemm_reload_env() { gemm_env() = GemmEnv(); }   // sweep-tool
 static int gemm_entry(const void* A, long long lda, int K1, const void* A2, long long lda2, int K2, const void* Wt,
                       long long ldw, int M, int N, const float* bias, const float* bias2, int bias2_div, float scale,
                       const void* residual, long long ldr, void* out, long long ldc, int out_f32, int block_n,
-                      const float* ln_stats, const float* ln_colsum, void* stream) {
+                      const float* ln_stats, const float* ln_colsum, void* stream, float ln_eps = 0.f) {
   const int geglu = out_f32 == 2 ? 1 : 0;  // out_f32: 0 bf16, 1 fp32, 2 bf16 + GEGLU epilogue
+  const bool ares = ln_colsum && !ln_stats;   // LayerNorm GEMM with in-kernel statistics (A tile resident)
   if (geglu) out_f32 = 0;
   VX_REQUIRE(M > 0 && N > 0 && K1 > 0, "vx_gemm_bf16: bad shape M=%d N=%d K1=%d", M, N, K1);
   const int gran = geglu ? 64 : (out_f32 ? 16 : 32);
@@ -726,7 +944,30 @@ static int gemm_entry(const void* A, long long lda, int K1, const void* A2, long
   const int tiles_m = (M + kBlockM - 1) / kBlockM;
   const int total_kb = (K1 + kBlockK - 1) / kBlockK + (K2 + kBlockK - 1) / kBlockK;
   if (block_n <= 0) block_n = gemm_env().bn;
-  if (block_n <= 0) block_n = pick_block_n(tiles_m, N, gran, out_f32, total_kb);
+  bool b_split = false;   // W tile split between the two CTAs of a pair
+  if (ares) {
+    VX_REQUIRE(K2 == 0 && K1 % kBlockK == 0 && K1 <= 8 * kBlockK && !out_f32,
+               "vx_gemm_ln_bf16: K=%d must be a multiple of 64, <= 512 (the row tile stays in shared memory)", K1);
+    b_split = tiles_m >= 2;
+    const size_t cap = (size_t)227 * 1024 - 2048 - kAresExtra - (size_t)(K1 / kBlockK) * kBlockM * kBlockK * 2;
+    auto fits = [&](int bn, int nbuf) {   // four ring stages + nbuf staging tiles
+      const size_t b = (size_t)(b_split ? bn / 2 : bn) * kBlockK * 2, buf = (size_t)((geglu ? bn / 2 : bn) / kPanelCols) * kPanelBytes;
+      return 4 * b + nbuf * buf <= cap;
+    };
+    if (block_n <= 0 || N % block_n || block_n % gran || !fits(block_n, 1)) {
+      block_n = 0;
+      for (int nbuf = 2; nbuf >= 1 && !block_n; --nbuf)   // widest column tile that keeps both staging tiles, else one
+        for (int bn = 256; bn >= gran; bn -= gran)
+          if (N % bn == 0 && fits(bn, nbuf)) {
+            block_n = bn;
+            break;
+          }
+    }
+    VX_REQUIRE(block_n > 0, "vx_gemm_ln_bf16: no column tile of N=%d fits beside the resident K=%d tile", N, K1);
+  } else {
+    if (block_n <= 0) block_n = pick_block_n(tiles_m, N, gran, out_f32, total_kb);
+    b_split = pair_ok(out_f32, block_n, tiles_m, total_kb);
+  }
   VX_REQUIRE(block_n >= gran && block_n % gran == 0 && block_n <= 256 && N % block_n == 0,
              "vx_gemm_bf16: block_n=%d invalid for N=%d", block_n, N);
   CUtensorMap mA, mA2, mB, mR, mC;
@@ -747,7 +988,7 @@ static int gemm_entry(const void* A, long long lda, int K1, const void* A2, long
   {
     uint64_t dims[2] = {(uint64_t)(K1 + K2), (uint64_t)N};
     uint64_t str[1] = {(uint64_t)ldw * 2};
-    uint32_t box[2] = {kBlockK, (uint32_t)(pair_ok(out_f32, block_n, tiles_m, total_kb) ? block_n / 2 : block_n)};
+    uint32_t box[2] = {kBlockK, (uint32_t)(b_split ? block_n / 2 : block_n)};
     if (make_tmap_bf16(&mB, Wt, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
   }
   if (!out_f32) {
@@ -772,6 +1013,9 @@ static int gemm_entry(const void* A, long long lda, int K1, const void* A2, long
   a.bias = bias; a.bias2 = bias2; a.bias2_div = bias2_div > 0 ? bias2_div : 1; a.scale = scale;
   a.out32 = (float*)out; a.ldc = ldc;
   a.ln_stats = ln_stats; a.ln_colsum = ln_colsum;
+  a.ares = ares ? 1 : 0;
+  a.ares_bytes = ares ? a.kblocks1 * kBlockM * kBlockK * 2 : 0;
+  a.ln_eps = ln_eps;
   return launch(mA, mA2, mB, mR, mC, a, (cudaStream_t)stream);
 }
 
@@ -793,6 +1037,18 @@ extern "C" int vx_gemm_lnfold_bf16(const void* A, long long lda, int K, const vo
   VX_REQUIRE(stats && colsum, "vx_gemm_lnfold_bf16: stats / colsum missing (M=%d)", M);
   return gemm_entry(A, lda, K, nullptr, 0, 0, Wt, ldw, M, N, bias, bias2, bias2_div, scale, residual, ldr, out, ldc,
                     geglu ? 2 : 0, block_n, stats, colsum, stream);
+}
+
+// LayerNorm -> Linear in ONE kernel: A holds the un-normalised rows (K <= 512), Wt / colsum / bias are the folded parameters
+// of vx_gemm_lnfold_bf16; the row statistics are computed inside the kernel from the shared-memory resident row tile
+// (two-pass mean / variance, eps as in nn.LayerNorm), so neither LayerNorm(A) nor a statistics array ever exists in HBM.
+extern "C" int vx_gemm_ln_bf16(const void* A, long long lda, int K, const void* Wt, long long ldw, int M, int N,
+                               const float* colsum, const float* bias, float eps, const float* bias2, int bias2_div,
+                               float scale, const void* residual, long long ldr, void* out, long long ldc, int geglu,
+                               int block_n, void* stream) {
+  VX_REQUIRE(colsum, "vx_gemm_ln_bf16: colsum missing (M=%d)", M);
+  return gemm_entry(A, lda, K, nullptr, 0, 0, Wt, ldw, M, N, bias, bias2, bias2_div, scale, residual, ldr, out, ldc,
+                    geglu ? 2 : 0, block_n, nullptr, colsum, stream, eps);
 }
 
 // X: NHWC bf16 [NB, H, W, C];  Wt: [Cout, 9*C] with K index = (ky*3+kx)*C + c;  out: [NB*H*W, ldc]
@@ -829,11 +1085,21 @@ extern "C" int vx_conv3x3_bf16(const void* X, int NB, int H, int W, int C, const
   if (block_n <= 0) block_n = pick_block_n(tiles_m, Cout, 32, 0, total_kb);
   VX_REQUIRE(block_n % 32 == 0 && block_n >= 32 && block_n <= 256 && Cout % block_n == 0,
              "vx_conv3x3_bf16: block_n=%d invalid for Cout=%d", block_n, Cout);
+  // Row reuse: when a tile is hbox >= 2 whole image rows of one frame, ONE box of hbox + 2 rows per (dx, channel block)
+  // serves the three dy taps (each tap's 128 rows start dy image rows further down, a multiple of the swizzle atom):
+  // 3 (hbox + 2) / (9 hbox) of the A traffic.  The 3x3 convs run at the L2 -> SM cap (~13 TB/s,
+  // profiles/r02_roofline.csv), so operand bytes are what they are bound by.
+  bool rr = gemm_env().conv_rr && nbox == 1 && wbox == W && hbox >= 2 && rows_valid == kBlockM && (W * 128) % 1024 == 0;
+  if (rr) {   // two ring stages + one staging tile must fit
+    const int cgx = pair_ok(0, block_n, tiles_m, total_kb) ? 2 : 1;
+    const size_t st = (size_t)(hbox + 2) * W * kBlockK * 2 + (size_t)3 * (block_n / cgx) * kBlockK * 2;
+    if (2 * st + (size_t)(block_n / kPanelCols) * kPanelBytes > (size_t)227 * 1024 - 2048) rr = false;
+  }
   CUtensorMap mA, mB, mR, mC;
   {
     uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)NB};
     uint64_t str[3] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
-    uint32_t box[4] = {kBlockK, (uint32_t)wbox, (uint32_t)hbox, (uint32_t)nbox};
+    uint32_t box[4] = {kBlockK, (uint32_t)wbox, (uint32_t)(rr ? hbox + 2 : hbox), (uint32_t)nbox};
     if (make_tmap_bf16(&mA, X, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
   }
   {
@@ -848,6 +1114,8 @@ extern "C" int vx_conv3x3_bf16(const void* X, int NB, int H, int W, int C, const
   a.kblocks1 = C / kBlockK;
   a.kblocks2 = 0;
   a.taps = 9;
+  a.rr = rr ? 1 : 0;
+  a.a_bytes = rr ? (hbox + 2) * W * kBlockK * 2 : kBlockM * kBlockK * 2;
   a.block_n = block_n;
   a.rows_valid = rows_valid;
   a.W = W; a.H = H;

@@ -421,17 +421,22 @@ class UNetEngine:
 
     # ---------------------------------------------------------------- LayerNorm folded into the consumer GEMM
     def _pack_ln_fold(self):
-        """VX_LN_FOLD=1 (experiment, default off; not yet run on hardware): every LayerNorm -> Linear pair of the
-        transformer blocks runs as row statistics + one GEMM whose epilogue applies the normalisation
-        (ops.fold_layernorm / ops.gemm_lnfold), so LayerNorm(x) is never written to HBM."""
+        """LayerNorm -> Linear pairs of the transformer blocks with the normalisation applied in the GEMM epilogue
+        (ops.fold_layernorm), so LayerNorm(x) is never written to HBM.
+        Default (VX_LN_GEMM=0 turns it off): the pairs of the 320-wide level (K <= ops.LN_GEMM_MAX_K) run as ONE kernel,
+        ops.gemm_ln -- the row tile stays resident in shared memory, the kernel computes the statistics itself.
+        VX_LN_FOLD=1 (experiment): the wider levels too, as vx_row_stats + ops.gemm_lnfold (measured: no gain there)."""
         self.ln_fold = os.environ.get("VX_LN_FOLD") == "1"
+        self.ln_gemm = os.environ.get("VX_LN_GEMM", "0") != "0"   # default flips to on once the GPU run has validated it
         self.F: Dict[str, tuple] = {}
         self._pe_proj: Dict[str, torch.Tensor] = {}
         self._pe_bias: Dict[tuple, torch.Tensor] = {}
-        if not self.ln_fold:
+        if not (self.ln_fold or self.ln_gemm):
             return
         W = self.W
         for k in list(W):
+            if not (self.ln_fold or W[k].shape[0] <= ops.LN_GEMM_MAX_K):
+                continue
             if k.endswith(".norm1.weight") and ".attentions." in k:
                 t = k[:-len(".norm1.weight")]
                 for norm, lin in (("norm1", "attn1.qkv"), ("norm1_5", "attn1_5.to_q.weight"), ("norm2", "attn2.to_q.weight")):
@@ -455,13 +460,14 @@ class UNetEngine:
         """LayerNorm(h) [+ pe] -> Linear.  Default: the LayerNorm kernel followed by the GEMM; under VX_LN_FOLD the
         statistics kernel and the GEMM with the normalising epilogue."""
         W = self.W
-        if not self.ln_fold:
+        K = h.shape[1]
+        one_kernel = self.ln_gemm and K <= ops.LN_GEMM_MAX_K and K % 64 == 0 and norm_key in self.F
+        if not (self.ln_fold or one_kernel):
             n = ops.layernorm(h, W[norm_key + ".weight"], W[norm_key + ".bias"], pe=pe, rows_per_frame=rows_per_frame)
             if geglu:
                 return ops.gemm(n, W[w_key + ".geglu_w"], W[w_key + ".geglu_b"], geglu=True)
             return ops.gemm(n, W[w_key])
         wf, cs, bf = self.F[norm_key]
-        st = ops.row_stats(h)
         bias2, div = None, 1
         if pe is not None:
             f = pe.shape[0]
@@ -472,7 +478,9 @@ class UNetEngine:
                 bias2 = self._pe_proj[a_][:f].repeat(b, 1).contiguous()
                 self._pe_bias[key] = bias2
             div = rows_per_frame
-        return ops.gemm_lnfold(h, wf, st, cs, bf, bias2=bias2, bias2_div=div, geglu=geglu)
+        if one_kernel:
+            return ops.gemm_ln(h, wf, cs, bf, 1e-5, bias2=bias2, bias2_div=div, geglu=geglu)
+        return ops.gemm_lnfold(h, wf, ops.row_stats(h), cs, bf, bias2=bias2, bias2_div=div, geglu=geglu)
 
     # ---------------------------------------------------------------- banks
     def _bank_kv(self, name: str, block: TemporalBasicTransformerBlock):

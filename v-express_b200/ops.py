@@ -253,6 +253,27 @@ def smallkv_attention(q, k, v, rows_per_frame, heads, Lk, out=None):
     return out
 
 
+LN_GEMM_MAX_K = 512   # vx_gemm_ln_bf16 keeps the whole 128-row x K tile in shared memory
+
+
+def gemm_ln(a, wf, colsum, bias, eps=1e-5, *, bias2=None, bias2_div=1, scale=1.0, residual=None, out=None, geglu=False):
+    """LayerNorm(a) @ W.T + b in one kernel (fold_layernorm's wf / colsum / bias; row statistics computed in the kernel from
+    the shared-memory resident row tile): out = rstd * (a @ wf.T - mean * colsum) + bias (+ bias2[row // bias2_div])
+    (* scale + residual | GEGLU).  K = a.shape[1] must be a multiple of 64 and <= LN_GEMM_MAX_K."""
+    _chk_bf16(a, wf, residual, out)
+    M, K = a.shape
+    N = wf.shape[0]
+    assert wf.shape[1] == K and colsum.shape == (N,) and K % 64 == 0 and K <= LN_GEMM_MAX_K
+    if out is None:
+        out = torch.empty((M, N // 2 if geglu else N), device=a.device, dtype=BF16)
+    check(_ffi.lib().vx_gemm_ln_bf16(
+        ptr(a), c_ll(a.stride(0)), c_int(K), ptr(wf), c_ll(wf.stride(0)), c_int(M), c_int(N), ptr(colsum), ptr(bias),
+        c_float(eps), ptr(bias2), c_int(bias2_div), c_float(scale), ptr(residual),
+        c_ll(0 if residual is None else residual.stride(0)), ptr(out), c_ll(out.stride(0)), c_int(int(geglu)),
+        c_int(geglu_block_n(N) if geglu else 0), stream_ptr()), "vx_gemm_ln_bf16")
+    return out
+
+
 # ----------------------------------------------------------------------------- norms / activations
 _GN_CAP = {}
 
