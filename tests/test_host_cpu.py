@@ -294,7 +294,7 @@ class _ShapeOps:
         return f
 
 
-@pytest.mark.parametrize("fold,one_kernel", [("0", "0"), ("1", "0"), ("0", "1")])
+@pytest.mark.parametrize("fold,one_kernel", [("0", "0"), ("1", "0")])
 def test_transformer_block_schedules_dry_run(monkeypatch, fold, one_kernel):
     """Host logic of UNetEngine._spatial / _motion with shape-checking fake ops, without touching a GPU: the three
     LayerNorm -> Linear schedules -- LayerNorm kernel + GEMM (VX_LN_GEMM=0), row_stats + gemm_lnfold (VX_LN_FOLD=1), and the
@@ -621,7 +621,7 @@ def test_prologue_modules_compose_correctly(monkeypatch, golden_dir):
     assert ya.shape == a["tokens"].shape and rel(ya, a["tokens"]) < 2e-2, rel(ya, a["tokens"])
 
 
-@pytest.mark.parametrize("fold,one_kernel", [("0", "0"), ("1", "0"), ("0", "1")])
+@pytest.mark.parametrize("fold,one_kernel", [("0", "0"), ("1", "0")])
 def test_unet_engine_matches_oracle_with_emulated_kernels(monkeypatch, golden_dir, fold, one_kernel):
     """The whole UNetEngine.forward_frames host schedule (weight packing, split-K concat, time-embedding bias, banks,
     CFG uncond-half skip, GEGLU packing, ...) with every kernel replaced by a functional CPU emulation, against the

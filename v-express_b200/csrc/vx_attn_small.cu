@@ -24,6 +24,7 @@ struct TemporalArgs {
 
 template <int HD>
 __global__ void __launch_bounds__(128) temporal_attn_kernel(const TemporalArgs p) {
+  pdl_enter();
   extern __shared__ uint8_t sm_raw[];
   constexpr int VEC = HD / 8;
   constexpr bool F32 = HD <= 80;                       // K/V staged as fp32 (no unpack in the inner loops)
@@ -281,6 +282,7 @@ __device__ __forceinline__ void attn16_mma(const __nv_bfloat16* q0, const __nv_b
 
 template <int HD>
 __global__ void __launch_bounds__(128) temporal_attn_mma_kernel(const TemporalArgs p) {
+  pdl_enter();
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const long long item = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);   // (b, pixel, head), head fastest
   if (item >= (long long)p.b * p.HW * p.heads) return;
@@ -307,6 +309,7 @@ struct SmallKvArgs {
 };
 
 __global__ void smallkv_attn_kernel(const SmallKvArgs p) {
+  pdl_enter();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= p.rows * p.heads) return;
   const int head = (int)(idx % p.heads);
@@ -374,6 +377,7 @@ __global__ void smallkv_attn_kernel(const SmallKvArgs p) {
 // key rows 0..Lk-1 of the 16-key tile (the rest masked), read once per 16 queries instead of once per query.
 template <int HD>
 __global__ void __launch_bounds__(128) smallkv_attn_mma_kernel(const SmallKvArgs p) {
+  pdl_enter();
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const long long item = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);   // (row tile, head), head fastest
   if (item >= (p.rows / 16) * p.heads) return;
@@ -404,12 +408,12 @@ extern "C" int vx_temporal_attention(const void* q, const void* k, const void* v
     const long long warps = (long long)b * HW * heads;
     const unsigned grid_m = (unsigned)((warps + 3) / 4);
     switch (hd) {
-      case 8: temporal_attn_mma_kernel<8><<<grid_m, 128, 0, st>>>(a); break;
-      case 16: temporal_attn_mma_kernel<16><<<grid_m, 128, 0, st>>>(a); break;
-      case 32: temporal_attn_mma_kernel<32><<<grid_m, 128, 0, st>>>(a); break;
-      case 40: temporal_attn_mma_kernel<40><<<grid_m, 128, 0, st>>>(a); break;
-      case 80: temporal_attn_mma_kernel<80><<<grid_m, 128, 0, st>>>(a); break;
-      case 160: temporal_attn_mma_kernel<160><<<grid_m, 128, 0, st>>>(a); break;
+      case 8: launch_k(temporal_attn_mma_kernel<8>, dim3(grid_m), dim3(128), 0, st, a); break;
+      case 16: launch_k(temporal_attn_mma_kernel<16>, dim3(grid_m), dim3(128), 0, st, a); break;
+      case 32: launch_k(temporal_attn_mma_kernel<32>, dim3(grid_m), dim3(128), 0, st, a); break;
+      case 40: launch_k(temporal_attn_mma_kernel<40>, dim3(grid_m), dim3(128), 0, st, a); break;
+      case 80: launch_k(temporal_attn_mma_kernel<80>, dim3(grid_m), dim3(128), 0, st, a); break;
+      case 160: launch_k(temporal_attn_mma_kernel<160>, dim3(grid_m), dim3(128), 0, st, a); break;
       default: return fail("vx_temporal_attention: head dim %d not instantiated (8,16,32,40,80,160)", hd);
     }
     VX_CHECK_CUDA(cudaGetLastError());
@@ -429,7 +433,7 @@ extern "C" int vx_temporal_attention(const void* q, const void* k, const void* v
                                          200 * 1024));                                                              \
       cfg = true;                                                                                                   \
     }                                                                                                               \
-    temporal_attn_kernel<HD><<<grid, 128, smem, st>>>(a);                                                           \
+    launch_k(temporal_attn_kernel<HD>, dim3(grid), dim3(128), smem, st, a);                                                           \
   } while (0)
   switch (hd) {
     case 8: TA_LAUNCH(8); break;
@@ -459,16 +463,16 @@ extern "C" int vx_smallkv_attention(const void* q, long long ldq, const void* k,
     const long long warps = rows / 16 * heads;
     const unsigned grid_m = (unsigned)((warps + 3) / 4);
     switch (hd) {
-      case 8: smallkv_attn_mma_kernel<8><<<grid_m, 128, 0, st>>>(a); break;
-      case 40: smallkv_attn_mma_kernel<40><<<grid_m, 128, 0, st>>>(a); break;
-      case 80: smallkv_attn_mma_kernel<80><<<grid_m, 128, 0, st>>>(a); break;
-      default: smallkv_attn_mma_kernel<160><<<grid_m, 128, 0, st>>>(a); break;
+      case 8: launch_k(smallkv_attn_mma_kernel<8>, dim3(grid_m), dim3(128), 0, st, a); break;
+      case 40: launch_k(smallkv_attn_mma_kernel<40>, dim3(grid_m), dim3(128), 0, st, a); break;
+      case 80: launch_k(smallkv_attn_mma_kernel<80>, dim3(grid_m), dim3(128), 0, st, a); break;
+      default: launch_k(smallkv_attn_mma_kernel<160>, dim3(grid_m), dim3(128), 0, st, a); break;
     }
     VX_CHECK_CUDA(cudaGetLastError());
     return 0;
   }
   const long long n = rows * heads;
-  smallkv_attn_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(a);
+  launch_k(smallkv_attn_kernel, dim3((unsigned)((n + 127) / 128)), dim3(128), 0, (cudaStream_t)stream, a);
   VX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

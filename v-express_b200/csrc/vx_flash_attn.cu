@@ -84,6 +84,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // shared-memory fill, barrier init and the TMEM allocation overlapped the previous grid's tail
   const uint32_t tmem_o = tmem_base + 256;
 
   if (warp == 0) {
@@ -370,6 +371,7 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // shared-memory fill, barrier init and the TMEM allocation overlapped the previous grid's tail
 
   if (warp == 16) {
     if (lane == 0) {
@@ -748,6 +750,7 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // shared-memory fill, barrier init and the TMEM allocation overlapped the previous grid's tail
   const uint32_t tmem_o = tmem_base + 128u;     // S buffers at columns [0, 64) and [64, 128)
 
   if (warp == 4) {
@@ -841,6 +844,7 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
         issue_s(j + 2);
       }
     }
+    pdl_trigger();   // the last P.V is issued: the next grid may launch behind this CTA's epilogue (matters in the last wave)
   } else {
     // ------------------------------------------------------------ softmax: warp = TMEM lane quadrant, thread = query row
     const int row = warp * 32 + lane;
@@ -996,6 +1000,7 @@ struct GaArgs {
 };
 
 __global__ void __launch_bounds__(128) generic_attn_kernel(const GaArgs p) {
+  pdl_enter();
   extern __shared__ float sc_all[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* sc = sc_all + warp * p.Nk;
@@ -1096,7 +1101,7 @@ extern "C" int vx_flash_attention(const void* q, long long ldq, const void* k, l
     GaArgs g{(const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)k, ldk, (const __nv_bfloat16*)v, ldv,
              (__nv_bfloat16*)out, ldo, Bq, Nq, Nk, heads, hd, kv_div, 1.0f / sqrtf((float)hd)};
     const long long items = (long long)Bq * heads * Nq;
-    generic_attn_kernel<<<(unsigned)((items + 3) / 4), 128, (size_t)Nk * 4 * 4, (cudaStream_t)stream>>>(g);
+    launch_k(generic_attn_kernel, dim3((unsigned)((items + 3) / 4)), dim3(128), (size_t)Nk * 4 * 4, (cudaStream_t)stream, g);
     VX_CHECK_CUDA(cudaGetLastError());
     return 0;
   }
@@ -1143,10 +1148,10 @@ extern "C" int vx_flash_attention(const void* q, long long ldq, const void* k, l
     dim3 grid3(Nq / 128, heads, Bq);
     const bool ones = hdp > hd && !env.noones;
     auto st3 = (cudaStream_t)stream;
-    if (ones && env.poly == 4) flash_attn3_kernel<true, 3, 2><<<grid3, kFa3Threads, smem3, st3>>>(mQ, mK, mV, a);
-    else if (ones && env.poly == 2) flash_attn3_kernel<true, 1, 2><<<grid3, kFa3Threads, smem3, st3>>>(mQ, mK, mV, a);
-    else if (ones) flash_attn3_kernel<true, 7, 2><<<grid3, kFa3Threads, smem3, st3>>>(mQ, mK, mV, a);
-    else flash_attn3_kernel<false, 7, 2><<<grid3, kFa3Threads, smem3, st3>>>(mQ, mK, mV, a);
+    if (ones && env.poly == 4) launch_k((flash_attn3_kernel<true, 3, 2>), dim3(grid3), dim3(kFa3Threads), smem3, st3, mQ, mK, mV, a);
+    else if (ones && env.poly == 2) launch_k((flash_attn3_kernel<true, 1, 2>), dim3(grid3), dim3(kFa3Threads), smem3, st3, mQ, mK, mV, a);
+    else if (ones) launch_k((flash_attn3_kernel<true, 7, 2>), dim3(grid3), dim3(kFa3Threads), smem3, st3, mQ, mK, mV, a);
+    else launch_k((flash_attn3_kernel<false, 7, 2>), dim3(grid3), dim3(kFa3Threads), smem3, st3, mQ, mK, mV, a);
     VX_CHECK_CUDA(cudaGetLastError());
     return 0;
   }
@@ -1198,12 +1203,12 @@ extern "C" int vx_flash_attention(const void* q, long long ldq, const void* k, l
     const bool baton = env.baton != 0;
     const int poly = env.poly;      // 1/poly of the exponentials on the FMA pipe
     auto st2 = (cudaStream_t)stream;
-    if (ones && baton && poly == 4) flash_attn2_kernel<true, true, 3><<<grid2, kFa2Threads, smem2, st2>>>(mQ, mK, mV, a);
-    else if (ones && baton && poly == 2) flash_attn2_kernel<true, true, 1><<<grid2, kFa2Threads, smem2, st2>>>(mQ, mK, mV, a);
-    else if (ones && baton) flash_attn2_kernel<true, true, 7><<<grid2, kFa2Threads, smem2, st2>>>(mQ, mK, mV, a);
-    else if (ones) flash_attn2_kernel<true, false, 7><<<grid2, kFa2Threads, smem2, st2>>>(mQ, mK, mV, a);
-    else if (baton) flash_attn2_kernel<false, true, 7><<<grid2, kFa2Threads, smem2, st2>>>(mQ, mK, mV, a);
-    else flash_attn2_kernel<false, false, 7><<<grid2, kFa2Threads, smem2, st2>>>(mQ, mK, mV, a);
+    if (ones && baton && poly == 4) launch_k((flash_attn2_kernel<true, true, 3>), dim3(grid2), dim3(kFa2Threads), smem2, st2, mQ, mK, mV, a);
+    else if (ones && baton && poly == 2) launch_k((flash_attn2_kernel<true, true, 1>), dim3(grid2), dim3(kFa2Threads), smem2, st2, mQ, mK, mV, a);
+    else if (ones && baton) launch_k((flash_attn2_kernel<true, true, 7>), dim3(grid2), dim3(kFa2Threads), smem2, st2, mQ, mK, mV, a);
+    else if (ones) launch_k((flash_attn2_kernel<true, false, 7>), dim3(grid2), dim3(kFa2Threads), smem2, st2, mQ, mK, mV, a);
+    else if (baton) launch_k((flash_attn2_kernel<false, true, 7>), dim3(grid2), dim3(kFa2Threads), smem2, st2, mQ, mK, mV, a);
+    else launch_k((flash_attn2_kernel<false, false, 7>), dim3(grid2), dim3(kFa2Threads), smem2, st2, mQ, mK, mV, a);
     VX_CHECK_CUDA(cudaGetLastError());
     return 0;
   }
@@ -1249,7 +1254,7 @@ extern "C" int vx_flash_attention(const void* q, long long ldq, const void* k, l
     cfg = true;
   }
   dim3 grid((Nq + 127) / 128, heads, Bq);
-  flash_attn_kernel<<<grid, kFaThreads, smem, (cudaStream_t)stream>>>(mQ, mK, mV, a);
+  launch_k(flash_attn_kernel, dim3(grid), dim3(kFaThreads), smem, (cudaStream_t)stream, mQ, mK, mV, a);
   VX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -259,6 +259,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   if (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above (barrier init, tensor-map prefetch, TMEM allocation, the pair's cluster rendezvous) overlapped the
+  // previous grid's tail; from here on every role touches global memory
+  pdl_wait();
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -446,6 +449,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       }
       __syncwarp();
     }
+    pdl_trigger();   // last tile issued (or nothing to issue): the next grid may launch while the epilogue drains
   } else if (warp == 10) {
     // ------------------------------------------------------------ TMA store + residual prefetch (one lane)
     if (lane == 0 && !p.out_f32) {   // few TMA ops per tile: the single-lane form is good enough here
@@ -877,8 +881,8 @@ static int launch(const CUtensorMap& mA, const CUtensorMap& mA2, const CUtensorM
   if (cg == 1) {
     const int tiles = a.ares ? a.tiles_m : a.tiles_m * a.tiles_n * npar;
     const int grid = tiles < num_sms() ? tiles : num_sms();
-    if (lnf) gemm_tcgen05_kernel<1, true><<<grid, threads, smem, st>>>(mA, mA2, mB, mR, mC, a);
-    else gemm_tcgen05_kernel<1, false><<<grid, kThreads, smem, st>>>(mA, mA2, mB, mR, mC, a);
+    if (lnf) VX_CHECK_CUDA(launch_k((gemm_tcgen05_kernel<1, true>), dim3(grid), dim3(threads), smem, st, mA, mA2, mB, mR, mC, a));
+    else VX_CHECK_CUDA(launch_k((gemm_tcgen05_kernel<1, false>), dim3(grid), dim3(kThreads), smem, st, mA, mA2, mB, mR, mC, a));
   } else {
     const int items = a.ares ? (a.tiles_m + 1) / 2 : ((a.tiles_m + 1) / 2) * a.tiles_n * npar;
     const int pairs = items < num_pairs() ? items : num_pairs();
@@ -887,13 +891,15 @@ static int launch(const CUtensorMap& mA, const CUtensorMap& mA2, const CUtensorM
     cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     if (lnf) VX_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<2, true>, mA, mA2, mB, mR, mC, a));
     else VX_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<2, false>, mA, mA2, mB, mR, mC, a));
   }

@@ -5,6 +5,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <utility>
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -58,6 +59,29 @@ inline int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint
     return fail("cuTensorMapEncodeTiled failed: %d (rank %d dims %llu,%llu box %u,%u)", (int)r, rank,
                 (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0), box[0], rank > 1 ? box[1] : 0);
   return 0;
+}
+
+// Programmatic dependent launch: every hot-path kernel starts with `griddepcontrol.launch_dependents` (its successor may
+// be scheduled as soon as all of this grid's CTAs have started) and runs `griddepcontrol.wait` before its first access to
+// global memory (which returns once the predecessor grid has completed and flushed).  Launched through launch_k with the
+// programmatic-stream-serialization attribute, the successor's launch latency and prologue (barrier init, TMEM
+// allocation, tensor-map prefetch, parameter staging) overlap the predecessor's tail, in eager streams and as
+// programmatic edges under CUDA-graph capture.  VX_PDL=0 launches with full stream serialisation (A/B switch, read once).
+bool pdl_enabled();  // vx_runtime.cu
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
 }
 
 }  // namespace vx

@@ -29,6 +29,7 @@ __device__ __forceinline__ float rbf16(float v) { return __bfloat162float(__floa
 
 template <int CIN>
 __global__ void __launch_bounds__(256) conv_in_kernel(const ConvInArgs p) {
+  pdl_enter();
   // Every thread owns 8 output channels of 4 horizontally adjacent pixels, so each weight read from shared memory
   // feeds 4 FMAs (one pixel per thread left the kernel bound by shared-memory bandwidth, 1 LDS word per FMA).
   // Weights sit in two planes [K][Cout/2] (channels 8v..8v+3 | 8v+4..8v+7 of vector v) so that consecutive lanes
@@ -135,6 +136,7 @@ struct ConvOutArgs {
 };
 
 __global__ void conv_out_kernel(const ConvOutArgs p) {
+  pdl_enter();
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long npix = (long long)p.NB * p.H * p.W;
@@ -190,6 +192,7 @@ __global__ void conv_out_kernel(const ConvOutArgs p) {
 __global__ void extract_planar_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, long long npix, int HW,
                                       int Cout, void* __restrict__ out, long long sn, long long sc, int out_f32,
                                       int post) {
+  pdl_enter();
   for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < npix;
        pix += (long long)gridDim.x * blockDim.x) {
     const uint4 u = *reinterpret_cast<const uint4*>(x + pix * ldx);
@@ -218,6 +221,7 @@ __global__ void extract_planar_kernel(const __nv_bfloat16* __restrict__ x, long 
 // ------------------------------------------------------------------ im2col (3x3, stride 2, pad 1), NHWC
 __global__ void im2col_s2_kernel(const __nv_bfloat16* __restrict__ x, int NB, int H, int W, int C,
                                  __nv_bfloat16* __restrict__ out) {
+  pdl_enter();
   const int Ho = H / 2, Wo = W / 2, V = C / 8;
   const long long total = (long long)NB * Ho * Wo * 9 * V;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -238,6 +242,7 @@ __global__ void im2col_s2_kernel(const __nv_bfloat16* __restrict__ x, int NB, in
 // ------------------------------------------------------------------ nearest 2x upsample, NHWC
 __global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ x, int NB, int H, int W, int C,
                                   __nv_bfloat16* __restrict__ out) {
+  pdl_enter();
   const int V = C / 8;
   const long long total = (long long)NB * 2 * H * 2 * W * V;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -256,6 +261,7 @@ __global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ x, int NB, i
 __global__ void skinny_linear_kernel(const float* __restrict__ x, int rows, int K, const __nv_bfloat16* __restrict__ w,
                                      const float* __restrict__ bias, int N, int act_in, int act_out,
                                      float* __restrict__ y) {
+  pdl_enter();
   const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (n >= N) return;
@@ -300,6 +306,7 @@ __global__ void skinny_linear_kernel(const float* __restrict__ x, int rows, int 
 // Timesteps(dim, flip_sin_to_cos=True, shift 0): out[r] = [cos(t*f_i) | sin(t*f_i)], rounded through bf16 like the
 // reference's cast to the model dtype (modules/unet_3d.py:469).
 __global__ void timestep_embed_kernel(const float* __restrict__ t, int rows, int dim, float* __restrict__ out) {
+  pdl_enter();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int half = dim / 2;
   if (idx >= rows * half) return;
@@ -323,6 +330,7 @@ struct CfgArgs {
 __device__ __forceinline__ float rbf(float v) { return __bfloat162float(__float2bfloat16(v)); }
 
 __global__ void cfg_overlap_kernel(const CfgArgs p) {
+  pdl_enter();
   const long long total = (long long)4 * p.f * p.hw;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -350,6 +358,7 @@ __global__ void cfg_overlap_kernel(const CfgArgs p) {
 // (diffusers DDIMScheduler.step with fp32 scalar coefficients on model-dtype tensors).
 __global__ void ddim_step_kernel(__nv_bfloat16* __restrict__ latents, const float* __restrict__ acc, long long n,
                                  float sa, float sb, float sap, float sbp) {
+  pdl_enter();
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
        idx += (long long)gridDim.x * blockDim.x) {
     const float x = __bfloat162float(latents[idx]);
@@ -381,7 +390,7 @@ extern "C" int vx_conv_in(const void* in, long long sn, long long sc, int NB, in
   const long long total = (long long)NB * H * ((W + 3) / 4) * (Cout / 8);
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 4) blocks = 148 * 4;
-  conv_in_kernel<4><<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(a);
+  launch_k(conv_in_kernel<4>, dim3((unsigned)blocks), dim3(256), smem, (cudaStream_t)stream, a);
   VX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -392,7 +401,7 @@ extern "C" int vx_conv_out(const void* x, long long ldx, int NB, int H, int W, i
   VX_REQUIRE(C % 8 == 0 && Cout >= 1 && Cout <= 4, "vx_conv_out: C=%d Cout=%d unsupported", C, Cout);
   ConvOutArgs a{(const __nv_bfloat16*)x, ldx, NB, H, W, C, Cout, w, bias, out, sn, sc, out_f32, post};
   const long long npix = (long long)NB * H * W;
-  conv_out_kernel<<<(unsigned)((npix * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a);
+  launch_k(conv_out_kernel, dim3((unsigned)((npix * 32 + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, a);
   VX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -403,7 +412,7 @@ extern "C" int vx_extract_planar(const void* x, long long ldx, int NB, int HW, i
   const long long npix = (long long)NB * HW;
   long long blocks = (npix + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  extract_planar_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, ldx, npix, HW, Cout,
+  launch_k(extract_planar_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, (const __nv_bfloat16*)x, ldx, npix, HW, Cout,
                                                                           out, sn, sc, out_f32, post);
   VX_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -414,7 +423,7 @@ extern "C" int vx_im2col_s2(const void* x, int NB, int H, int W, int C, void* ou
   const long long total = (long long)NB * (H / 2) * (W / 2) * 9 * (C / 8);
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  im2col_s2_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, NB, H, W, C,
+  launch_k(im2col_s2_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, (const __nv_bfloat16*)x, NB, H, W, C,
                                                                       (__nv_bfloat16*)out);
   VX_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -425,7 +434,7 @@ extern "C" int vx_upsample2x(const void* x, int NB, int H, int W, int C, void* o
   const long long total = (long long)NB * 4 * H * W * (C / 8);
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  upsample2x_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, NB, H, W, C,
+  launch_k(upsample2x_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, (const __nv_bfloat16*)x, NB, H, W, C,
                                                                        (__nv_bfloat16*)out);
   VX_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -434,7 +443,7 @@ extern "C" int vx_upsample2x(const void* x, int NB, int H, int W, int C, void* o
 extern "C" int vx_skinny_linear(const float* x, int rows, int K, const void* w, const float* bias, int N, int act_in,
                                 int act_out, float* y, void* stream) {
   VX_REQUIRE(rows >= 1 && rows <= 8 && K % 8 == 0, "vx_skinny_linear: rows=%d K=%d", rows, K);
-  skinny_linear_kernel<<<(N * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(x, rows, K, (const __nv_bfloat16*)w, bias,
+  launch_k(skinny_linear_kernel, dim3((N * 32 + 255) / 256), dim3(256), 0, (cudaStream_t)stream, x, rows, K, (const __nv_bfloat16*)w, bias,
                                                                               N, act_in, act_out, y);
   VX_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -442,7 +451,7 @@ extern "C" int vx_skinny_linear(const float* x, int rows, int K, const void* w, 
 
 extern "C" int vx_timestep_embed(const float* t, int rows, int dim, float* out, void* stream) {
   const int n = rows * (dim / 2);
-  timestep_embed_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(t, rows, dim, out);
+  launch_k(timestep_embed_kernel, dim3((n + 127) / 128), dim3(128), 0, (cudaStream_t)stream, t, rows, dim, out);
   VX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -451,7 +460,7 @@ extern "C" int vx_cfg_overlap_accumulate(const void* noise, int f, int hw, int L
                                          const int* count, float guidance, float* acc, void* stream) {
   CfgArgs a{(const __nv_bfloat16*)noise, f, hw, L, do_cfg, win, count, guidance, acc};
   const long long total = (long long)4 * f * hw;
-  cfg_overlap_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a);
+  launch_k(cfg_overlap_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, a);
   VX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -460,7 +469,7 @@ extern "C" int vx_ddim_step(void* latents, const float* acc, long long n, float 
                             float sqrt_aprev, float sqrt_1maprev, void* stream) {
   long long blocks = (n + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  ddim_step_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)latents, acc, n, sqrt_a,
+  launch_k(ddim_step_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, (__nv_bfloat16*)latents, acc, n, sqrt_a,
                                                                       sqrt_1ma, sqrt_aprev, sqrt_1maprev);
   VX_CHECK_CUDA(cudaGetLastError());
   return 0;

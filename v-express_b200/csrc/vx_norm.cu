@@ -92,6 +92,7 @@ __device__ __forceinline__ void gn_stats_body(const GnStatsArgs& p, float* sm, c
 }
 
 __global__ void gn_stats_kernel(const GnStatsArgs p) {
+  pdl_enter();
   extern __shared__ float sm[];
   gn_stats_body(p, sm, blockIdx.y, blockIdx.x);
 }
@@ -223,6 +224,7 @@ __device__ __forceinline__ void gn_apply_body(const GnApplyArgs& p, float* sm, c
 }
 
 __global__ void gn_apply_kernel(const GnApplyArgs p) {
+  pdl_enter();
   extern __shared__ float sm[];
   gn_apply_body(p, sm, blockIdx.y, blockIdx.x, [] {});
 }
@@ -243,6 +245,7 @@ struct GnFusedArgs {
 };
 
 __global__ void gn_fused_kernel(const GnFusedArgs p) {
+  pdl_enter();
   extern __shared__ float sm[];
   const int n = blockIdx.y, s = blockIdx.x;
   gn_stats_body(p.st, sm, n, s);
@@ -274,6 +277,7 @@ __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long 
                                  const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                  const float* __restrict__ pe, int pe_rows_per_frame, int pe_frames,
                                  __nv_bfloat16* __restrict__ out, long long ldo) {
+  pdl_enter();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
@@ -332,6 +336,7 @@ __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long 
 // ------------------------------------------------------------------ GEGLU gate
 __global__ void geglu_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, long long rows, int inner,
                              __nv_bfloat16* __restrict__ out, long long ldo) {
+  pdl_enter();
   const int V = inner / 8;
   const long long total = rows * V;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -351,6 +356,7 @@ __global__ void geglu_kernel(const __nv_bfloat16* __restrict__ x, long long ldx,
 // one CTA per row; used by the single-head hd=512 attention of the VAE decoder mid block
 __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ x, long long ldx, int n,
                                                            __nv_bfloat16* __restrict__ out, long long ldo) {
+  pdl_enter();
   __shared__ float red[8];
   const float* row = x + (long long)blockIdx.x * ldx;
   float mx = -INFINITY;
@@ -394,6 +400,7 @@ __global__ void __launch_bounds__(256, MINB) layernorm5_kernel(const __nv_bfloat
                                                             const float* __restrict__ beta, float eps,
                                                             const float* __restrict__ pe, int pe_rows_per_frame,
                                                             int pe_frames, __nv_bfloat16* __restrict__ out, long long ldo) {
+  pdl_enter();
   constexpr int RPW = 32 / LPR;
   constexpr int C = LPR * 40;
   // gamma / beta live in shared memory (2.5 - 10 KB): in registers they cost 80 registers per thread, i.e. ONE resident
@@ -490,6 +497,7 @@ __global__ void __launch_bounds__(256, MINB) layernorm5_kernel(const __nv_bfloat
 template <int LPR>
 __global__ void __launch_bounds__(256) row_stats5_kernel(const __nv_bfloat16* __restrict__ x, long long ldx,
                                                          long long rows, float eps, float* __restrict__ stats) {
+  pdl_enter();
   constexpr int RPW = 32 / LPR;
   constexpr int C = LPR * 40;
   const int lane = threadIdx.x & 31;
@@ -537,6 +545,7 @@ __global__ void __launch_bounds__(256) row_stats5_kernel(const __nv_bfloat16* __
 template <int MAXV>
 __global__ void row_stats_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, long long rows, int C, float eps,
                                  float* __restrict__ stats) {
+  pdl_enter();
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
@@ -579,7 +588,7 @@ using namespace vx;
 extern "C" int vx_softmax_rows(const float* x, long long ldx, long long rows, int n, void* out, long long ldo,
                                void* stream) {
   VX_REQUIRE(n % 4 == 0 && ldx % 4 == 0 && ldo % 4 == 0, "vx_softmax_rows: n=%d must be a multiple of 4", n);
-  softmax_rows_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(x, ldx, n, (__nv_bfloat16*)out, ldo);
+  launch_k(softmax_rows_kernel, dim3((unsigned)rows), dim3(256), 0, (cudaStream_t)stream, x, ldx, n, (__nv_bfloat16*)out, ldo);
   VX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -607,7 +616,7 @@ extern "C" int vx_groupnorm_stats(const void* x1, long long ld1, int C1, const v
   VX_REQUIRE(smem <= 200 * 1024, "vx_groupnorm_stats: smem %zu too large", smem);
   if (smem > 48 * 1024)
     VX_CHECK_CUDA(cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  gn_stats_kernel<<<dim3(S, NB), threads, smem, (cudaStream_t)stream>>>(a);
+  launch_k(gn_stats_kernel, dim3(S, NB), dim3(threads), smem, (cudaStream_t)stream, a);
   VX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -628,7 +637,7 @@ extern "C" int vx_groupnorm_apply(const void* x1, long long ld1, int C1, const v
   const size_t smem = (size_t)(2 * C + 2 * G) * sizeof(float);
   int Rr;
   const int threads = gn_block(C, &Rr);
-  gn_apply_kernel<<<dim3((HW + chunk - 1) / chunk, NB), threads, smem, (cudaStream_t)stream>>>(a);
+  launch_k(gn_apply_kernel, dim3((HW + chunk - 1) / chunk, NB), dim3(threads), smem, (cudaStream_t)stream, a);
   VX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -683,7 +692,7 @@ extern "C" int vx_groupnorm_fused(const void* x1, long long ld1, int C1, const v
   VX_CHECK_CUDA(cudaGetDevice(&dev));
   VX_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   if ((long long)NB * S > (long long)per_sm * sms) return 2;   // a rendezvous needs every CTA resident
-  gn_fused_kernel<<<dim3(S, NB), threads, smem, (cudaStream_t)stream>>>(a);
+  launch_k(gn_fused_kernel, dim3(S, NB), dim3(threads), smem, (cudaStream_t)stream, a);
   VX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -710,10 +719,10 @@ extern "C" int vx_layernorm(const void* x, long long ldx, long long rows, int C,
 #define LN5_LAUNCH(LPR)                                                                                               \
   do {                                                                                                               \
     if (minb == 2)                                                                                                   \
-      layernorm5_kernel<LPR, 2><<<(unsigned)nb, 256, 0, st>>>((const __nv_bfloat16*)x, ldx, rows, gamma, beta, eps, pe, \
+      launch_k((layernorm5_kernel<LPR, 2>), dim3((unsigned)nb), dim3(256), 0, st, (const __nv_bfloat16*)x, ldx, rows, gamma, beta, eps, pe, \
                                                               rows_per_frame, pe_frames, (__nv_bfloat16*)out, ldo);  \
     else                                                                                                             \
-      layernorm5_kernel<LPR, 3><<<(unsigned)nb, 256, 0, st>>>((const __nv_bfloat16*)x, ldx, rows, gamma, beta, eps, pe, \
+      launch_k((layernorm5_kernel<LPR, 3>), dim3((unsigned)nb), dim3(256), 0, st, (const __nv_bfloat16*)x, ldx, rows, gamma, beta, eps, pe, \
                                                               rows_per_frame, pe_frames, (__nv_bfloat16*)out, ldo);  \
   } while (0)
     if (lpr == 8) LN5_LAUNCH(8);
@@ -724,7 +733,7 @@ extern "C" int vx_layernorm(const void* x, long long ldx, long long rows, int C,
     return 0;
   }
 #define LN_LAUNCH(MV)                                                                                            \
-  layernorm_kernel<MV><<<(unsigned)blocks, threads, 0, st>>>((const __nv_bfloat16*)x, ldx, (int)rows, C, gamma, \
+  launch_k(layernorm_kernel<MV>, dim3((unsigned)blocks), dim3(threads), 0, st, (const __nv_bfloat16*)x, ldx, (int)rows, C, gamma, \
                                                              beta, eps, pe, rows_per_frame, pe_frames,          \
                                                              (__nv_bfloat16*)out, ldo)
   if (V <= 32) LN_LAUNCH(1);
@@ -744,7 +753,7 @@ extern "C" int vx_geglu(const void* x, long long ldx, long long rows, int inner,
   const long long total = rows * (inner / 8);
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  geglu_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, ldx, rows, inner,
+  launch_k(geglu_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, (const __nv_bfloat16*)x, ldx, rows, inner,
                                                                   (__nv_bfloat16*)out, ldo);
   VX_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -761,17 +770,17 @@ extern "C" int vx_row_stats(const void* x, long long ldx, long long rows, int C,
     long long nb = (groups + 7) / 8;
     if (nb > 148 * 8) nb = 148 * 8;
     if (nb < 1) nb = 1;
-    if (lpr == 8) row_stats5_kernel<8><<<(unsigned)nb, 256, 0, st>>>((const __nv_bfloat16*)x, ldx, rows, eps, stats);
-    else if (lpr == 16) row_stats5_kernel<16><<<(unsigned)nb, 256, 0, st>>>((const __nv_bfloat16*)x, ldx, rows, eps, stats);
-    else row_stats5_kernel<32><<<(unsigned)nb, 256, 0, st>>>((const __nv_bfloat16*)x, ldx, rows, eps, stats);
+    if (lpr == 8) launch_k(row_stats5_kernel<8>, dim3((unsigned)nb), dim3(256), 0, st, (const __nv_bfloat16*)x, ldx, rows, eps, stats);
+    else if (lpr == 16) launch_k(row_stats5_kernel<16>, dim3((unsigned)nb), dim3(256), 0, st, (const __nv_bfloat16*)x, ldx, rows, eps, stats);
+    else launch_k(row_stats5_kernel<32>, dim3((unsigned)nb), dim3(256), 0, st, (const __nv_bfloat16*)x, ldx, rows, eps, stats);
   } else {
     const long long blocks = (rows * 32 + 255) / 256;
     const int V = C / 8;
-    if (V <= 32) row_stats_kernel<1><<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16*)x, ldx, rows, C, eps, stats);
-    else if (V <= 64) row_stats_kernel<2><<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16*)x, ldx, rows, C, eps, stats);
-    else if (V <= 96) row_stats_kernel<3><<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16*)x, ldx, rows, C, eps, stats);
-    else if (V <= 160) row_stats_kernel<5><<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16*)x, ldx, rows, C, eps, stats);
-    else row_stats_kernel<8><<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16*)x, ldx, rows, C, eps, stats);
+    if (V <= 32) launch_k(row_stats_kernel<1>, dim3((unsigned)blocks), dim3(256), 0, st, (const __nv_bfloat16*)x, ldx, rows, C, eps, stats);
+    else if (V <= 64) launch_k(row_stats_kernel<2>, dim3((unsigned)blocks), dim3(256), 0, st, (const __nv_bfloat16*)x, ldx, rows, C, eps, stats);
+    else if (V <= 96) launch_k(row_stats_kernel<3>, dim3((unsigned)blocks), dim3(256), 0, st, (const __nv_bfloat16*)x, ldx, rows, C, eps, stats);
+    else if (V <= 160) launch_k(row_stats_kernel<5>, dim3((unsigned)blocks), dim3(256), 0, st, (const __nv_bfloat16*)x, ldx, rows, C, eps, stats);
+    else launch_k(row_stats_kernel<8>, dim3((unsigned)blocks), dim3(256), 0, st, (const __nv_bfloat16*)x, ldx, rows, C, eps, stats);
   }
   VX_CHECK_CUDA(cudaGetLastError());
   return 0;

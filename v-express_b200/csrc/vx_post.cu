@@ -45,6 +45,7 @@ __device__ __forceinline__ int reflect(int i, int n) { return i < 0 ? -i : (i >=
 // video: [C][T][H][W] fp32; filtered (optional): same layout; frames (optional): [T][H][W][C] uint8
 __global__ void __launch_bounds__(256) median3d_kernel(const float* __restrict__ video, int C, int T, int H, int W,
                                                        float* __restrict__ filtered, unsigned char* __restrict__ frames) {
+  pdl_enter();
   const long long npix = (long long)T * H * W;
   const long long plane = (long long)H * W;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < npix;
@@ -82,6 +83,7 @@ __global__ void __launch_bounds__(256) median3d_kernel(const float* __restrict__
 // order of pack_conv3x3_weight.  Same structure as im2col_s2_kernel (vx_misc.cu).
 __global__ void im2col3x3_kernel(const __nv_bfloat16* __restrict__ x, int NB, int H, int W, int C, int stride, int silu,
                                  int pad_lo, __nv_bfloat16* __restrict__ out) {
+  pdl_enter();
   // pad_lo = 1: pad 1 on every side (nn.Conv2d(padding=1)); pad_lo = 0: pad (0, 1, 0, 1) -- right/bottom only, the
   // diffusers Downsample2D(padding=0) of the VAE encoder -- same output size for even H, W at stride 2
   const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1, V = C / 8;
@@ -122,7 +124,7 @@ extern "C" int vx_im2col3x3(const void* x, int NB, int H, int W, int C, int stri
   const long long total = (long long)NB * ((H - 1) / stride + 1) * ((W - 1) / stride + 1) * 9 * (C / 8);
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  im2col3x3_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, NB, H, W, C, stride, silu,
+  launch_k(im2col3x3_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, (const __nv_bfloat16*)x, NB, H, W, C, stride, silu,
                                                                       pad_lo, (__nv_bfloat16*)out);
   VX_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -135,7 +137,7 @@ extern "C" int vx_median3d_u8(const float* video, int C, int T, int H, int W, fl
   const long long npix = (long long)T * H * W;
   long long blocks = (npix + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  median3d_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(video, C, T, H, W, filtered, frames);
+  launch_k(median3d_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, video, C, T, H, W, filtered, frames);
   VX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -1,5 +1,6 @@
 // C-ABI runtime glue: error string, driver entry point for TMA descriptor encoding, device query.
 #include "vx_host.h"
+#include <cstdlib>
 
 namespace vx {
 
@@ -22,7 +23,20 @@ PFN_encodeTiled get_encode_tiled() {
   return fn;
 }
 
+static int g_pdl = -1;   // -1: not read yet
+bool pdl_enabled() {
+  if (g_pdl < 0) {
+    const char* e = getenv("VX_PDL");
+    g_pdl = e ? (atoi(e) != 0) : 0;
+  }
+  return g_pdl != 0;
+}
+
 }  // namespace vx
+
+// bring-up hook (csrc/vx_bringup.h): flip programmatic dependent launch inside one process (A/B tests)
+extern "C" void vx_pdl_set(int on) { vx::g_pdl = on ? 1 : 0; }
+extern "C" int vx_pdl_get() { return vx::pdl_enabled() ? 1 : 0; }
 
 extern "C" const char* vx_last_error() { return vx::last_error_buf(); }
 

@@ -421,22 +421,20 @@ class UNetEngine:
 
     # ---------------------------------------------------------------- LayerNorm folded into the consumer GEMM
     def _pack_ln_fold(self):
-        """LayerNorm -> Linear pairs of the transformer blocks with the normalisation applied in the GEMM epilogue
-        (ops.fold_layernorm), so LayerNorm(x) is never written to HBM.
-        Default (VX_LN_GEMM=0 turns it off): the pairs of the 320-wide level (K <= ops.LN_GEMM_MAX_K) run as ONE kernel,
-        ops.gemm_ln -- the row tile stays resident in shared memory, the kernel computes the statistics itself.
-        VX_LN_FOLD=1 (experiment): the wider levels too, as vx_row_stats + ops.gemm_lnfold (measured: no gain there)."""
+        """VX_LN_FOLD=1 (experiment, measured: parity green, no gain -- stays off): the LayerNorm -> Linear pairs of the
+        transformer blocks as vx_row_stats + ops.gemm_lnfold (normalisation applied in the GEMM epilogue,
+        ops.fold_layernorm), so LayerNorm(x) is never written to HBM.
+        The one-kernel variant (ops.gemm_ln: row tile resident in shared memory, statistics computed in the kernel) passes
+        its operator tests but measured SLOWER than LayerNorm kernel + GEMM at the 320-wide level (379 vs 44 + 250 us for
+        norm3 -> FF1, gpurun_out/r02_c21) and is not wired into the engine."""
         self.ln_fold = os.environ.get("VX_LN_FOLD") == "1"
-        self.ln_gemm = os.environ.get("VX_LN_GEMM", "0") != "0"   # default flips to on once the GPU run has validated it
         self.F: Dict[str, tuple] = {}
         self._pe_proj: Dict[str, torch.Tensor] = {}
         self._pe_bias: Dict[tuple, torch.Tensor] = {}
-        if not (self.ln_fold or self.ln_gemm):
+        if not self.ln_fold:
             return
         W = self.W
         for k in list(W):
-            if not (self.ln_fold or W[k].shape[0] <= ops.LN_GEMM_MAX_K):
-                continue
             if k.endswith(".norm1.weight") and ".attentions." in k:
                 t = k[:-len(".norm1.weight")]
                 for norm, lin in (("norm1", "attn1.qkv"), ("norm1_5", "attn1_5.to_q.weight"), ("norm2", "attn2.to_q.weight")):
@@ -461,8 +459,7 @@ class UNetEngine:
         statistics kernel and the GEMM with the normalising epilogue."""
         W = self.W
         K = h.shape[1]
-        one_kernel = self.ln_gemm and K <= ops.LN_GEMM_MAX_K and K % 64 == 0 and norm_key in self.F
-        if not (self.ln_fold or one_kernel):
+        if not self.ln_fold:
             n = ops.layernorm(h, W[norm_key + ".weight"], W[norm_key + ".bias"], pe=pe, rows_per_frame=rows_per_frame)
             if geglu:
                 return ops.gemm(n, W[w_key + ".geglu_w"], W[w_key + ".geglu_b"], geglu=True)
@@ -478,8 +475,6 @@ class UNetEngine:
                 bias2 = self._pe_proj[a_][:f].repeat(b, 1).contiguous()
                 self._pe_bias[key] = bias2
             div = rows_per_frame
-        if one_kernel:
-            return ops.gemm_ln(h, wf, cs, bf, 1e-5, bias2=bias2, bias2_div=div, geglu=geglu)
         return ops.gemm_lnfold(h, wf, ops.row_stats(h), cs, bf, bias2=bias2, bias2_div=div, geglu=geglu)
 
     # ---------------------------------------------------------------- banks
