@@ -162,6 +162,14 @@ int vx_median3d_u8(const float* video, int C, int T, int H, int W, float* filter
 int vx_upconv3x3_bf16(const void* X, int NB, int H, int W, int C, const void* Wt, int Cout, const float* bias, void* out,
                       long long ldc, int block_n, void* stream);
 
+/* ---- 3x3 convolution with stride 2 on the tensor cores without a gathered copy of the input: the implicit-GEMM A boxes
+ * are fetched through a TMA tensor map with traversal stride 2 along x and y.  X [NB,H,W,C] (H, W even), W [Cout, 9*C],
+ * out [NB*(H/2)*(W/2), ldc].  pad_lo = 1: nn.Conv2d(stride=2, padding=1), the Downsample3D / Downsample2D of the denoising
+ * UNet and the ReferenceNet (reference modules/resnet.py:93-120, modules/unet_3d_blocks.py:483-486, 620-623);
+ * pad_lo = 0: F.pad(x, (0,1,0,1)) + padding 0, the Downsample2D(padding=0) of the VAE encoder (diffusers). */
+int vx_conv3x3s2_bf16(const void* X, int NB, int H, int W, int C, const void* Wt, int Cout, const float* bias, int pad_lo,
+                      void* out, long long ldc, int block_n, void* stream);
+
 /* ---- conditioning prologue: im2col of a 3x3 conv (stride 1 or 2, pad 1, NHWC bf16) with an
  * optional SiLU on the gathered input; VKpsGuider's narrow conv -> SiLU chain (modules/v_kps_guider.py:35-45) runs as
  * im2col(SiLU(x)) + vx_gemm_bf16.  out [NB*Ho*Wo, 9*C], K order (tap, channel).  pad_lo = 1: pad 1 all round;

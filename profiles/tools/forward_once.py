@@ -42,6 +42,18 @@ def meta_of(name, a, k):
         res = k.get("residual")
         return (f"{nb}x{h}x{w} C={c}->{co}" + (" +res" if res is not None else ""), 2.0 * M * co * 9 * c,
                 2.0 * (M * c + 9 * c * co + M * co) + (2.0 * M * co if res is not None else 0))
+    if name == "upconv3x3":   # conv3x3(upsample2x(x)): canonical 9-tap FLOPs on the 2x image (the kernel executes 4/9 of them)
+        X, W4 = a[0], a[1]
+        nb, h, w, c = X.shape
+        co = W4.shape[0] // 4
+        M = nb * h * w
+        return (f"{nb}x{h}x{w}->2x C={c}->{co}", 2.0 * (4 * M) * co * 9 * c, 2.0 * (M * c + 9 * c * co + 4 * M * co))
+    if name == "conv3x3_s2":
+        X, W = a[0], a[1]
+        nb, h, w, c = X.shape
+        co = W.shape[0]
+        M = nb * (h // 2) * (w // 2)
+        return (f"{nb}x{h}x{w} C={c}->{co} stride 2", 2.0 * M * co * 9 * c, 2.0 * (nb * h * w * c + 9 * c * co + M * co))
     if name == "flash_attention":
         q, kk, heads, Nq, Nk = a[0], a[1], a[3], a[4], a[5]
         C = q.shape[1]
@@ -75,7 +87,7 @@ def meta_of(name, a, k):
     return ("", 0.0, 0.0)
 
 
-NAMES = ["gemm", "conv3x3", "flash_attention", "temporal_attention", "smallkv_attention", "groupnorm", "layernorm", "conv_in",
+NAMES = ["gemm", "conv3x3", "conv3x3_s2", "upconv3x3", "flash_attention", "temporal_attention", "smallkv_attention", "groupnorm", "layernorm", "conv_in",
          "conv_out_tc", "im2col_s2", "im2col3x3", "upsample2x", "skinny_linear", "timestep_embed", "softmax_rows", "geglu",
          "cfg_overlap_accumulate", "ddim_step"]
 

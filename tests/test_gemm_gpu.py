@@ -69,6 +69,38 @@ def test_conv3x3(ops, NB, H, W, C, Cout):
     assert err < 5e-3 and err_r < 5e-3
 
 
+@pytest.mark.parametrize("NB,H,W,C,Cout", [(2, 16, 16, 64, 64), (4, 32, 32, 128, 256), (32, 64, 64, 320, 320),
+                                           (32, 32, 32, 640, 640), (32, 16, 16, 1280, 1280), (3, 8, 8, 128, 64),
+                                           (1, 512, 512, 128, 128), (2, 256, 256, 256, 256), (2, 24, 40, 64, 96)])
+@pytest.mark.parametrize("pad_lo", [1, 0])
+def test_conv3x3_stride2(ops, NB, H, W, C, Cout, pad_lo):
+    """Stride-2 3x3 conv through the TMA traversal stride (no im2col tensor) vs torch fp32 and vs the gathered path
+    (im2col + GEMM: same K order, same MMAs -> identical bits).  pad_lo=1: nn.Conv2d(stride=2, padding=1), the UNet
+    downsamplers (reference modules/resnet.py:93-120); pad_lo=0: F.pad(x, (0,1,0,1)) + padding 0 (VAE encoder)."""
+    F = torch.nn.functional
+    g = torch.Generator(device="cuda").manual_seed(NB * H + C + pad_lo)
+    x = torch.randn(NB, H, W, C, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(Cout, C, 3, 3, device="cuda", generator=g) / (9 * C) ** 0.5).bfloat16()
+    bias = torch.randn(Cout, device="cuda", generator=g)
+    wp = ops.pack_conv3x3_weight(w)
+    out = ops.conv3x3_s2(x, wp, bias, pad_lo=pad_lo)
+    xin = x.permute(0, 3, 1, 2).float()
+    if pad_lo == 0:
+        ref = F.conv2d(F.pad(xin, (0, 1, 0, 1)), w.float(), bias, stride=2)
+    else:
+        ref = F.conv2d(xin, w.float(), bias, stride=2, padding=1)
+    ref = ref.permute(0, 2, 3, 1).reshape(-1, Cout)
+    xt = x.view(NB * H * W, C)
+    col = ops.im2col_s2(xt, NB, H, W) if pad_lo == 1 else ops.im2col3x3(xt, NB, H, W, stride=2, pad_lo=0)
+    gathered = ops.gemm(col, wp, bias)
+    err = _rel(out, ref)
+    same = torch.equal(out, gathered)
+    print(f"conv s2 pad_lo={pad_lo} {NB}x{H}x{W}x{C}->{Cout} rel={err:.3e} identical to im2col+gemm: {same} "
+          f"(max diff {(out.float() - gathered.float()).abs().max().item():.2e})")
+    assert out.shape == (NB * (H // 2) * (W // 2), Cout) and err < 5e-3
+    assert _rel(out, gathered.float()) < 1e-3
+
+
 @pytest.mark.parametrize("M,C", [(1024, 64), (4096, 320), (2048, 1280), (300, 128)])
 def test_gemm_geglu_epilogue(ops, M, C):
     g = torch.Generator(device="cuda").manual_seed(M + C)

@@ -271,6 +271,11 @@ class _ShapeOps:
                 x, NB, H, W = a[:4]
                 assert x.shape[0] == NB * H * W
                 return torch.zeros(NB * (H // 2) * (W // 2), 9 * x.shape[1])
+            if op == "downsample_conv":
+                x, NB, H, W, w, bias = a[:6]
+                assert x.shape[0] == NB * H * W and w.shape[1] == 9 * x.shape[1] and bias.shape == (w.shape[0],)
+                assert H % 2 == 0 and W % 2 == 0
+                return torch.zeros(NB * (H // 2) * (W // 2), w.shape[0])
             if op == "upsample2x":
                 x, NB, H, W = a[:4]
                 assert x.shape[0] == NB * H * W
@@ -534,6 +539,10 @@ class _EmuOps:
 
     def im2col_s2(self, x, NB, H, W, out=None):
         return self._ret(self.im2col3x3(x, NB, H, W, stride=2), out)
+
+    def downsample_conv(self, x, NB, H, W, w, bias, pad_lo=1):
+        assert pad_lo == 1            # the (0,1,0,1) variant belongs to the VAE encoder, which has GPU tests only
+        return self.gemm(self.im2col3x3(x, NB, H, W, stride=2), w, bias)
 
     def upconv3x3(self, x, w4, bias, out=None, block_n=0):
         """conv3x3(upsample2x(x)) from the parity-folded weights (ops.pack_upconv_weight), like vx_upconv3x3_bf16."""

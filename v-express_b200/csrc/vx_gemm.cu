@@ -44,7 +44,9 @@ struct GemmArgs {
   int stages;
   int nbuf;        // staging tiles (2 when shared memory allows: TMA store/residual latency fully hidden)
   int rows_valid;  // output rows covered by one tile (128 for plain; wbox*hbox*nbox for conv)
-  int W, H;        // conv image size
+  int W, H;        // conv OUTPUT image size (= input size at stride 1)
+  int cstride;     // conv stride (1 | 2): tap (dy, dx) of output pixel (y, x) reads input pixel (cstride * y + dy, cstride * x + dx)
+  int cpad;        // conv padding on the low side (1: nn.Conv2d(padding=1); 0: F.pad(x, (0, 1, 0, 1)) + padding 0)
   int tiles_m, tiles_n;
   int geglu;
   int has_residual;
@@ -349,14 +351,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         }
         // 3x3: taps (dy, dx) in {-1, 0, 1}^2.  Folded upsample: output pixel (2i + py, 2j + px) reads the 2x2 input
         // neighbourhood rows i + py - 1 + {0, 1}, columns j + px - 1 + {0, 1} (weights pre-summed per parity on the host).
-        const int dy = p.ups ? (tap >> 1) + (par >> 1) - 1 : tap / 3 - 1;
-        const int dx = p.ups ? (tap & 1) + (par & 1) - 1 : tap % 3 - 1;
+        const int dy = p.ups ? (tap >> 1) + (par >> 1) - 1 : tap / 3 - p.cpad;
+        const int dx = p.ups ? (tap & 1) + (par & 1) - 1 : tap % 3 - p.cpad;
         if (leader) {
           if (CG == 2) {
             const uint32_t fb = mapa_rank(smem_u32(&full_bar[stage]), 0);
             if (pair_leader) mbar_expect_tx(&full_bar[stage], tx_bytes);
             if (p.taps != 1) {
-              tma_load_4d_cg2(sa, &mapA, fb, cb * kBlockK, x0 + dx, y0 + dy, n0);
+              tma_load_4d_cg2(sa, &mapA, fb, cb * kBlockK, x0 * p.cstride + dx, y0 * p.cstride + dy, n0);
             } else if (kb < p.kblocks1) {
               tma_load_2d_cg2(sa, &mapA, fb, kb * kBlockK, (int)m0);
             } else {
@@ -366,7 +368,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
           } else {
             mbar_expect_tx(&full_bar[stage], tx_bytes);
             if (p.taps != 1) {
-              tma_load_4d(sa, &mapA, &full_bar[stage], cb * kBlockK, x0 + dx, y0 + dy, n0);
+              tma_load_4d(sa, &mapA, &full_bar[stage], cb * kBlockK, x0 * p.cstride + dx, y0 * p.cstride + dy, n0);
             } else if (kb < p.kblocks1) {
               tma_load_2d(sa, &mapA, &full_bar[stage], kb * kBlockK, (int)m0);
             } else {
@@ -1057,13 +1059,19 @@ extern "C" int vx_gemm_ln_bf16(const void* A, long long lda, int K, const void* 
                     geglu ? 2 : 0, block_n, nullptr, colsum, stream, eps);
 }
 
-// X: NHWC bf16 [NB, H, W, C];  Wt: [Cout, 9*C] with K index = (ky*3+kx)*C + c;  out: [NB*H*W, ldc]
-extern "C" int vx_conv3x3_bf16(const void* X, int NB, int H, int W, int C, const void* Wt, int Cout,
-                               const float* bias, const float* bias2, int bias2_div, float scale,
-                               const void* residual, long long ldr, void* out, long long ldc, int block_n,
-                               void* stream) {
+// X: NHWC bf16 [NB, Hin, Win, C];  Wt: [Cout, 9*C] with K index = (ky*3+kx)*C + c;  out: [NB*H*W, ldc], H x W the output
+// size.  stride 2: the A boxes are fetched through a tensor map with traversal stride 2 along x and y (the box covers
+// 2 * wbox x 2 * hbox input pixels, every second one lands in shared memory), so the tile of output pixels (y, x) gets
+// input pixels (2y + dy, 2x + dx) for tap (dy, dx) without any gathered copy of the input (no im2col tensor).
+static int conv3x3_entry(const void* X, int NB, int Hin, int Win, int C, const void* Wt, int Cout, const float* bias,
+                         const float* bias2, int bias2_div, float scale, const void* residual, long long ldr, void* out,
+                         long long ldc, int block_n, int stride, int pad_lo, void* stream) {
   VX_REQUIRE(C % kBlockK == 0 && Cout % 32 == 0, "vx_conv3x3_bf16: C=%d must be %%64, Cout=%d %%32", C, Cout);
   VX_REQUIRE(ldc % 8 == 0 && (!residual || ldr % 8 == 0), "vx_conv3x3_bf16: ld must be %%8");
+  VX_REQUIRE(stride == 1 || (stride == 2 && Hin % 2 == 0 && Win % 2 == 0), "vx_conv3x3: stride %d on %dx%d unsupported", stride,
+             Hin, Win);
+  VX_REQUIRE(pad_lo == 1 || (pad_lo == 0 && stride == 2), "vx_conv3x3: pad_lo=%d only with stride 2", pad_lo);
+  const int H = Hin / stride, W = Win / stride;   // 3x3, pad 1 (or (0,1,0,1)), even sizes: H_out = H_in / stride
   // pixel rectangle of <= 128 output rows that is contiguous in NHWC row order
   int wbox, hbox = 1, nbox = 1;
   if (W >= kBlockM) {
@@ -1095,7 +1103,7 @@ extern "C" int vx_conv3x3_bf16(const void* X, int NB, int H, int W, int C, const
   // serves the three dy taps (each tap's 128 rows start dy image rows further down, a multiple of the swizzle atom):
   // 3 (hbox + 2) / (9 hbox) of the A traffic.  The 3x3 convs run at the L2 -> SM cap (~13 TB/s,
   // profiles/r02_roofline.csv), so operand bytes are what they are bound by.
-  bool rr = gemm_env().conv_rr && nbox == 1 && wbox == W && hbox >= 2 && rows_valid == kBlockM && (W * 128) % 1024 == 0;
+  bool rr = gemm_env().conv_rr && stride == 1 && nbox == 1 && wbox == W && hbox >= 2 && rows_valid == kBlockM && (W * 128) % 1024 == 0;
   if (rr) {   // two ring stages + one staging tile must fit
     const int cgx = pair_ok(0, block_n, tiles_m, total_kb) ? 2 : 1;
     const size_t st = (size_t)(hbox + 2) * W * kBlockK * 2 + (size_t)3 * (block_n / cgx) * kBlockK * 2;
@@ -1103,10 +1111,11 @@ extern "C" int vx_conv3x3_bf16(const void* X, int NB, int H, int W, int C, const
   }
   CUtensorMap mA, mB, mR, mC;
   {
-    uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)NB};
-    uint64_t str[3] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
-    uint32_t box[4] = {kBlockK, (uint32_t)wbox, (uint32_t)(rr ? hbox + 2 : hbox), (uint32_t)nbox};
-    if (make_tmap_bf16(&mA, X, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+    uint64_t dims[4] = {(uint64_t)C, (uint64_t)Win, (uint64_t)Hin, (uint64_t)NB};
+    uint64_t str[3] = {(uint64_t)C * 2, (uint64_t)Win * C * 2, (uint64_t)Hin * Win * C * 2};
+    uint32_t box[4] = {kBlockK, (uint32_t)(wbox * stride), (uint32_t)((rr ? hbox + 2 : hbox) * stride), (uint32_t)nbox};
+    uint32_t est[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
+    if (make_tmap_bf16(&mA, X, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, est)) return 1;
   }
   {
     uint64_t dims[2] = {(uint64_t)9 * C, (uint64_t)Cout};
@@ -1125,6 +1134,7 @@ extern "C" int vx_conv3x3_bf16(const void* X, int NB, int H, int W, int C, const
   a.block_n = block_n;
   a.rows_valid = rows_valid;
   a.W = W; a.H = H;
+  a.cstride = stride; a.cpad = pad_lo;
   a.tiles_m = (int)tiles_m;
   a.tiles_n = Cout / block_n;
   a.geglu = 0;
@@ -1133,6 +1143,21 @@ extern "C" int vx_conv3x3_bf16(const void* X, int NB, int H, int W, int C, const
   a.bias = bias; a.bias2 = bias2; a.bias2_div = bias2_div > 0 ? bias2_div : 1; a.scale = scale;
   a.out32 = (float*)out; a.ldc = ldc;
   return launch(mA, mA, mB, mR, mC, a, (cudaStream_t)stream);
+}
+
+extern "C" int vx_conv3x3_bf16(const void* X, int NB, int H, int W, int C, const void* Wt, int Cout,
+                               const float* bias, const float* bias2, int bias2_div, float scale,
+                               const void* residual, long long ldr, void* out, long long ldc, int block_n,
+                               void* stream) {
+  return conv3x3_entry(X, NB, H, W, C, Wt, Cout, bias, bias2, bias2_div, scale, residual, ldr, out, ldc, block_n, 1, 1, stream);
+}
+
+// 3x3 convolution with stride 2 on an even-sized NHWC image -> [NB * (H/2) * (W/2), ldc].  pad_lo = 1: nn.Conv2d(padding=1)
+// (Downsample3D / Downsample2D of the UNets, reference modules/resnet.py:93-120); pad_lo = 0: F.pad(x, (0, 1, 0, 1)) + padding 0
+// (diffusers Downsample2D(padding=0) of the VAE encoder).  Out-of-image taps are zero-filled by the TMA unit.
+extern "C" int vx_conv3x3s2_bf16(const void* X, int NB, int H, int W, int C, const void* Wt, int Cout, const float* bias,
+                                 int pad_lo, void* out, long long ldc, int block_n, void* stream) {
+  return conv3x3_entry(X, NB, H, W, C, Wt, Cout, bias, nullptr, 1, 1.0f, nullptr, 0, out, ldc, block_n, 2, pad_lo, stream);
 }
 
 // conv3x3(nearest_upsample_2x(X)) without the upsampled tensor (reference modules/resnet.py:53-90 Upsample3D,
@@ -1202,6 +1227,7 @@ extern "C" int vx_upconv3x3_bf16(const void* X, int NB, int H, int W, int C, con
   a.kblocks2 = 0;
   a.taps = 4;
   a.ups = 1;
+  a.cstride = 1; a.cpad = 1;
   a.block_n = block_n;
   a.rows_valid = rows_valid;
   a.W = W; a.H = H;

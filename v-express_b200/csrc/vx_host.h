@@ -38,8 +38,11 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 PFN_encodeTiled get_encode_tiled();  // vx_runtime.cu
 
 // bf16 tensor map of rank `rank`: dims[i] elements, strides_bytes[i-1] for i>=1, box[i] elements.
+// estrides (optional): traversal stride per dimension (1..8): the box then covers box[i] tensor elements of which every
+// estrides[i]-th is loaded, i.e. box[i] / estrides[i] elements land in shared memory (the stride-2 convolutions).
 inline int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims,
-                          const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz) {
+                          const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz,
+                          const uint32_t* estrides = nullptr) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) return fail("cuTensorMapEncodeTiled entry point unavailable");
   cuuint64_t gd[5];
@@ -49,7 +52,7 @@ inline int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint
   for (int i = 0; i < rank; ++i) {
     gd[i] = dims[i];
     bx[i] = box[i];
-    es[i] = 1;
+    es[i] = estrides ? estrides[i] : 1;
     if (i) gs[i - 1] = strides_bytes[i - 1];
   }
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,

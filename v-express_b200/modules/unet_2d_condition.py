@@ -305,8 +305,7 @@ class RefNetEngine(UNetEngine):
                     x = self._transformer_write(f"{p}.attentions.{j}", x, NB, h_ * w_, enc_flat)
                 skips.append((x, h_, w_))
             if i < 3:
-                col = ops.im2col_s2(x, NB, h_, w_)
-                x = ops.gemm(col, W[f"{p}.downsamplers.0.conv.weight"], W[f"{p}.downsamplers.0.conv.bias"])
+                x = ops.downsample_conv(x, NB, h_, w_, W[f"{p}.downsamplers.0.conv.weight"], W[f"{p}.downsamplers.0.conv.bias"])
                 h_, w_ = h_ // 2, w_ // 2
                 skips.append((x, h_, w_))
         x = self._resnet("mid_block.resnets.0", x, None, NB, h_, w_, temb)

@@ -632,8 +632,7 @@ class UNetEngine:
                 tap(f"{p}.motion_modules.{j}", x, h_, w_)
                 skips.append((x, h_, w_))
             if i < 3:
-                col = ops.im2col_s2(x, NB, h_, w_)
-                x = ops.gemm(col, W[f"{p}.downsamplers.0.conv.weight"], W[f"{p}.downsamplers.0.conv.bias"])
+                x = ops.downsample_conv(x, NB, h_, w_, W[f"{p}.downsamplers.0.conv.weight"], W[f"{p}.downsamplers.0.conv.bias"])
                 h_, w_ = h_ // 2, w_ // 2
                 tap(f"{p}.downsamplers.0", x, h_, w_)
                 skips.append((x, h_, w_))

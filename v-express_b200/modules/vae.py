@@ -387,9 +387,8 @@ class VaeEncoderEngine:
                 h = self._res(f"{e}.down_blocks.{i}.resnets.{j}", h, NB, H, Wd)
             if i < len(self.boc) - 1:
                 # Downsample2D(padding=0): F.pad(x, (0, 1, 0, 1)) then conv3x3 stride 2
-                col = ops.im2col3x3(h, NB, H, Wd, stride=2, pad_lo=0)
-                h = ops.gemm(col, W[f"{e}.down_blocks.{i}.downsamplers.0.conv.weight"],
-                             W[f"{e}.down_blocks.{i}.downsamplers.0.conv.bias"])
+                h = ops.downsample_conv(h, NB, H, Wd, W[f"{e}.down_blocks.{i}.downsamplers.0.conv.weight"],
+                                        W[f"{e}.down_blocks.{i}.downsamplers.0.conv.bias"], pad_lo=0)
                 H, Wd = H // 2, Wd // 2
         h = self._res(e + ".mid_block.resnets.0", h, NB, H, Wd)
         h = self._attn(e + ".mid_block.attentions.0", h, NB, H * Wd)

@@ -136,6 +136,34 @@ def conv3x3(x, w, bias=None, *, bias2=None, bias2_div=1, scale=1.0, residual=Non
     return out
 
 
+CONV_S2_TMA = os.environ.get("VX_CONV_S2", "1") != "0"   # A/B switch: 0 = im2col + GEMM (the round-1 path)
+
+
+def downsample_conv(x, NB, H, W, w, bias, pad_lo=1):
+    """Stride-2 3x3 conv of the [NB*H*W, C] token matrix -> [NB*(H/2)*(W/2), Cout]."""
+    if CONV_S2_TMA and x.shape[1] % 64 == 0:
+        return conv3x3_s2(x.view(NB, H, W, x.shape[1]), w, bias, pad_lo=pad_lo)
+    col = im2col_s2(x, NB, H, W) if pad_lo == 1 else im2col3x3(x, NB, H, W, stride=2, pad_lo=0)
+    return gemm(col, w, bias)
+
+
+def conv3x3_s2(x, w, bias=None, *, pad_lo=1, out=None, block_n=0):
+    """3x3 conv, stride 2, on the tensor cores straight from the NHWC input (TMA traversal stride 2: no im2col tensor).
+    x: NHWC bf16 [NB,H,W,C], H and W even; w: [Cout, 9*C]; returns [NB*(H/2)*(W/2), Cout].  pad_lo=1: padding 1 all round
+    (UNet downsamplers); pad_lo=0: pad (0,1,0,1) (VAE encoder downsamplers)."""
+    _chk_bf16(x, w, out)
+    assert x.is_contiguous()
+    NB, H, W, C = x.shape
+    Cout = w.shape[0]
+    assert w.shape[1] == 9 * C and H % 2 == 0 and W % 2 == 0
+    if out is None:
+        out = torch.empty((NB * (H // 2) * (W // 2), Cout), device=x.device, dtype=BF16)
+    check(_ffi.lib().vx_conv3x3s2_bf16(
+        ptr(x), c_int(NB), c_int(H), c_int(W), c_int(C), ptr(w), c_int(Cout), ptr(bias), c_int(pad_lo), ptr(out),
+        c_ll(out.stride(0)), c_int(block_n), stream_ptr()), "vx_conv3x3s2_bf16")
+    return out
+
+
 def pack_upconv_weight(w):
     """(Cout, Cin, 3, 3) conv weight of an `nearest-2x upsample -> conv3x3` pair -> [4*Cout, 4*Cin] bf16 for
     vx_upconv3x3_bf16: block (py, px) holds the 2x2 kernel seen by output pixels (2i+py, 2j+px); tap a (b) of that kernel
