@@ -31,6 +31,12 @@ def add_conv(NB, H, W, C, Cout, residual=False):
     cases.append((f"conv NB={NB} {H}x{W} C={C} Cout={Cout}{' +res' if residual else ''}", 2.0 * NB * H * W * 9 * C * Cout,
                   lambda: ops.conv3x3(x, w, b, residual=r, out=out)))
 
+def add_geglu(M, K, N):
+    a, w, b = bf(M, K), bf(N, K), torch.randn(N, device=dev)
+    wp, bp, _ = ops.pack_geglu(w, b)
+    out = torch.empty(M, N // 2, device=dev, dtype=torch.bfloat16)
+    cases.append((f"gemm M={M} K={K} N={N} geglu", 2.0 * M * K * N, lambda: ops.gemm(a, wp, bp, geglu=True, out=out)))
+add_geglu(131072, 320, 2560); add_geglu(32768, 640, 5120); add_geglu(8192, 1280, 10240)
 add_gemm(131072, 320, 960); add_gemm(131072, 320, 320, True); add_gemm(131072, 1280, 320, True)
 add_gemm(32768, 640, 1920); add_gemm(32768, 640, 640, True); add_gemm(32768, 2560, 640, True)
 add_gemm(8192, 1280, 3840); add_gemm(8192, 1280, 1280, True); add_gemm(8192, 5120, 1280, True)
@@ -38,12 +44,12 @@ add_conv(32, 64, 64, 320, 320); add_conv(32, 64, 64, 640, 320); add_conv(32, 32,
 add_conv(32, 32, 32, 1280, 640); add_conv(32, 16, 16, 1280, 1280); add_conv(32, 16, 16, 2560, 1280)
 add_conv(16, 128, 128, 512, 512); add_conv(16, 256, 256, 256, 256); add_conv(16, 512, 512, 128, 128)
 
-settings = [("cg1", {"VX_GEMM_CG": "1"}), ("auto", {}), ("cg2", {"VX_GEMM_CG": "2"}), ("cg2 nbuf1", {"VX_GEMM_CG": "2", "VX_GEMM_NBUF": "1"}),
+settings = [("cg1", {"VX_GEMM_CG": "1"}), ("auto", {}), ("mc", {"VX_GEMM_MC": "1"}), ("cg1 mc", {"VX_GEMM_CG": "1", "VX_GEMM_MC": "1"}), ("cg2", {"VX_GEMM_CG": "2"}), ("cg2 nbuf1", {"VX_GEMM_CG": "2", "VX_GEMM_NBUF": "1"}),
             ("cg2 bn128", {"VX_GEMM_CG": "2", "VX_GEMM_BN": "128"}),
             ("cg1 bn128", {"VX_GEMM_CG": "1", "VX_GEMM_BN": "128"})]
 if len(sys.argv) > 1:
     settings = [s for s in settings if s[0] in sys.argv[1:]]
-keys = ["VX_GEMM_CG", "VX_GEMM_NBUF", "VX_GEMM_BN", "VX_GEMM_STAGES"]
+keys = ["VX_GEMM_CG", "VX_GEMM_NBUF", "VX_GEMM_BN", "VX_GEMM_STAGES", "VX_GEMM_MC"]
 os.environ["VX_GEMM_VERBOSE"] = "1"
 for name, flop, fn in cases: fn()
 torch.cuda.synchronize()

@@ -66,6 +66,12 @@ struct GemmArgs {
   // compute the row statistics from the resident tile -- no statistics pass, no LayerNorm pass, 1/tiles_n of the A traffic.
   int ares;
   int ares_bytes;           // kblocks1 x 16 KB
+  // W multicast (CG = 1 only): the grid runs as clusters of two CTAs that own adjacent 128-row tiles and walk the same
+  // column tiles in lock step per ring stage; each CTA fetches HALF of every W tile and multicasts it into both shared
+  // memories (cp.async.bulk.tensor .multicast::cluster), the MMA commits release a stage in both CTAs.  L2 -> SM operand
+  // traffic per 128 x bn x 64 MMA block drops from 16 KB + bn * 128 B to 16 KB + bn * 64 B like in the cta_group::2
+  // kernel, but the two CTAs keep their own MMA stream, accumulators and epilogue.
+  int mc;
   float ln_eps;
 };
 
@@ -133,6 +139,21 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
 }
+// TMA load of a 2-D box into the same shared-memory offset of every CTA in `mask`; each destination CTA's mbarrier at the
+// offset of `bar` receives the complete_tx
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::
+          "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+// completion of all prior MMAs of this thread (cta_group::1) -> arrive on the barrier at the same offset in both CTAs
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_alloc_cg2(uint32_t* smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
@@ -172,8 +193,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   const int b_bytes = (p.block_n / CG) * kBlockK * 2;   // this CTA's share of one W tile
   const int nbt = p.rr ? 3 : 1;                         // W tiles per stage (rr: the three dy taps of one dx)
   const int stage_bytes = a_bytes + nbt * b_bytes;
-  const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
-  const bool pair_leader = cta_rank == 0;
+  const bool mc = CG == 1 && p.mc;                 // W multicast between the two CTAs of a cluster (see GemmArgs::mc)
+  const int G = (CG == 2 || mc) ? 2 : 1;           // row tiles per work item = CTAs per cluster
+  const uint32_t cta_rank = G == 2 ? cluster_ctarank() : 0u;
+  const bool pair_leader = CG == 2 ? cta_rank == 0 : true;   // CG = 1: every CTA issues its own MMAs
   uint8_t* ring = smem;                         // TMA ring (behind the resident A tile in `ares` mode)
   if constexpr (LNF) ring += p.ares ? p.ares_bytes : 0;
   uint8_t* sC = ring + p.stages * stage_bytes;  // staging: (block_n or block_n/2)/32 panels of 8 KB
@@ -200,13 +223,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   const int lane = threadIdx.x & 31;
   const int total_kb = p.rr ? 3 * p.kblocks1 : p.taps * p.kblocks1 + p.kblocks2;   // ring stages per output tile
   // work items are (row-tile group of CG tiles, column tile); every CTA of a pair walks the same sequence
-  const int tiles_per_par = ((p.tiles_m + CG - 1) / CG) * p.tiles_n;
+  const int tiles_per_par = ((p.tiles_m + G - 1) / G) * p.tiles_n;
   const int num_tiles = tiles_per_par * (p.ups ? 4 : 1);   // ups: (parity, row-tile group, column tile), parity slowest
-  const int first_item = blockIdx.x / CG, item_stride = gridDim.x / CG;
+  const int first_item = blockIdx.x / G, item_stride = gridDim.x / G;
   // the it-th output tile of this CTA (pair) as a flat (row-tile group, column tile) index, or -1 past the end.  Default:
   // tiles strided over the grid, n fastest.  `ares`: row-tile groups strided over the grid, each walked through all its
   // column tiles.
-  const int groups = (p.tiles_m + CG - 1) / CG;
+  const int groups = (p.tiles_m + G - 1) / G;
   auto item_at = [&](int it) -> int {
     if constexpr (LNF) {
       if (p.ares) {
@@ -226,7 +249,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     if (p.has_residual || p.ups) tma_prefetch_desc(&mapR);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], mc ? 2 : 1);   // mc: released by the MMA commits of BOTH CTAs (both read the shared W halves)
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
@@ -258,7 +281,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     }
   }
   tc_fence_before();
-  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (G == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // everything above (barrier init, tensor-map prefetch, TMEM allocation, the pair's cluster rendezvous) overlapped the
@@ -275,7 +298,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     uint32_t phase = 0;
     for (int it = 0, t = item_at(0); t >= 0; t = item_at(++it)) {
       const int par = t / tiles_per_par, tt = t - par * tiles_per_par;
-      const int tile_n = tt % p.tiles_n, tile_m = (tt / p.tiles_n) * CG + (int)cta_rank;
+      const int tile_n = tt % p.tiles_n, tile_m = (tt / p.tiles_n) * G + (int)cta_rank;
       int n0 = 0, y0 = 0, x0 = 0;
       const long long m0 = (long long)tile_m * p.rows_valid;
       if (p.taps != 1) {
@@ -287,7 +310,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       }
       // the pair's loads all complete on the LEADER's full barrier (it alone waits for the operands)
       const uint32_t tx_bytes = (uint32_t)(CG * ((p.rr ? a_bytes : p.rows_valid * kBlockK * 2) + nbt * b_bytes));
-      const int b_row = par * p.N + tile_n * p.block_n + (int)cta_rank * (p.block_n / CG);
+      const int b_row = par * p.N + tile_n * p.block_n + (CG == 2 ? (int)cta_rank * (p.block_n / 2) : 0);
+      // CG = 1: the whole W tile [b_row, b_row + block_n) lands at dst; with mc this CTA fetches its half of the rows for both
+      auto load_w = [&](uint8_t* dst, int c0, int row) {
+        if (mc)
+          tma_load_2d_mc(dst + cta_rank * (uint32_t)(b_bytes / 2), &mapB, &full_bar[stage], c0, row + (int)cta_rank * (p.block_n / 2),
+                         (uint16_t)3);
+        else
+          tma_load_2d(dst, &mapB, &full_bar[stage], c0, row);
+      };
       for (int kb = 0; kb < total_kb; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = ring + stage * stage_bytes;
@@ -339,7 +370,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
               tma_load_4d(sa, &mapA, &full_bar[stage], cb * kBlockK, x0 + tap - 1, y0 - 1, n0);
 #pragma unroll
               for (int dyi = 0; dyi < 3; ++dyi)
-                tma_load_2d(sb + dyi * b_bytes, &mapB, &full_bar[stage], ((dyi * 3 + tap) * p.kblocks1 + cb) * kBlockK, b_row);
+                load_w(sb + dyi * b_bytes, ((dyi * 3 + tap) * p.kblocks1 + cb) * kBlockK, b_row);
             }
           }
           __syncwarp();
@@ -374,7 +405,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             } else {
               tma_load_2d(sa, &mapA2, &full_bar[stage], (kb - p.kblocks1) * kBlockK, (int)m0);
             }
-            tma_load_2d(sb, &mapB, &full_bar[stage], kb * kBlockK, b_row);
+            load_w(sb, kb * kBlockK, b_row);
           }
         }
         __syncwarp();
@@ -435,7 +466,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
               else umma_ss(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
             }
           }
-          if (CG == 2) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
+          if (CG == 2) umma_commit_pair(&empty_bar[stage]);
+          else if (mc) umma_commit_mc(&empty_bar[stage]);
+          else umma_commit(&empty_bar[stage]);
           if (a_last) {
             if (CG == 2) umma_commit_pair(&a_empty[kb]); else umma_commit(&a_empty[kb]);
           }
@@ -458,7 +491,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       const uint32_t res_bytes = (uint32_t)(p.rows_valid * out_cols * 2);
       auto arm = [&](int t, int b) {  // make staging tile b usable for output tile t
         if (p.has_residual) {   // (never with ups: the upsampler convs have no residual)
-          const int tn_ = t % p.tiles_n, tm_ = (t / p.tiles_n) * CG + (int)cta_rank;
+          const int tn_ = t % p.tiles_n, tm_ = (t / p.tiles_n) * G + (int)cta_rank;
           mbar_expect_tx(&c_ready[b], res_bytes);
           for (int pn = 0; pn < npanels; ++pn)
             tma_load_2d(sC + b * buf_bytes + pn * kPanelBytes, &mapR, &c_ready[b], tn_ * out_cols + pn * kPanelCols,
@@ -472,7 +505,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       for (int it = 0, t = item_at(0); t >= 0; t = item_at(++it)) {
         const int b = it % p.nbuf;
         const int par = t / tiles_per_par, tt = t - par * tiles_per_par;
-        const int tile_n = tt % p.tiles_n, tile_m = (tt / p.tiles_n) * CG + (int)cta_rank;
+        const int tile_n = tt % p.tiles_n, tile_m = (tt / p.tiles_n) * G + (int)cta_rank;
         mbar_wait(&staged[b], (uint32_t)((it / p.nbuf) & 1));
         if (p.ups) {
           // rows of the tile = low-resolution pixels (n, i, j); they land on (n, 2i + py, 2j + px): 5-D map (c, j, i, n, py)
@@ -511,7 +544,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     const uint32_t te_leader1 = CG == 2 ? mapa_rank(smem_u32(&tmem_empty[1]), 0) : 0u;
     for (int it = 0, t = item_at(0); t >= 0; t = item_at(++it)) {
       const int tt = t % tiles_per_par;
-      const int tile_n = tt % p.tiles_n, tile_m = (tt / p.tiles_n) * CG + (int)cta_rank;
+      const int tile_n = tt % p.tiles_n, tile_m = (tt / p.tiles_n) * G + (int)cta_rank;
       const int as = it & 1;
       const long long m = (long long)tile_m * p.rows_valid + row;
       const bool row_ok = row < p.rows_valid && m < p.M;
@@ -715,7 +748,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     }
   }
   tc_fence_before();
-  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (G == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     if (CG == 2) tmem_dealloc_cg2(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
@@ -725,20 +758,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
 // A/B switches (bring-up only) are read ONCE per process: the launch path never touches the environment
 // (the sweep tools re-read them through vx_gemm_reload_env).
 struct GemmEnv {
-  int cg, cg_minkb, pairs, stages, nbuf, bn, verbose, conv_rr;
+  int cg, cg_minkb, pairs, stages, nbuf, bn, verbose, conv_rr, mc;
   static int geti(const char* name, int dflt) {
     const char* s = getenv(name);
     return s ? atoi(s) : dflt;
   }
   GemmEnv() {
     cg = geti("VX_GEMM_CG", 0);
-    cg_minkb = geti("VX_GEMM_CG_MINKB", 12);
+    cg_minkb = geti("VX_GEMM_CG_MINKB", 10);   // K >= 640: profiles/r02_gemm_notes.md (pairs +2..10 % at K = 640, -15 % at K = 320)
     pairs = geti("VX_GEMM_PAIRS", 0);
     stages = geti("VX_GEMM_STAGES", 0);
     nbuf = geti("VX_GEMM_NBUF", 0);
     bn = geti("VX_GEMM_BN", 0);
     verbose = geti("VX_GEMM_VERBOSE", 0);
     conv_rr = geti("VX_CONV_RR", 1);
+    mc = geti("VX_GEMM_MC", 0);
   }
 };
 static GemmEnv& gemm_env() {
@@ -760,11 +794,21 @@ static int num_sms() {
 
 static bool pair_ok(int out_f32, int block_n, long long tiles_m, int total_kb) {
   // CTA pairs need an even split of the W tile into 8-row swizzle groups and at least two row tiles.  They pay off
-  // once the K loop is long enough to be MMA/operand bound; short K loops (K <= 640) are bound by the epilogue and
-  // the output stores, where two independent CTAs overlap better (profiles/tools/gemm_sweep.py).
+  // once the K loop is long enough to be MMA/operand bound (K >= 640); the K = 320 loops are bound by the epilogue and
+  // the output stores, where two independent CTAs overlap better (profiles/tools/gemm_sweep.py, profiles/r02_gemm_notes.md).
   const int mode = gemm_env().cg;   // 0 = auto, 1 = never, 2 = whenever legal
   if (out_f32 || block_n % 32 != 0 || tiles_m < 2 || mode == 1) return false;
   return mode == 2 || total_kb >= gemm_env().cg_minkb;   // threshold from profiles/tools/gemm_sweep.py
+}
+
+// W multicast between two 1-CTA tiles (GemmArgs::mc): whenever the pair kernel is not chosen, the W tile splits into two
+// halves of whole 8-row swizzle groups and there are at least two row tiles
+static bool mc_ok(int out_f32, int block_n, long long tiles_m, int total_kb) {
+  return gemm_env().mc && !out_f32 && block_n % 32 == 0 && tiles_m >= 2 && !pair_ok(out_f32, block_n, tiles_m, total_kb);
+}
+// the W tensor-map box holds half a column tile (each CTA of a pair / cluster fetches one half)
+static bool w_split(int out_f32, int block_n, long long tiles_m, int total_kb) {
+  return pair_ok(out_f32, block_n, tiles_m, total_kb) || mc_ok(out_f32, block_n, tiles_m, total_kb);
 }
 
 // resident CTA pairs of the persistent cta_group::2 kernel (GPCs with an odd SM count strand one SM)
@@ -830,6 +874,7 @@ static int num_pairs() {
 static int launch(const CUtensorMap& mA, const CUtensorMap& mA2, const CUtensorMap& mB, const CUtensorMap& mR,
                   const CUtensorMap& mC, GemmArgs& a, cudaStream_t st) {
   const int cg = use_pair(a) ? 2 : 1;
+  a.mc = (cg == 1 && !a.ares && mc_ok(a.out_f32, a.block_n, a.tiles_m, a.taps * a.kblocks1 + a.kblocks2)) ? 1 : 0;
   if (a.ares) a.a_bytes = 0;   // A lives in its own resident slots, the ring stages hold W only
   else if (a.a_bytes <= 0) a.a_bytes = kBlockM * kBlockK * 2;
   const int stage_bytes = a.a_bytes + (a.rr ? 3 : 1) * (a.block_n / cg) * kBlockK * 2;
@@ -867,8 +912,8 @@ static int launch(const CUtensorMap& mA, const CUtensorMap& mA2, const CUtensorM
   VX_REQUIRE(smem <= (size_t)227 * 1024, "vx_gemm: %zu bytes of shared memory needed (bn=%d, K blocks=%d)", smem, a.block_n,
              a.kblocks1);
   if (gemm_env().verbose)
-    fprintf(stderr, "[vx_gemm] M=%d N=%d kb=%d taps=%d cg=%d bn=%d stages=%d nbuf=%d tiles=%dx%d\n", a.M, a.N, total_kb,
-            a.taps, cg, a.block_n, stages, nbuf, a.tiles_m, a.tiles_n);
+    fprintf(stderr, "[vx_gemm] M=%d N=%d kb=%d taps=%d cg=%d mc=%d bn=%d stages=%d nbuf=%d tiles=%dx%d\n", a.M, a.N, total_kb,
+            a.taps, cg, a.mc, a.block_n, stages, nbuf, a.tiles_m, a.tiles_n);
   static bool configured = false;
   if (!configured) {
     VX_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -880,7 +925,27 @@ static int launch(const CUtensorMap& mA, const CUtensorMap& mA2, const CUtensorM
   const int npar = a.ups ? 4 : 1;
   const bool lnf = a.ln_stats != nullptr || a.ares;
   const int threads = a.ares ? kThreads + kStatThreads : kThreads;
-  if (cg == 1) {
+  if (cg == 1 && a.mc) {
+    // clusters of two CTAs (adjacent row tiles), same residency as the pair kernel (one CTA per SM, two SMs of a TPC)
+    const int items = ((a.tiles_m + 1) / 2) * a.tiles_n * npar;
+    const int clusters = items < num_pairs() ? items : num_pairs();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    if (lnf) VX_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<1, true>, mA, mA2, mB, mR, mC, a));
+    else VX_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<1, false>, mA, mA2, mB, mR, mC, a));
+  } else if (cg == 1) {
     const int tiles = a.ares ? a.tiles_m : a.tiles_m * a.tiles_n * npar;
     const int grid = tiles < num_sms() ? tiles : num_sms();
     if (lnf) VX_CHECK_CUDA(launch_k((gemm_tcgen05_kernel<1, true>), dim3(grid), dim3(threads), smem, st, mA, mA2, mB, mR, mC, a));
@@ -974,7 +1039,7 @@ static int gemm_entry(const void* A, long long lda, int K1, const void* A2, long
     VX_REQUIRE(block_n > 0, "vx_gemm_ln_bf16: no column tile of N=%d fits beside the resident K=%d tile", N, K1);
   } else {
     if (block_n <= 0) block_n = pick_block_n(tiles_m, N, gran, out_f32, total_kb);
-    b_split = pair_ok(out_f32, block_n, tiles_m, total_kb);
+    b_split = w_split(out_f32, block_n, tiles_m, total_kb);
   }
   VX_REQUIRE(block_n >= gran && block_n % gran == 0 && block_n <= 256 && N % block_n == 0,
              "vx_gemm_bf16: block_n=%d invalid for N=%d", block_n, N);
@@ -1120,7 +1185,7 @@ static int conv3x3_entry(const void* X, int NB, int Hin, int Win, int C, const v
   {
     uint64_t dims[2] = {(uint64_t)9 * C, (uint64_t)Cout};
     uint64_t str[1] = {(uint64_t)9 * C * 2};
-    uint32_t box[2] = {kBlockK, (uint32_t)(pair_ok(0, block_n, tiles_m, total_kb) ? block_n / 2 : block_n)};
+    uint32_t box[2] = {kBlockK, (uint32_t)(w_split(0, block_n, tiles_m, total_kb) ? block_n / 2 : block_n)};
     if (make_tmap_bf16(&mB, Wt, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
   }
   if (make_out_maps(&mR, &mC, residual, ldr, out, ldc, M, Cout, rows_valid)) return 1;
@@ -1197,7 +1262,7 @@ extern "C" int vx_upconv3x3_bf16(const void* X, int NB, int H, int W, int C, con
   if (block_n <= 0) block_n = pick_block_n(tiles_m * 4, Cout, 32, 0, total_kb);
   VX_REQUIRE(block_n % 32 == 0 && block_n >= 32 && block_n <= 256 && Cout % block_n == 0,
              "vx_upconv3x3_bf16: block_n=%d invalid for Cout=%d", block_n, Cout);
-  const bool pair = pair_ok(0, block_n, tiles_m, total_kb);
+  const bool pair = w_split(0, block_n, tiles_m, total_kb);   // half-tile W boxes (CTA pair or W multicast)
   CUtensorMap mA, mB, mC0, mC1;
   {
     uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)NB};
