@@ -174,7 +174,7 @@ def op_table(pipe, host, L, h, which="unet"):
     during an eager forward is replayed 8x back-to-back and timed with CUDA events (so host launch overhead overlaps)."""
     from vexpress_b200 import ops
     recs = []
-    names = ["gemm", "gemm_ln", "conv3x3", "upconv3x3", "flash_attention", "temporal_attention", "smallkv_attention", "groupnorm",
+    names = ["gemm", "gemm_ln", "gemm_rowsums", "gemm_lnparts", "conv3x3", "conv3x3_s2", "upconv3x3", "flash_attention", "temporal_attention", "smallkv_attention", "groupnorm",
              "layernorm", "conv_in", "conv_out", "im2col_s2", "upsample2x", "skinny_linear", "timestep_embed", "softmax_rows"]
     orig = {n: getattr(ops, n) for n in names}
 
@@ -239,8 +239,8 @@ def kernel_roofline(pipe, host, L, h):
     CUDA events on the launching stream; achieved = sum(2*M*N*K) / sum(duration)."""
     from vexpress_b200 import ops
     recs = []
-    orig = dict(gemm=ops.gemm, gemm_ln=ops.gemm_ln, conv3x3=ops.conv3x3, flash_attention=ops.flash_attention,
-                upconv3x3=ops.upconv3x3, groupnorm=ops.groupnorm, layernorm=ops.layernorm)
+    orig = dict(gemm=ops.gemm, gemm_ln=ops.gemm_ln, gemm_rowsums=ops.gemm_rowsums, gemm_lnparts=ops.gemm_lnparts, conv3x3=ops.conv3x3, flash_attention=ops.flash_attention,
+                upconv3x3=ops.upconv3x3, conv3x3_s2=ops.conv3x3_s2, groupnorm=ops.groupnorm, layernorm=ops.layernorm)
 
     def timed(name, fn, flops_of):
         def w(*a, **k):
@@ -260,6 +260,10 @@ def kernel_roofline(pipe, host, L, h):
         nb, hh, ww, c = a[0].shape
         return 2.0 * nb * hh * ww * 9 * c * a[1].shape[0]
 
+    def f_conv_s2(a, k, out):      # stride 2: a quarter of the output pixels
+        nb, hh, ww, c = a[0].shape
+        return 2.0 * nb * (hh // 2) * (ww // 2) * 9 * c * a[1].shape[0]
+
     def f_fa(a, k, out):
         q, heads, nq, nk = a[0], a[3], a[4], a[5]
         return 4.0 * q.shape[0] * nk * q.shape[1]
@@ -274,8 +278,11 @@ def kernel_roofline(pipe, host, L, h):
 
     ops.gemm = timed("gemm", orig["gemm"], f_gemm)
     ops.gemm_ln = timed("gemm", orig["gemm_ln"], f_gemm)     # LayerNorm -> Linear in one launch: the GEMM's FLOPs
+    ops.gemm_rowsums = timed("gemm", orig["gemm_rowsums"], f_gemm)      # producer / consumer of the LayerNorm statistics
+    ops.gemm_lnparts = timed("gemm", orig["gemm_lnparts"], f_gemm)      # hand-over: plain GEMM FLOPs
     ops.conv3x3 = timed("conv3x3", orig["conv3x3"], f_conv)
     ops.upconv3x3 = timed("conv3x3", orig["upconv3x3"], f_upconv)
+    ops.conv3x3_s2 = timed("conv3x3", orig["conv3x3_s2"], f_conv_s2)
     ops.flash_attention = timed("flash", orig["flash_attention"], f_fa)
     ops.groupnorm = timed("groupnorm", orig["groupnorm"], b_norm)
     ops.layernorm = timed("layernorm", orig["layernorm"], b_norm)
@@ -317,7 +324,7 @@ def ncu_evidence():
         return None
     rows = [r for r in csv.DictReader(open(p)) if r["part"] == "unet"]
     f = lambda r, k: float(r[k]) if r.get(k) not in (None, "") else 0.0
-    dom = [r for r in rows if r["kernel"].startswith("gemm_tcgen05_kernel") and r["op"] in ("gemm", "conv3x3")]
+    dom = [r for r in rows if r["kernel"].startswith("gemm_tcgen05_kernel") and r["op"] in ("gemm", "conv3x3", "conv3x3_s2", "upconv3x3")]
     n = sum(int(r["launches"]) for r in dom)
     if not n:
         return None

@@ -33,8 +33,8 @@ int vx_gemm_bf16(const void* A, long long lda, int K1, const void* A2, long long
                  const void* residual, long long ldr, void* out, long long ldc, int out_f32, int block_n,
                  void* stream);
 
-/* ---- LayerNorm folded into the consumer GEMM (experiment, default off in the engine: VX_LN_FOLD=1; written at the
- * end of round 1 without GPU budget left -- not yet run on hardware).  vx_row_stats writes (mean, rstd) per row of the
+/* ---- LayerNorm folded into the consumer GEMM (VX_LN_FOLD=1; run on hardware in round 2: parity green, no gain with the
+ * separate statistics pass -- see vx_gemm_rowsums_bf16 for the variant without one).  vx_row_stats writes (mean, rstd) per row of the
  * un-normalised activations; vx_gemm_lnfold_bf16 computes rstd[m] * (A @ Wt^T - mean[m] * colsum) + bias with
  * Wt = W * gamma, colsum[n] = sum_k Wt[n,k], bias[n] = sum_k beta[k] W[n,k] + b[n]: the nn.LayerNorm + nn.Linear pairs
  * of modules/attention.py:329-375 and modules/motion_module.py:228-234 without writing LayerNorm(x) to HBM. */
@@ -43,6 +43,22 @@ int vx_gemm_lnfold_bf16(const void* A, long long lda, int K, const void* Wt, lon
                         const float* stats, const float* colsum, const float* bias, const float* bias2, int bias2_div,
                         float scale, const void* residual, long long ldr, void* out, long long ldc, int geglu,
                         int block_n, void* stream);
+
+/* LayerNorm statistics handed from GEMM to GEMM.  Every nn.LayerNorm of the transformer blocks normalises the output of a
+ * Linear (+ residual) -- attn.to_out / proj_in of modules/attention.py:321-375, modules/transformer_3d.py:64-66,
+ * modules/motion_module.py:122,228-234,300-321 -- and feeds another Linear.  vx_gemm_rowsums_bf16 is vx_gemm_bf16 (linear
+ * epilogue, bf16 out) that also writes per output row `*nparts` = 2 * ceil(N / block_n) float2 partials (sum, sum of
+ * squares) of the ROUNDED outputs, row_parts[slot * parts_stride + m] (parts_cap slots allocated); vx_gemm_lnparts_bf16 is vx_gemm_lnfold_bf16 that
+ * derives mean / rstd from such partials (slot order, fp32, variance = E[x^2] - mean^2, eps as nn.LayerNorm).  Together:
+ * LayerNorm(x) @ W^T with neither a normalisation pass nor a statistics pass over x. */
+int vx_gemm_rowsums_bf16(const void* A, long long lda, int K1, const void* A2, long long lda2, int K2, const void* W,
+                         long long ldw, int M, int N, const float* bias, const float* bias2, int bias2_div, float scale,
+                         const void* residual, long long ldr, void* out, long long ldc, int block_n, float* row_parts,
+                         long long parts_stride, int parts_cap, int* nparts, void* stream);
+int vx_gemm_lnparts_bf16(const void* A, long long lda, int K, const void* Wt, long long ldw, int M, int N,
+                         const float* row_parts, long long parts_stride, int nparts, float eps, const float* colsum,
+                         const float* bias, const float* bias2, int bias2_div, float scale, const void* residual,
+                         long long ldr, void* out, long long ldc, int geglu, int block_n, void* stream);
 
 /* nn.LayerNorm -> nn.Linear in ONE kernel for K <= 512 (the UNet's 320-wide level): same folded parameters as
  * vx_gemm_lnfold_bf16, but the (mean, rstd) of a row tile are computed inside the kernel from the shared-memory resident

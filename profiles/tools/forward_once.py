@@ -34,6 +34,14 @@ def meta_of(name, a, k):
         ob = 4 if k.get("out_f32") else 2
         return (f"M={M} K={K} N={N}" + (" geglu" if k.get("geglu") else "") + (" +res" if res is not None else ""),
                 2.0 * M * N * K, 2.0 * (M * K + N * K) + ob * M * nout + (2.0 * M * nout if res is not None else 0))
+    if name in ("gemm_rowsums", "gemm_lnparts"):   # LayerNorm statistics hand-over: producer (+ 8 B x slots per row) / consumer
+        A, W = a[0], a[1]
+        res = k.get("residual")
+        M, K, N = A.shape[0], A.shape[1], W.shape[0]
+        nout = N // 2 if k.get("geglu") else N
+        tag = "rowsums" if name == "gemm_rowsums" else "lnparts"
+        return (f"M={M} K={K} N={N} {tag}" + (" geglu" if k.get("geglu") else "") + (" +res" if res is not None else ""),
+                2.0 * M * N * K, 2.0 * (M * K + N * K) + 2.0 * M * nout + (2.0 * M * nout if res is not None else 0))
     if name == "conv3x3":
         X, W = a[0], a[1]
         nb, h, w, c = X.shape
@@ -87,7 +95,7 @@ def meta_of(name, a, k):
     return ("", 0.0, 0.0)
 
 
-NAMES = ["gemm", "conv3x3", "conv3x3_s2", "upconv3x3", "flash_attention", "temporal_attention", "smallkv_attention", "groupnorm", "layernorm", "conv_in",
+NAMES = ["gemm", "gemm_rowsums", "gemm_lnparts", "conv3x3", "conv3x3_s2", "upconv3x3", "flash_attention", "temporal_attention", "smallkv_attention", "groupnorm", "layernorm", "conv_in",
          "conv_out_tc", "im2col_s2", "im2col3x3", "upsample2x", "skinny_linear", "timestep_embed", "softmax_rows", "geglu",
          "cfg_overlap_accumulate", "ddim_step"]
 

@@ -201,7 +201,7 @@ def _cpu_engine(cls, model):
     if cls is unet_3d.UNetEngine:
         eng._pack_ln_fold()
     else:
-        eng.ln_fold = False
+        eng.ln_fold = eng.ln_fuse = False
     return eng
 
 
@@ -242,6 +242,20 @@ class _ShapeOps:
                 K = x.shape[1] + (k["a2"].shape[1] if k.get("a2") is not None else 0)
                 assert w.shape[1] == K, (x.shape, w.shape)
                 return torch.zeros(x.shape[0], w.shape[0] // 2 if k.get("geglu") else w.shape[0])
+            if op == "gemm_rowsums":
+                x, w = a[:2]
+                assert w.shape[1] == x.shape[1], (x.shape, w.shape)
+                if k.get("residual") is not None:
+                    assert k["residual"].shape == (x.shape[0], w.shape[0])
+                return torch.zeros(x.shape[0], w.shape[0]), torch.zeros(2 * (w.shape[0] // 32), x.shape[0], 2), 4
+            if op == "gemm_lnparts":
+                x, wf, parts, nparts, cs, bf = a[:6]
+                M, K = x.shape
+                N = wf.shape[0]
+                assert wf.shape[1] == K and parts.shape[1:] == (M, 2) and 0 < nparts <= parts.shape[0] and cs.shape == (N,) and bf.shape == (N,)
+                if k.get("bias2") is not None:
+                    assert k["bias2"].shape == (M // k["bias2_div"], N) and M % k["bias2_div"] == 0
+                return torch.zeros(M, N // 2 if k.get("geglu") else N)
             if op == "layernorm":
                 assert a[1].shape == (a[0].shape[1],)
                 return torch.zeros_like(a[0])
@@ -299,16 +313,17 @@ class _ShapeOps:
         return f
 
 
-@pytest.mark.parametrize("fold,one_kernel", [("0", "0"), ("1", "0")])
-def test_transformer_block_schedules_dry_run(monkeypatch, fold, one_kernel):
+@pytest.mark.parametrize("fold,fuse", [("0", "0"), ("1", "0"), ("0", "1")])
+def test_transformer_block_schedules_dry_run(monkeypatch, fold, fuse):
     """Host logic of UNetEngine._spatial / _motion with shape-checking fake ops, without touching a GPU: the three
-    LayerNorm -> Linear schedules -- LayerNorm kernel + GEMM (VX_LN_GEMM=0), row_stats + gemm_lnfold (VX_LN_FOLD=1), and the
-    default one-kernel gemm_ln for K <= 512 (incl. the positional-encoding bias of the motion modules)."""
+    LayerNorm -> Linear schedules -- LayerNorm kernel + GEMM (VX_LN_FUSE=0), row_stats + gemm_lnfold (VX_LN_FOLD=1), and the
+    statistics hand-over (VX_LN_FUSE=1): gemm_rowsums in the producer, gemm_lnparts in the consumer (incl. the
+    positional-encoding bias of the motion modules)."""
     import torch
     from oracle import vx_oracle as O
     from vexpress_b200.modules import UNet3DConditionModel, unet_3d
     monkeypatch.setenv("VX_LN_FOLD", fold)
-    monkeypatch.setenv("VX_LN_GEMM", one_kernel)
+    monkeypatch.setenv("VX_LN_FUSE", fuse)
     cfg = O.small_cfg()
     m = UNet3DConditionModel(
         block_out_channels=cfg["block_out_channels"], cross_attention_dim=cfg["cross_attention_dim"],
@@ -319,7 +334,7 @@ def test_transformer_block_schedules_dry_run(monkeypatch, fold, one_kernel):
                                   temporal_attention_dim_div=1))
     m.load_state_dict(O.synth_state_dict(O.unet_param_shapes(cfg), 1234), strict=True)
     eng = _cpu_engine(unet_3d.UNetEngine, m.to(torch.bfloat16))
-    assert eng.ln_fold == (fold == "1") and len(eng.F) == (127 if "1" in (fold, one_kernel) else 0)
+    assert eng.ln_fold == (fold == "1") and eng.ln_fuse == (fuse == "1") and len(eng.F) == (127 if "1" in (fold, fuse) else 0)
     fake = _ShapeOps()
     monkeypatch.setattr(unet_3d, "ops", fake)
     C, HW, f, b = 64, 256, 4, 2
@@ -330,8 +345,9 @@ def test_transformer_block_schedules_dry_run(monkeypatch, fold, one_kernel):
     assert eng._spatial("down_blocks.0.attentions.0", x, NB, HW, f, enc).shape == x.shape
     assert eng._motion("down_blocks.0.motion_modules.0", x, NB, HW, b, f).shape == x.shape
     n_ln = 7                                   # norm1, norm1_5, norm2, norm3 + norms.0, norms.1, ff_norm
-    if one_kernel == "1":
-        assert fake.calls.count("gemm_ln") == n_ln and not {"layernorm", "row_stats", "gemm_lnfold"} & set(fake.calls)
+    if fuse == "1":
+        assert fake.calls.count("gemm_rowsums") == n_ln and fake.calls.count("gemm_lnparts") == n_ln
+        assert not {"layernorm", "row_stats", "gemm_lnfold"} & set(fake.calls)
     elif fold == "1":
         assert fake.calls.count("row_stats") == n_ln and fake.calls.count("gemm_lnfold") == n_ln
         assert "layernorm" not in fake.calls
@@ -593,6 +609,26 @@ class _EmuOps:
             acc = acc + residual.float()
         return self._ret(acc.to(torch.bfloat16), out)
 
+    def gemm_rowsums(self, a, w, bias=None, *, a2=None, scale=1.0, residual=None, out=None):
+        """vx_gemm_rowsums_bf16: the GEMM plus per-row partial (sum, sum of squares) of its ROUNDED outputs, here split over
+        two slots (column halves) the way the kernel splits them over 2 * tiles_n."""
+        o = self.gemm(a, w, bias, a2=a2, scale=scale, residual=residual, out=out)
+        of = o.float()
+        half = of.shape[1] // 2
+        parts = torch.zeros(2 * ((of.shape[1] + 31) // 32), of.shape[0], 2)
+        for j, blk in enumerate((of[:, :half], of[:, half:])):
+            parts[j, :, 0] = blk.sum(1)
+            parts[j, :, 1] = (blk * blk).sum(1)
+        return o, parts, 2
+
+    def gemm_lnparts(self, a, wf, parts, nparts, colsum, bias, eps=1e-5, **k):
+        """vx_gemm_lnparts_bf16: mean / rstd from the partial sums (variance = E[x^2] - mean^2, fp32)."""
+        K = a.shape[1]
+        s1, s2 = parts[:nparts, :, 0].sum(0), parts[:nparts, :, 1].sum(0)
+        mean = s1 / K
+        rstd = ((s2 / K - mean * mean).clamp_min(0) + eps).rsqrt()
+        return self.gemm_lnfold(a, wf, torch.stack([mean, rstd], 1), colsum, bias, **k)
+
     def gemm_ln(self, a, wf, colsum, bias, eps=1e-5, **k):
         """vx_gemm_ln_bf16: the statistics come from the same bf16 rows the GEMM multiplies (two-pass variance)."""
         assert a.shape[1] % 64 == 0 and a.shape[1] <= self.real.LN_GEMM_MAX_K
@@ -630,8 +666,8 @@ def test_prologue_modules_compose_correctly(monkeypatch, golden_dir):
     assert ya.shape == a["tokens"].shape and rel(ya, a["tokens"]) < 2e-2, rel(ya, a["tokens"])
 
 
-@pytest.mark.parametrize("fold,one_kernel", [("0", "0"), ("1", "0")])
-def test_unet_engine_matches_oracle_with_emulated_kernels(monkeypatch, golden_dir, fold, one_kernel):
+@pytest.mark.parametrize("fold,fuse", [("0", "0"), ("1", "0"), ("0", "1")])
+def test_unet_engine_matches_oracle_with_emulated_kernels(monkeypatch, golden_dir, fold, fuse):
     """The whole UNetEngine.forward_frames host schedule (weight packing, split-K concat, time-embedding bias, banks,
     CFG uncond-half skip, GEGLU packing, ...) with every kernel replaced by a functional CPU emulation, against the
     oracle -- with the LayerNorm kernel, with VX_LN_FOLD=1 (LayerNorm folded into the GEMM epilogue, positional encoding
@@ -639,7 +675,7 @@ def test_unet_engine_matches_oracle_with_emulated_kernels(monkeypatch, golden_di
     from oracle import vx_oracle as O
     from vexpress_b200.modules import ReferenceAttentionControl, UNet3DConditionModel, unet_3d
     monkeypatch.setenv("VX_LN_FOLD", fold)
-    monkeypatch.setenv("VX_LN_GEMM", one_kernel)
+    monkeypatch.setenv("VX_LN_FUSE", fuse)
     cfg = O.small_cfg()
     m = UNet3DConditionModel(
         block_out_channels=cfg["block_out_channels"], cross_attention_dim=cfg["cross_attention_dim"],
@@ -669,7 +705,7 @@ def test_unet_engine_matches_oracle_with_emulated_kernels(monkeypatch, golden_di
     with torch.no_grad():
         ref = O.unet_forward(sd, cfg, x, 499, enc, kps, banks, 0.95, 3.0)
     err = ((out - ref).norm() / ref.norm()).item()
-    print(f"emulated engine vs oracle (VX_LN_FOLD={fold}, VX_LN_GEMM={one_kernel}): rel-L2 {err:.3e}")
+    print(f"emulated engine vs oracle (VX_LN_FOLD={fold}, VX_LN_FUSE={fuse}): rel-L2 {err:.3e}")
     assert err < 3e-2, err
 
 

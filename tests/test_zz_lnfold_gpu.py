@@ -99,8 +99,50 @@ def test_gemm_ln_matches_layernorm_then_linear(M, K, N, geglu, residual, pe):
         assert torch.equal(again, out)
 
 
+@pytest.mark.parametrize("M,K,C,N,geglu,residual", [(4096, 320, 320, 960, False, True), (131072, 320, 320, 320, False, True),
+                                                    (2048, 1280, 1280, 3840, False, True), (8192, 5120, 1280, 10240, True, True),
+                                                    (1000, 640, 640, 1920, False, False), (300, 64, 64, 192, False, True),
+                                                    (32768, 640, 640, 5120, True, True), (128 * 75, 256, 128, 256, False, True)])
+def test_layernorm_handover_between_gemms(M, K, C, N, geglu, residual):
+    """Producer GEMM [M,K]x[C,K] (+bias, +residual) with row sums -> consumer GEMM LayerNorm(h) @ W^T from the partial
+    sums, against (a) the producer's plain twin: identical output bits, row sums equal to fp32 sums of those bits within
+    fp32 rounding, and (b) LayerNorm kernel + GEMM on the same h / torch fp32."""
+    from vexpress_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(M + K + N)
+    a = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    wp = (torch.randn(C, K, device="cuda", generator=g) / K ** 0.5).bfloat16()
+    bp = torch.randn(C, device="cuda", generator=g)
+    res = (torch.randn(M, C, device="cuda", generator=g) * 2 + 0.5).bfloat16() if residual else None
+    h_plain = ops.gemm(a, wp, bp, residual=res)
+    h, parts, n = ops.gemm_rowsums(a, wp, bp, residual=res)
+    assert torch.equal(h, h_plain) and 2 <= n <= ops.rowsum_slots(C) == parts.shape[0]
+    hf = h.float()
+    s1, s2 = parts[:n, :, 0].sum(0), parts[:n, :, 1].sum(0)
+    e1 = ((s1 - hf.sum(1)).abs() / hf.abs().sum(1).clamp_min(1e-6)).max().item()
+    e2 = ((s2 - (hf * hf).sum(1)).abs() / (hf * hf).sum(1).clamp_min(1e-6)).max().item()
+    w = (torch.randn(N, C, device="cuda", generator=g) / C ** 0.5).bfloat16()
+    b = torch.randn(N, device="cuda", generator=g)
+    gamma = 1 + 0.1 * torch.randn(C, device="cuda", generator=g)
+    beta = 0.1 * torch.randn(C, device="cuda", generator=g)
+    wf, cs, bf = ops.fold_layernorm(w, b, gamma, beta, geglu=geglu)
+    out = ops.gemm_lnparts(h, wf, parts, n, cs, bf, 1e-5, geglu=geglu)
+    ref = F.layer_norm(hf, (C,), gamma, beta, 1e-5) @ w.float().t() + b
+    if geglu:
+        wg, bg, _ = ops.pack_geglu(w, b)
+        two = ops.gemm(ops.layernorm(h, gamma, beta, 1e-5), wg, bg, geglu=True)
+        v, gate = ref.chunk(2, dim=-1)
+        ref = v * F.gelu(gate)
+    else:
+        two = ops.gemm(ops.layernorm(h, gamma, beta, 1e-5), w, b)
+    err, err2 = _rel(out, ref), _rel(two, ref)
+    print(f"handover M={M} K={K} C={C} N={N} geglu={geglu}: {n} partials, row sums {e1:.1e} / {e2:.1e}; "
+          f"rel={err:.3e} (layernorm kernel + gemm: {err2:.3e})")
+    assert e1 < 1e-5 and e2 < 1e-5
+    assert err < 6e-3 and err < 1.5 * err2 + 1e-4, (err, err2)
+
+
 def test_unet_with_ln_fold_vs_oracle(golden_dir, monkeypatch):
-    """Whole small UNet with VX_LN_FOLD=1 against the fp32 oracle on the same bf16-rounded weights: same bound as the
+    """Whole small UNet with VX_LN_FOLD=1 and with the statistics hand-over (VX_LN_FUSE=1) against the fp32 oracle on the same bf16-rounded weights: same bound as the
     default LayerNorm-kernel path (two bf16 evaluation orders of the same network sit ~sqrt(2) x 1.6e-2 apart from each
     other, so they are each compared with fp32, not with one another)."""
     from oracle import vx_oracle as O
@@ -114,10 +156,14 @@ def test_unet_with_ln_fold_vs_oracle(golden_dir, monkeypatch):
     with torch.no_grad():
         ref = O.unet_forward({k: r(v) for k, v in sd.items()}, cfg, r(x), 499, r(enc), r(kps), [r(b) for b in banks], 0.95, 3.0)
     errs = {}
-    for fold in ("0", "1"):
+    for mode, (fold, fuse) in dict(kernel=("0", "0"), fold=("1", "0"), handover=("0", "1")).items():
         monkeypatch.setenv("VX_LN_FOLD", fold)
+        monkeypatch.setenv("VX_LN_FUSE", fuse)
         model, _ = build_product(cfg, sd, [b[1:] for b in banks], 0.95, 3.0)
+        eng = model.engine()
+        assert (eng.ln_fold, eng.ln_fuse) == (fold == "1", fuse == "1")
         out = model(x.cuda().bfloat16(), 499, enc.cuda().bfloat16(), kps_features=kps.cuda().bfloat16(), return_dict=False)[0]
-        errs[fold] = _rel(out.cpu(), ref)
-    print(f"unet vs oracle: default {errs['0']:.3e}, ln-fold {errs['1']:.3e}")
-    assert errs["1"] < 3e-2 and errs["1"] < 1.5 * errs["0"], errs
+        errs[mode] = _rel(out.cpu(), ref)
+    print(f"unet vs oracle: LayerNorm kernel {errs['kernel']:.3e}, ln-fold {errs['fold']:.3e}, statistics hand-over {errs['handover']:.3e}")
+    for mode in ("fold", "handover"):
+        assert errs[mode] < 3e-2 and errs[mode] < 1.5 * errs["kernel"], errs

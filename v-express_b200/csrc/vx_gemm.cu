@@ -66,6 +66,17 @@ struct GemmArgs {
   // compute the row statistics from the resident tile -- no statistics pass, no LayerNorm pass, 1/tiles_n of the A traffic.
   int ares;
   int ares_bytes;           // kblocks1 x 16 KB
+  // LayerNorm statistics handed from the producer GEMM to the consumer GEMM (no statistics pass over the activations):
+  //   producer (linear epilogue): rs_out[(tile_n * 2 + half) * rs_stride + m] = (sum, sum of squares) of the bf16-ROUNDED
+  //     outputs this epilogue thread wrote for row m (its half of the column tile) -- 2 * tiles_n partials per row;
+  //   consumer (LNF instantiations): mean / rstd of row m from ln_nparts such partials, summed in slot order
+  //     (deterministic), variance = E[x^2] - mean^2 in fp32, eps = ln_eps, channel count 1 / ln_invK.
+  float2* rs_out;
+  long long rs_stride;
+  const float2* ln_parts;
+  long long ln_pstride;
+  int ln_nparts;
+  float ln_invK;
   // W multicast (CG = 1 only): the grid runs as clusters of two CTAs that own adjacent 128-row tiles and walk the same
   // column tiles in lock step per ring stage; each CTA fetches HALF of every W tile and multicasts it into both shared
   // memories (cp.async.bulk.tensor .multicast::cluster), the MMA commits release a stage in both CTAs.  L2 -> SM operand
@@ -568,12 +579,24 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             __syncwarp();
             if (lane == 0) mbar_arrive(&stats_empty[sbuf]);
           }
+        } else if (p.ln_parts) {
+          if (row_ok) {
+            float s1 = 0.f, s2 = 0.f;
+            for (int j = 0; j < p.ln_nparts; ++j) {
+              const float2 v = __ldg(p.ln_parts + (long long)j * p.ln_pstride + m);
+              s1 += v.x;
+              s2 += v.y;
+            }
+            ln_mean = s1 * p.ln_invK;
+            ln_rstd = rsqrtf(fmaxf(fmaf(-ln_mean, ln_mean, s2 * p.ln_invK), 0.f) + p.ln_eps);
+          }
         } else if (row_ok) {
           const float2 st = *reinterpret_cast<const float2*>(p.ln_stats + 2 * m);
           ln_mean = st.x;
           ln_rstd = st.y;
         }
       }
+      float rs_sum = 0.f, rs_sq = 0.f;   // row sums of the rounded outputs (producer side of the LayerNorm hand-over)
       for (int c = c_begin; c < c_end; ++c) {
         uint32_t v[16];
         float f[16];
@@ -672,10 +695,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
               f[h * 8 + 2 * i + 1] += tt.y;
             }
           }
-          *sp = make_uint4(pack_bf16(f[h * 8], f[h * 8 + 1]), pack_bf16(f[h * 8 + 2], f[h * 8 + 3]),
-                           pack_bf16(f[h * 8 + 4], f[h * 8 + 5]), pack_bf16(f[h * 8 + 6], f[h * 8 + 7]));
+          const uint4 pk = make_uint4(pack_bf16(f[h * 8], f[h * 8 + 1]), pack_bf16(f[h * 8 + 2], f[h * 8 + 3]),
+                                      pack_bf16(f[h * 8 + 4], f[h * 8 + 5]), pack_bf16(f[h * 8 + 6], f[h * 8 + 7]));
+          *sp = pk;
+          if (p.rs_out) {
+            const uint32_t pw[4] = {pk.x, pk.y, pk.z, pk.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 t = unpack_bf16(pw[i]);
+              rs_sum += t.x + t.y;
+              rs_sq = fmaf(t.x, t.x, rs_sq);
+              rs_sq = fmaf(t.y, t.y, rs_sq);
+            }
+          }
         }
       }
+      if (p.rs_out && row_ok) p.rs_out[(long long)(tile_n * 2 + half) * p.rs_stride + m] = make_float2(rs_sum, rs_sq);
       // accumulator stage drained: hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
@@ -923,7 +958,7 @@ static int launch(const CUtensorMap& mA, const CUtensorMap& mA2, const CUtensorM
     configured = true;
   }
   const int npar = a.ups ? 4 : 1;
-  const bool lnf = a.ln_stats != nullptr || a.ares;
+  const bool lnf = a.ln_stats != nullptr || a.ln_parts != nullptr || a.ares;
   const int threads = a.ares ? kThreads + kStatThreads : kThreads;
   if (cg == 1 && a.mc) {
     // clusters of two CTAs (adjacent row tiles), same residency as the pair kernel (one CTA per SM, two SMs of a TPC)
@@ -997,14 +1032,26 @@ using namespace vx;
 
 extern "C" void vx_gemm_reload_env() { gemm_env() = GemmEnv(); }   // sweep-tool hook (csrc/vx_bringup.h), not product ABI
 
+// LayerNorm statistics hand-over between two GEMMs (GemmArgs::rs_out / ln_parts)
+struct RowStatsIO {
+  float* out;            // producer: [2 * tiles_n][stride] float2 partial (sum, sum of squares) per row, or null
+  long long out_stride;  // >= M
+  int out_cap;           // slots the caller allocated
+  int* nparts_out;       // producer: receives 2 * tiles_n
+  const float* parts;    // consumer: partials of the rows of A, or null
+  long long parts_stride;
+  int nparts;
+};
+
 // epilogue: 0 = linear (bias, bias2, scale, residual); 1 = GEGLU (W / bias packed per tile as value|gate halves,
 // see vx_geglu_pack_rows; out has N/2 columns)
 static int gemm_entry(const void* A, long long lda, int K1, const void* A2, long long lda2, int K2, const void* Wt,
                       long long ldw, int M, int N, const float* bias, const float* bias2, int bias2_div, float scale,
                       const void* residual, long long ldr, void* out, long long ldc, int out_f32, int block_n,
-                      const float* ln_stats, const float* ln_colsum, void* stream, float ln_eps = 0.f) {
+                      const float* ln_stats, const float* ln_colsum, void* stream, float ln_eps = 0.f,
+                      const RowStatsIO* rs = nullptr) {
   const int geglu = out_f32 == 2 ? 1 : 0;  // out_f32: 0 bf16, 1 fp32, 2 bf16 + GEGLU epilogue
-  const bool ares = ln_colsum && !ln_stats;   // LayerNorm GEMM with in-kernel statistics (A tile resident)
+  const bool ares = ln_colsum && !ln_stats && !(rs && rs->parts);   // LayerNorm GEMM with in-kernel statistics (A tile resident)
   if (geglu) out_f32 = 0;
   VX_REQUIRE(M > 0 && N > 0 && K1 > 0, "vx_gemm_bf16: bad shape M=%d N=%d K1=%d", M, N, K1);
   const int gran = geglu ? 64 : (out_f32 ? 16 : 32);
@@ -1089,6 +1136,20 @@ static int gemm_entry(const void* A, long long lda, int K1, const void* A2, long
   a.ares = ares ? 1 : 0;
   a.ares_bytes = ares ? a.kblocks1 * kBlockM * kBlockK * 2 : 0;
   a.ln_eps = ln_eps;
+  if (rs && rs->out) {
+    VX_REQUIRE(!out_f32 && !geglu && rs->out_stride >= M, "vx_gemm_rowsums_bf16: linear bf16 epilogue only, stride >= M");
+    VX_REQUIRE(2 * a.tiles_n <= rs->out_cap, "vx_gemm_rowsums_bf16: %d partial slots needed, %d allocated", 2 * a.tiles_n, rs->out_cap);
+    a.rs_out = reinterpret_cast<float2*>(rs->out);
+    a.rs_stride = rs->out_stride;
+    if (rs->nparts_out) *rs->nparts_out = 2 * a.tiles_n;
+  }
+  if (rs && rs->parts) {
+    VX_REQUIRE(ln_colsum && K2 == 0 && rs->nparts > 0 && rs->parts_stride >= M, "vx_gemm_lnparts_bf16: bad statistics operands");
+    a.ln_parts = reinterpret_cast<const float2*>(rs->parts);
+    a.ln_pstride = rs->parts_stride;
+    a.ln_nparts = rs->nparts;
+    a.ln_invK = 1.0f / (float)K1;
+  }
   return launch(mA, mA2, mB, mR, mC, a, (cudaStream_t)stream);
 }
 
@@ -1110,6 +1171,34 @@ extern "C" int vx_gemm_lnfold_bf16(const void* A, long long lda, int K, const vo
   VX_REQUIRE(stats && colsum, "vx_gemm_lnfold_bf16: stats / colsum missing (M=%d)", M);
   return gemm_entry(A, lda, K, nullptr, 0, 0, Wt, ldw, M, N, bias, bias2, bias2_div, scale, residual, ldr, out, ldc,
                     geglu ? 2 : 0, block_n, stats, colsum, stream);
+}
+
+// Producer side of the LayerNorm hand-over: vx_gemm_bf16's linear epilogue (bias, bias2, scale, residual; bf16 out) that also
+// writes, per output row, 2 * ceil(N / block_n) partial (sum, sum of squares) pairs of the ROUNDED outputs:
+// row_parts[slot * parts_stride + m] as float2, slot < *nparts.  The consumer GEMM (vx_gemm_lnparts_bf16) turns them into
+// mean / rstd, so LayerNorm(out) needs neither a normalisation pass nor a statistics pass over `out`.
+extern "C" int vx_gemm_rowsums_bf16(const void* A, long long lda, int K1, const void* A2, long long lda2, int K2,
+                                    const void* Wt, long long ldw, int M, int N, const float* bias, const float* bias2,
+                                    int bias2_div, float scale, const void* residual, long long ldr, void* out,
+                                    long long ldc, int block_n, float* row_parts, long long parts_stride, int parts_cap,
+                                    int* nparts, void* stream) {
+  VX_REQUIRE(row_parts && nparts, "vx_gemm_rowsums_bf16: row_parts / nparts missing (M=%d)", M);
+  RowStatsIO rs{row_parts, parts_stride, parts_cap, nparts, nullptr, 0, 0};
+  return gemm_entry(A, lda, K1, A2, lda2, K2, Wt, ldw, M, N, bias, bias2, bias2_div, scale, residual, ldr, out, ldc, 0,
+                    block_n, nullptr, nullptr, stream, 0.f, &rs);
+}
+
+// Consumer side: vx_gemm_lnfold_bf16 with the row statistics taken from a producer's partial sums instead of a
+// vx_row_stats array: mean = sum / K, variance = sum of squares / K - mean^2 (fp32), rstd = rsqrt(variance + eps).
+extern "C" int vx_gemm_lnparts_bf16(const void* A, long long lda, int K, const void* Wt, long long ldw, int M, int N,
+                                    const float* row_parts, long long parts_stride, int nparts, float eps,
+                                    const float* colsum, const float* bias, const float* bias2, int bias2_div, float scale,
+                                    const void* residual, long long ldr, void* out, long long ldc, int geglu, int block_n,
+                                    void* stream) {
+  VX_REQUIRE(row_parts && colsum, "vx_gemm_lnparts_bf16: row_parts / colsum missing (M=%d)", M);
+  RowStatsIO rs{nullptr, 0, 0, nullptr, row_parts, parts_stride, nparts};
+  return gemm_entry(A, lda, K, nullptr, 0, 0, Wt, ldw, M, N, bias, bias2, bias2_div, scale, residual, ldr, out, ldc,
+                    geglu ? 2 : 0, block_n, nullptr, colsum, stream, eps, &rs);
 }
 
 // LayerNorm -> Linear in ONE kernel: A holds the un-normalised rows (K <= 512), Wt / colsum / bias are the folded parameters

@@ -259,7 +259,7 @@ class RefNetEngine(UNetEngine):
         self.sd = {k: v.detach() for k, v in model.state_dict().items()}
         self.W: Dict[str, torch.Tensor] = {}
         self._pack(self.sd)
-        self.ln_fold = False
+        self.ln_fold = self.ln_fuse = False   # the write pass materialises LayerNorm(h) (it IS the bank): plain LayerNorm kernels
 
     def _transformer_write(self, p, x, NB, HW, enc_flat):
         """GroupNorm -> proj_in -> [norm1, attn1] -> bank = norm2(h) -> attn2(enc) -> ff -> proj_out + residual."""

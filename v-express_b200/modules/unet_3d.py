@@ -428,10 +428,17 @@ class UNetEngine:
         its operator tests but measured SLOWER than LayerNorm kernel + GEMM at the 320-wide level (379 vs 44 + 250 us for
         norm3 -> FF1, gpurun_out/r02_c21) and is not wired into the engine."""
         self.ln_fold = os.environ.get("VX_LN_FOLD") == "1"
+        # VX_LN_FUSE=1 (experiment, measured: parity green, SLOWER -- stays off): statistics hand-over.  Every LayerNorm
+        # input is the output of a Linear (+ residual); that GEMM's epilogue emits per-row partial sums (ops.gemm_rowsums),
+        # the consumer GEMM normalises in its epilogue (ops.gemm_lnparts): no LayerNorm kernel, no statistics kernel,
+        # LayerNorm(x) never written.  The normalising epilogue costs more than the LayerNorm kernel it removes: the K = 320
+        # / 640 GEMMs are bound by their epilogues' instruction issue (QKV 117 + 43 us -> 180 us, FF1 267 + 43 -> 383 us;
+        # UNet 54.9 -> 56.6 ms per step, gpurun_out/r02_c25).
+        self.ln_fuse = os.environ.get("VX_LN_FUSE", "0") != "0" and not self.ln_fold
         self.F: Dict[str, tuple] = {}
         self._pe_proj: Dict[str, torch.Tensor] = {}
         self._pe_bias: Dict[tuple, torch.Tensor] = {}
-        if not self.ln_fold:
+        if not (self.ln_fold or self.ln_fuse):
             return
         W = self.W
         for k in list(W):
@@ -454,12 +461,21 @@ class UNetEngine:
                     # (LayerNorm(x) + pe) W^T = LayerNorm(x) W^T + pe W^T: the positional encoding becomes a per-frame bias
                     self._pe_proj[a_] = (W[a_ + ".pos_encoder.pe"] @ W[a_ + ".qkv"].float().t()).contiguous()
 
-    def _ln_gemm(self, h, norm_key, w_key, *, geglu=False, pe=None, rows_per_frame=0, b=1):
-        """LayerNorm(h) [+ pe] -> Linear.  Default: the LayerNorm kernel followed by the GEMM; under VX_LN_FOLD the
-        statistics kernel and the GEMM with the normalising epilogue."""
+    def _gemm_p(self, a, w, bias, **kw):
+        """A Linear whose output feeds a LayerNorm: (out, hand-over) -- the hand-over is the (parts, nparts) of
+        ops.gemm_rowsums under the statistics hand-over, else None."""
+        if self.ln_fuse:
+            out, parts, n = ops.gemm_rowsums(a, w, bias, **kw)
+            return out, (parts, n)
+        return ops.gemm(a, w, bias, **kw), None
+
+    def _ln_gemm(self, h, norm_key, w_key, *, geglu=False, pe=None, rows_per_frame=0, b=1, rs=None):
+        """LayerNorm(h) [+ pe] -> Linear.  Default: the LayerNorm kernel followed by the GEMM.  With the producer's row sums
+        `rs` (VX_LN_FUSE=1): one GEMM with the normalising epilogue; VX_LN_FOLD=1: statistics kernel + GEMM with the
+        normalising epilogue."""
         W = self.W
         K = h.shape[1]
-        if not self.ln_fold:
+        if rs is None and not self.ln_fold:
             n = ops.layernorm(h, W[norm_key + ".weight"], W[norm_key + ".bias"], pe=pe, rows_per_frame=rows_per_frame)
             if geglu:
                 return ops.gemm(n, W[w_key + ".geglu_w"], W[w_key + ".geglu_b"], geglu=True)
@@ -475,6 +491,8 @@ class UNetEngine:
                 bias2 = self._pe_proj[a_][:f].repeat(b, 1).contiguous()
                 self._pe_bias[key] = bias2
             div = rows_per_frame
+        if rs is not None:
+            return ops.gemm_lnparts(h, wf, rs[0], rs[1], cs, bf, 1e-5, bias2=bias2, bias2_div=div, geglu=geglu)
         return ops.gemm_lnfold(h, wf, ops.row_stats(h), cs, bf, bias2=bias2, bias2_div=div, geglu=geglu)
 
     # ---------------------------------------------------------------- banks
@@ -537,15 +555,15 @@ class UNetEngine:
         heads = self.heads
         m = self.model
         h = ops.groupnorm(x, NB, HW, W[p + ".norm.weight"], W[p + ".norm.bias"], 1e-6, False, groups=self.groups)
-        h = ops.gemm(h, W[p + ".proj_in.weight"], W[p + ".proj_in.bias"])
+        h, rs = self._gemm_p(h, W[p + ".proj_in.weight"], W[p + ".proj_in.bias"])
         t = p + ".transformer_blocks.0"
         block = m.get_submodule(t)
         # attn1: self-attention
-        qkv = self._ln_gemm(h, t + ".norm1", t + ".attn1.qkv")
+        qkv = self._ln_gemm(h, t + ".norm1", t + ".attn1.qkv", rs=rs)
         a = ops.flash_attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], heads, HW, HW)
-        h = ops.gemm(a, W[t + ".attn1.to_out.0.weight"], W[t + ".attn1.to_out.0.bias"], residual=h)
+        h, rs = self._gemm_p(a, W[t + ".attn1.to_out.0.weight"], W[t + ".attn1.to_out.0.bias"], residual=h)
         # attn1_5: reference attention, K/V from the bank (one per CFG half, shared by the f frames)
-        q = self._ln_gemm(h, t + ".norm1_5", t + ".attn1_5.to_q.weight")
+        q = self._ln_gemm(h, t + ".norm1_5", t + ".attn1_5.to_q.weight", rs=rs)
         kv, uncond_zero = self._bank_kv(t, block)
         Nk = kv.shape[0] // (NB // f)
         if uncond_zero and NB == 2 * f:
@@ -554,17 +572,17 @@ class UNetEngine:
             ops.flash_attention(q[f * HW:], kv[Nk:, :C], kv[Nk:, C:], heads, HW, Nk, kv_div=f, out=a[f * HW:])
         else:
             a = ops.flash_attention(q, kv[:, :C], kv[:, C:], heads, HW, Nk, kv_div=f)
-        h = ops.gemm(a, W[t + ".attn1_5.to_out.0.weight"], W[t + ".attn1_5.to_out.0.bias"],
-                     scale=float(m.reference_attention_weight), residual=h)
+        h, rs = self._gemm_p(a, W[t + ".attn1_5.to_out.0.weight"], W[t + ".attn1_5.to_out.0.bias"],
+                             scale=float(m.reference_attention_weight), residual=h)
         # attn2: audio cross-attention (5 tokens per frame)
-        q = self._ln_gemm(h, t + ".norm2", t + ".attn2.to_q.weight")
+        q = self._ln_gemm(h, t + ".norm2", t + ".attn2.to_q.weight", rs=rs)
         kv2 = ops.gemm(enc_flat, W[t + ".attn2.kv"])
         Lk = enc_flat.shape[0] // NB
         a = ops.smallkv_attention(q, kv2[:, :C], kv2[:, C:], HW, heads, Lk)
-        h = ops.gemm(a, W[t + ".attn2.to_out.0.weight"], W[t + ".attn2.to_out.0.bias"],
-                     scale=float(m.audio_attention_weight), residual=h)
+        h, rs = self._gemm_p(a, W[t + ".attn2.to_out.0.weight"], W[t + ".attn2.to_out.0.bias"],
+                             scale=float(m.audio_attention_weight), residual=h)
         # feed-forward (GEGLU in the epilogue of the first GEMM)
-        g = self._ln_gemm(h, t + ".norm3", t + ".ff.net.0.proj", geglu=True)
+        g = self._ln_gemm(h, t + ".norm3", t + ".ff.net.0.proj", geglu=True, rs=rs)
         h = ops.gemm(g, W[t + ".ff.net.2.weight"], W[t + ".ff.net.2.bias"], residual=h)
         return ops.gemm(h, W[p + ".proj_out.weight"], W[p + ".proj_out.bias"], residual=x)
 
@@ -573,17 +591,17 @@ class UNetEngine:
         p = p + ".temporal_transformer"
         C = x.shape[1]
         h = ops.groupnorm(x, NB, HW, W[p + ".norm.weight"], W[p + ".norm.bias"], 1e-6, False, groups=self.groups)
-        h = ops.gemm(h, W[p + ".proj_in.weight"], W[p + ".proj_in.bias"])
+        h, rs = self._gemm_p(h, W[p + ".proj_in.weight"], W[p + ".proj_in.bias"])
         t = p + ".transformer_blocks.0"
         for i in (0, 1):
             a_ = f"{t}.attention_blocks.{i}"
             pe = W[a_ + ".pos_encoder.pe"]
             if f > pe.shape[0]:
                 raise ValueError(f"window of {f} frames exceeds temporal_position_encoding_max_len={pe.shape[0]}")
-            qkv = self._ln_gemm(h, f"{t}.norms.{i}", a_ + ".qkv", pe=pe[:f], rows_per_frame=HW, b=b)
+            qkv = self._ln_gemm(h, f"{t}.norms.{i}", a_ + ".qkv", pe=pe[:f], rows_per_frame=HW, b=b, rs=rs)
             a = ops.temporal_attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], b, f, HW, self.heads)
-            h = ops.gemm(a, W[a_ + ".to_out.0.weight"], W[a_ + ".to_out.0.bias"], residual=h)
-        g = self._ln_gemm(h, t + ".ff_norm", t + ".ff.net.0.proj", geglu=True)
+            h, rs = self._gemm_p(a, W[a_ + ".to_out.0.weight"], W[a_ + ".to_out.0.bias"], residual=h)
+        g = self._ln_gemm(h, t + ".ff_norm", t + ".ff.net.0.proj", geglu=True, rs=rs)
         h = ops.gemm(g, W[t + ".ff.net.2.weight"], W[t + ".ff.net.2.bias"], residual=h)
         return ops.gemm(h, W[p + ".proj_out.weight"], W[p + ".proj_out.bias"], residual=x)
 

@@ -120,6 +120,50 @@ def gemm_lnfold(a, wf, stats, colsum, bias, *, bias2=None, bias2_div=1, scale=1.
     return out
 
 
+def rowsum_slots(N):
+    """Upper bound of the 2 * ceil(N / block_n) partial sums per row vx_gemm_rowsums_bf16 may write (block_n >= 32)."""
+    return 2 * ((N + 31) // 32)
+
+
+def gemm_rowsums(a, w, bias=None, *, a2=None, scale=1.0, residual=None, out=None):
+    """ops.gemm (linear epilogue, bf16) that also returns the LayerNorm hand-over of its output: (out, parts, nparts) with
+    parts fp32 [rowsum_slots(N), M, 2] = per-row partial (sum, sum of squares) of the rounded outputs in slots < nparts."""
+    _chk_bf16(a, w, a2, residual, out)
+    M, K1 = a.shape
+    K2 = 0 if a2 is None else a2.shape[1]
+    N = w.shape[0]
+    assert w.shape[1] == K1 + K2 and N // 32 * 2 >= 2
+    if out is None:
+        out = torch.empty((M, N), device=a.device, dtype=BF16)
+    cap = rowsum_slots(N)
+    parts = torch.empty((cap, M, 2), device=a.device, dtype=torch.float32)
+    nparts = c_int(0)
+    check(_ffi.lib().vx_gemm_rowsums_bf16(
+        ptr(a), c_ll(a.stride(0)), c_int(K1), ptr(a2), c_ll(0 if a2 is None else a2.stride(0)), c_int(K2),
+        ptr(w), c_ll(w.stride(0)), c_int(M), c_int(N), ptr(bias), ptr(None), c_int(1), c_float(scale),
+        ptr(residual), c_ll(0 if residual is None else residual.stride(0)), ptr(out), c_ll(out.stride(0)),
+        c_int(0), ptr(parts), c_ll(M), c_int(cap), ctypes.byref(nparts), stream_ptr()), "vx_gemm_rowsums_bf16")
+    assert 0 < nparts.value <= cap, nparts.value
+    return out, parts, nparts.value
+
+
+def gemm_lnparts(a, wf, parts, nparts, colsum, bias, eps=1e-5, *, bias2=None, bias2_div=1, scale=1.0, residual=None, out=None,
+                 geglu=False):
+    """gemm_lnfold with the row statistics of `a` taken from its producer's partial sums (gemm_rowsums)."""
+    _chk_bf16(a, wf, residual, out)
+    M, K = a.shape
+    N = wf.shape[0]
+    assert wf.shape[1] == K and parts.shape[1:] == (M, 2) and 0 < nparts <= parts.shape[0] and colsum.shape == (N,)
+    if out is None:
+        out = torch.empty((M, N // 2 if geglu else N), device=a.device, dtype=BF16)
+    check(_ffi.lib().vx_gemm_lnparts_bf16(
+        ptr(a), c_ll(a.stride(0)), c_int(K), ptr(wf), c_ll(wf.stride(0)), c_int(M), c_int(N), ptr(parts), c_ll(M),
+        c_int(nparts), c_float(eps), ptr(colsum), ptr(bias), ptr(bias2), c_int(bias2_div), c_float(scale), ptr(residual),
+        c_ll(0 if residual is None else residual.stride(0)), ptr(out), c_ll(out.stride(0)), c_int(int(geglu)),
+        c_int(geglu_block_n(N) if geglu else 0), stream_ptr()), "vx_gemm_lnparts_bf16")
+    return out
+
+
 def conv3x3(x, w, bias=None, *, bias2=None, bias2_div=1, scale=1.0, residual=None, out=None, block_n=0):
     """x: NHWC bf16 [NB,H,W,C]; w: [Cout, 9*C]; returns [NB*H*W, Cout] (= NHWC)."""
     _chk_bf16(x, w, residual, out)
