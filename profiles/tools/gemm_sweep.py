@@ -46,7 +46,9 @@ add_conv(16, 128, 128, 512, 512); add_conv(16, 256, 256, 256, 256); add_conv(16,
 
 settings = [("cg1", {"VX_GEMM_CG": "1"}), ("auto", {}), ("mc", {"VX_GEMM_MC": "1"}), ("cg1 mc", {"VX_GEMM_CG": "1", "VX_GEMM_MC": "1"}), ("cg2", {"VX_GEMM_CG": "2"}), ("cg2 nbuf1", {"VX_GEMM_CG": "2", "VX_GEMM_NBUF": "1"}),
             ("cg2 bn128", {"VX_GEMM_CG": "2", "VX_GEMM_BN": "128"}),
-            ("cg1 bn128", {"VX_GEMM_CG": "1", "VX_GEMM_BN": "128"})]
+            ("cg1 bn128", {"VX_GEMM_CG": "1", "VX_GEMM_BN": "128"}), ("bn128", {"VX_GEMM_BN": "128"}), ("bn64", {"VX_GEMM_BN": "64"}),
+            ("bn160", {"VX_GEMM_BN": "160"}), ("bn256", {"VX_GEMM_BN": "256"}), ("bn320", {"VX_GEMM_BN": "320"}),
+            ("nbuf1", {"VX_GEMM_NBUF": "1"}), ("st2", {"VX_GEMM_STAGES": "2"}), ("st4", {"VX_GEMM_STAGES": "4"})]
 if len(sys.argv) > 1:
     settings = [s for s in settings if s[0] in sys.argv[1:]]
 keys = ["VX_GEMM_CG", "VX_GEMM_NBUF", "VX_GEMM_BN", "VX_GEMM_STAGES", "VX_GEMM_MC"]

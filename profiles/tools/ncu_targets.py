@@ -27,6 +27,19 @@ elif what == "gemm320":
     res = torch.randn(M, C, device="cuda").bfloat16()
     for _ in range(3):
         ops.gemm(a, w, bias, residual=res)
+elif what == "gemm_qkv":       # level-0 fused QKV projection: N = 960, no residual -- neither MMA-, HBM- nor issue-bound on paper
+    a = torch.randn(M, C, device="cuda").bfloat16()
+    w = (torch.randn(3 * C, C, device="cuda") / 18).bfloat16()
+    out = torch.empty(M, 3 * C, device="cuda", dtype=torch.bfloat16)
+    for _ in range(3):
+        ops.gemm(a, w, None, out=out)
+elif what == "gemm_k640":      # level-1 out-projection: M = 32768, K = N = 640, + residual
+    a = torch.randn(32768, 640, device="cuda").bfloat16()
+    w = (torch.randn(640, 640, device="cuda") / 25).bfloat16()
+    bias = torch.zeros(640, device="cuda")
+    res = torch.randn(32768, 640, device="cuda").bfloat16()
+    for _ in range(3):
+        ops.gemm(a, w, bias, residual=res)
 elif what == "gemm_ff1":
     a = torch.randn(M, C, device="cuda").bfloat16()
     w = (torch.randn(8 * C, C, device="cuda") / 18).bfloat16()

@@ -83,6 +83,7 @@ struct GemmArgs {
   // traffic per 128 x bn x 64 MMA block drops from 16 KB + bn * 128 B to 16 KB + bn * 64 B like in the cta_group::2
   // kernel, but the two CTAs keep their own MMA stream, accumulators and epilogue.
   int mc;
+  int strict_arrive;   // cluster-scope release on the pair's accumulator hand-back (default; VX_GEMM_STRICT_ARRIVE=0: .release.cta, A/B)
   float ln_eps;
 };
 
@@ -149,6 +150,14 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+// The same arrival with the default (.release.cta) semantics: no cluster-scope fence in front of it.  Enough for the
+// accumulator hand-back: what the leader's next MMAs must not overtake are this warp's tcgen05.ld reads, and those have
+// completed (tcgen05.wait::ld) and are ordered by tcgen05.fence::before_thread_sync; no generic-proxy data is handed over.
+// The cluster-scope release compiles to an ERRBAR in front of every arrival: 15 % of the warp samples of the K = 640 pair
+// GEMM (ncu r02_gemm_k640).
+__device__ __forceinline__ void mbar_arrive_cluster_cta(uint32_t bar_cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
 }
 // TMA load of a 2-D box into the same shared-memory offset of every CTA in `mask`; each destination CTA's mbarrier at the
 // offset of `bar` receives the complete_tx
@@ -715,7 +724,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if (CG == 2) mbar_arrive_cluster(as ? te_leader1 : te_leader0);   // the pair leader's MMA warp owns both halves
+        if (CG == 2) {   // the pair leader's MMA warp owns both halves
+          if (p.strict_arrive) mbar_arrive_cluster(as ? te_leader1 : te_leader0);
+          else mbar_arrive_cluster_cta(as ? te_leader1 : te_leader0);
+        }
         else mbar_arrive(&tmem_empty[as]);
       }
       if (!p.out_f32) {
@@ -793,7 +805,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
 // A/B switches (bring-up only) are read ONCE per process: the launch path never touches the environment
 // (the sweep tools re-read them through vx_gemm_reload_env).
 struct GemmEnv {
-  int cg, cg_minkb, pairs, stages, nbuf, bn, verbose, conv_rr, mc;
+  int cg, cg_minkb, pairs, stages, nbuf, bn, verbose, conv_rr, mc, strict_arrive;
   static int geti(const char* name, int dflt) {
     const char* s = getenv(name);
     return s ? atoi(s) : dflt;
@@ -808,6 +820,7 @@ struct GemmEnv {
     verbose = geti("VX_GEMM_VERBOSE", 0);
     conv_rr = geti("VX_CONV_RR", 1);
     mc = geti("VX_GEMM_MC", 0);
+    strict_arrive = geti("VX_GEMM_STRICT_ARRIVE", 1);   // 0 measured: +16 % on K = 320 pair tiles, -3..5 % on long-K convs, forward unchanged
   }
 };
 static GemmEnv& gemm_env() {
@@ -909,6 +922,7 @@ static int num_pairs() {
 static int launch(const CUtensorMap& mA, const CUtensorMap& mA2, const CUtensorMap& mB, const CUtensorMap& mR,
                   const CUtensorMap& mC, GemmArgs& a, cudaStream_t st) {
   const int cg = use_pair(a) ? 2 : 1;
+  a.strict_arrive = gemm_env().strict_arrive;
   a.mc = (cg == 1 && !a.ares && mc_ok(a.out_f32, a.block_n, a.tiles_m, a.taps * a.kblocks1 + a.kblocks2)) ? 1 : 0;
   if (a.ares) a.a_bytes = 0;   // A lives in its own resident slots, the ring stages hold W only
   else if (a.a_bytes <= 0) a.a_bytes = kBlockM * kBlockK * 2;
