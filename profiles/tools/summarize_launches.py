@@ -9,13 +9,14 @@ with open(path, newline="") as f:
 rd = csv.reader(lines)
 hdr = next(rd)
 ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+mi = hdr.index("Metric Name") if "Metric Name" in hdr else -1      # multi-metric logs: only the duration rows count
 tot = defaultdict(lambda: [0, 0.0])
 for r in rd:
-    if len(r) <= vi or not r[vi]:
+    if len(r) <= vi or not r[vi] or (mi >= 0 and r[mi] != "gpu__time_duration.sum"):
         continue
     v = float(r[vi].replace(",", ""))
     unit = r[ui]
-    ns = v * {"ns": 1.0, "us": 1e3, "ms": 1e6, "s": 1e9}.get(unit, 1.0)
+    ns = v * {"ns": 1.0, "us": 1e3, "ms": 1e6, "s": 1e9, "nsecond": 1.0, "usecond": 1e3, "msecond": 1e6, "second": 1e9}.get(unit, 1.0)
     name = re.sub(r"\(.*", "", r[ki])
     t = tot[name]
     t[0] += 1
