@@ -115,6 +115,13 @@ int vx_groupnorm_fused(const void* x1, long long ld1, int C1, const void* x2, lo
                        int S, float* partial, int* counters, const float* gamma, const float* beta, float eps, int silu,
                        void* out, long long ldo, void* stream);
 
+/* GroupNorm of small frames (the 8x8 / 16x16 levels) with the frame resident in the shared memory of a thread-block
+ * cluster: one pass over HBM, partial statistics exchanged through distributed shared memory, no workspace.  Same
+ * operands as vx_groupnorm_fused; returns 2 without launching when the frame does not fit a cluster of <= 8 CTAs. */
+int vx_groupnorm_cluster(const void* x1, long long ld1, int C1, const void* x2, long long ld2, int C2, int NB, int HW,
+                         int G, const float* gamma, const float* beta, float eps, int silu, void* out, long long ldo,
+                         void* stream);
+
 /* ---- LayerNorm over C, optional + pe[(row / rows_per_frame) % pe_frames] (temporal positional encoding).
  * Replaces nn.LayerNorm (modules/attention.py:329-333; modules/motion_module.py:228,234) and
  * PositionalEncoding.forward (modules/motion_module.py:275-277). */

@@ -166,8 +166,43 @@ def test_groupnorm(ops, NB, HW, C1, C2, silu, eps):
     assert err < 4e-3
 
 
+@pytest.mark.parametrize("NB,HW,C1,C2,silu", [(32, 64, 1280, 0, True), (32, 64, 1280, 1280, True), (32, 256, 1280, 0, False),
+                                              (32, 256, 1280, 640, True), (8, 64, 1280, 0, True), (2, 256, 640, 640, True),
+                                              (4, 64, 320, 0, False), (3, 16, 256, 0, True), (32, 1024, 640, 0, True),
+                                              (5, 36, 64, 32, True)])
+def test_groupnorm_cluster_resident(ops, NB, HW, C1, C2, silu):
+    """GroupNorm with the frame resident in a thread-block cluster's shared memory (one pass over HBM, partial statistics
+    through distributed shared memory) vs torch fp32 and vs the one-launch rendezvous kernel; repeated launches must give
+    identical bits (fixed merge order).  Frames that do not fit one wave of clusters fall back to the rendezvous kernel
+    (the 16x16 x 32-frame and 32x32 cases: identical bits to it)."""
+    g = _gen(NB + HW + C1)
+    x1 = (torch.randn(NB * HW, C1, device="cuda", generator=g) * 2 + 0.3).bfloat16()
+    x2 = (torch.randn(NB * HW, C2, device="cuda", generator=g) - 0.5).bfloat16() if C2 else None
+    C = C1 + C2
+    gamma = 1 + 0.1 * torch.randn(C, device="cuda", generator=g)
+    beta = 0.1 * torch.randn(C, device="cuda", generator=g)
+    old = ops._GN_CLUSTER
+    try:
+        ops._GN_CLUSTER = False
+        base = ops.groupnorm(x1, NB, HW, gamma, beta, 1e-5, silu, x2=x2).clone()
+        ops._GN_CLUSTER = True
+        outs = [ops.groupnorm(x1, NB, HW, gamma, beta, 1e-5, silu, x2=x2).clone() for _ in range(3)]
+    finally:
+        ops._GN_CLUSTER = old
+    x = x1.float() if x2 is None else torch.cat([x1.float(), x2.float()], 1)
+    ref = F.group_norm(x.view(NB, HW, C).transpose(1, 2), 32, gamma, beta, 1e-5)
+    if silu:
+        ref = F.silu(ref)
+    ref = ref.transpose(1, 2).reshape(NB * HW, C)
+    err, err_base = _rel(outs[0], ref), _rel(base, ref)
+    print(f"groupnorm cluster NB={NB} HW={HW} C={C1}+{C2} rel={err:.3e} (rendezvous kernel {err_base:.3e}), "
+          f"vs rendezvous kernel {_rel(outs[0], base.float()):.2e}")
+    assert err < 4e-3 and torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2])
+
+
 @pytest.mark.parametrize("rows,C,with_pe", [(4096, 320, False), (1000, 1280, True), (512, 640, True), (777, 64, False),
-                                            (2 * 9216, 320, False), (2 * 2304 + 3, 640, False), (4 * 144, 1280, True)])
+                                            (2 * 9216, 320, False), (2 * 2304 + 3, 640, False), (4 * 144, 1280, True),
+                                            (4096 + 5, 320, True), (131072, 320, True)])
 def test_layernorm(ops, rows, C, with_pe):
     g = _gen(rows + C)
     x = (torch.randn(rows, C, device="cuda", generator=g) * 3 + 1).bfloat16()

@@ -270,6 +270,163 @@ __global__ void gn_fused_kernel(const GnFusedArgs p) {
   });
 }
 
+// ------------------------------------------------------------------ GroupNorm with the frame resident in a cluster
+// Small frames (the 8x8 and 16x16 levels of the UNet: 64 / 256 pixels x <= 2560 channels) fit the shared memory of a
+// thread-block cluster: grid (CL, NB), cluster (CL, 1, 1), CTA r of frame n keeps pixels [r * P, (r + 1) * P) as raw bf16 in
+// shared memory.  ONE pass over HBM: load the chunk (statistics on the fly) -> per-CTA partial (count, mean, M2) per group
+// in shared memory -> cluster barrier -> every CTA reads all CL partials through distributed shared memory and merges them
+// in rank order (Chan et al., deterministic) -> normalise (+SiLU) its chunk out of shared memory -> store.  No global
+// partials, no counters, no spin wait, no second read; same per-chunk / merge arithmetic as gn_stats_body + gn_apply_body.
+struct GnClusterArgs {
+  const __nv_bfloat16* x1; long long ld1; int C1;
+  const __nv_bfloat16* x2; long long ld2; int C2;
+  int HW, G, P, R;          // P pixels per CTA (HW = CL * P), R pixel lanes (blockDim.x = (C / 8) * R)
+  const float* gamma; const float* beta;
+  float eps; int silu;
+  __nv_bfloat16* out; long long ldo;
+};
+
+__device__ __forceinline__ uint32_t gn_cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void gn_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float gn_ld_dsmem(const float* local, uint32_t rank) {   // the same offset in CTA `rank`'s shared memory
+  uint32_t ra;
+  float v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(local)), "r"(rank));
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
+  return v;
+}
+
+__global__ void gn_cluster_kernel(const GnClusterArgs p) {
+  pdl_enter();
+  extern __shared__ __align__(16) uint8_t gn_smem[];
+  const int C = p.C1 + p.C2, V = C / 8, G = p.G, cpg = C / G, R = p.R, P = p.P;
+  uint4* tile = reinterpret_cast<uint4*>(gn_smem);                      // [P][V] raw bf16 vectors
+  float* ssum = reinterpret_cast<float*>(tile + (size_t)P * V);         // [R][C]
+  float* ssq = ssum + (size_t)R * C;                                    // [R][C]
+  float* part = ssq + (size_t)R * C;                                    // [G][3]: read by the peers
+  float* gmean = part + 3 * G;                                          // [G]
+  float* grstd = gmean + G;                                             // [G]
+  float* scale = grstd + G;                                             // [C]
+  float* shift = scale + C;                                             // [C]
+  const int n = blockIdx.y;
+  const uint32_t rank = gn_cluster_rank(), CL = gridDim.x;
+  const int p0 = (int)rank * P;
+  const int v = threadIdx.x % V, r = threadIdx.x / V;
+  const int c0 = v * 8;
+  const bool second = c0 >= p.C1;
+  const __nv_bfloat16* base = second ? p.x2 + (long long)n * p.HW * p.ld2 + (c0 - p.C1)
+                                     : p.x1 + (long long)n * p.HW * p.ld1 + c0;
+  const long long ld = second ? p.ld2 : p.ld1;
+  float sum[8], sq[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sum[i] = sq[i] = 0.f;
+  constexpr int U = 4;   // global loads in flight per thread
+  int px = r;
+  for (; px + (U - 1) * R < P; px += U * R) {
+    uint4 raw[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) raw[u] = *reinterpret_cast<const uint4*>(base + (long long)(p0 + px + u * R) * ld);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      tile[(size_t)(px + u * R) * V + v] = raw[u];
+      const uint32_t w4[4] = {raw[u].x, raw[u].y, raw[u].z, raw[u].w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 t = unpack_bf16(w4[i]);
+        sum[2 * i] += t.x; sq[2 * i] = fmaf(t.x, t.x, sq[2 * i]);
+        sum[2 * i + 1] += t.y; sq[2 * i + 1] = fmaf(t.y, t.y, sq[2 * i + 1]);
+      }
+    }
+  }
+  for (; px < P; px += R) {
+    const uint4 raw = *reinterpret_cast<const uint4*>(base + (long long)(p0 + px) * ld);
+    tile[(size_t)px * V + v] = raw;
+    const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 t = unpack_bf16(w4[i]);
+      sum[2 * i] += t.x; sq[2 * i] = fmaf(t.x, t.x, sq[2 * i]);
+      sum[2 * i + 1] += t.y; sq[2 * i + 1] = fmaf(t.y, t.y, sq[2 * i + 1]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    ssum[(size_t)r * C + c0 + i] = sum[i];
+    ssq[(size_t)r * C + c0 + i] = sq[i];
+  }
+  __syncthreads();
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {   // this CTA's partial of group g (as gn_stats_body)
+    float a = 0.f, b = 0.f;
+    for (int rr = 0; rr < R; ++rr)
+      for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+        a += ssum[(size_t)rr * C + c];
+        b += ssq[(size_t)rr * C + c];
+      }
+    const float cnt = (float)P * cpg;
+    const float mean = a / cnt;
+    part[3 * g] = cnt;
+    part[3 * g + 1] = mean;
+    part[3 * g + 2] = fmaxf(b - a * mean, 0.f);
+  }
+  gn_cluster_sync();                                    // every CTA's partials are written and visible cluster-wide
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {   // merge the CL partials in rank order (same in every CTA)
+    float cnt = 0.f, mean = 0.f, m2 = 0.f;
+    for (uint32_t k = 0; k < CL; ++k) {
+      const float cb = gn_ld_dsmem(part + 3 * g, k), mb = gn_ld_dsmem(part + 3 * g + 1, k), qb = gn_ld_dsmem(part + 3 * g + 2, k);
+      const float tot = cnt + cb, delta = mb - mean;
+      mean += delta * (cb / tot);
+      m2 += qb + delta * delta * (cnt * cb / tot);
+      cnt = tot;
+    }
+    gmean[g] = mean;
+    grstd[g] = rsqrtf(m2 / cnt + p.eps);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    const float sc = grstd[g] * p.gamma[c];
+    scale[c] = sc;
+    shift[c] = p.beta[c] - gmean[g] * sc;
+  }
+  __syncthreads();
+  float sc[8], sh[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    sc[i] = scale[c0 + i];
+    sh[i] = shift[c0 + i];
+  }
+  __nv_bfloat16* dst = p.out + (long long)n * p.HW * p.ldo + c0;
+  for (int q = r; q < P; q += R) {
+    const uint4 raw = tile[(size_t)q * V + v];
+    const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
+    float f[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 t = unpack_bf16(w4[i]);
+      f[2 * i] = t.x;
+      f[2 * i + 1] = t.y;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float y = fmaf(f[i], sc[i], sh[i]);
+      if (p.silu) {
+        float t;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * y));
+        y = y * fmaf(0.5f, t, 0.5f);
+      }
+      f[i] = y;
+    }
+    store8(dst + (long long)(p0 + q) * p.ldo, f);
+  }
+  gn_cluster_sync();                                    // nobody leaves while a peer may still read its partials
+}
+
 // ------------------------------------------------------------------ LayerNorm (+PE)
 // One warp per row; the row lives in registers (C <= 2048), exact two-pass mean/variance like torch.
 template <int MAXV>
@@ -697,6 +854,62 @@ extern "C" int vx_groupnorm_fused(const void* x1, long long ld1, int C1, const v
   return 0;
 }
 
+// GroupNorm of small frames with the frame resident in the shared memory of a thread-block cluster (gn_cluster_kernel).
+// Returns 2 (and launches nothing) when the frame does not fit a cluster of <= 8 CTAs -- the caller then takes the
+// one-launch rendezvous kernel or the two-kernel pair.
+extern "C" int vx_groupnorm_cluster(const void* x1, long long ld1, int C1, const void* x2, long long ld2, int C2, int NB,
+                                    int HW, int G, const float* gamma, const float* beta, float eps, int silu, void* out,
+                                    long long ldo, void* stream) {
+  const int C = C1 + C2;
+  VX_REQUIRE(C1 % 8 == 0 && C2 % 8 == 0 && C % G == 0 && C / 8 <= 1024, "vx_groupnorm_cluster: bad C1=%d C2=%d G=%d", C1, C2, G);
+  const int V = C / 8;
+  int R = 640 / V;                       // ~640 threads: 4 pixel lanes at C = 1280, 2 at C = 2560
+  if (R < 1) R = 1;
+  while (V * R > 1024) --R;
+  const int threads = V * R;
+  const size_t fixed = ((size_t)2 * R * C + 5 * (size_t)G + 2 * (size_t)C) * sizeof(float);
+  int CL = 0;
+  for (int cl = 1; cl <= 8; cl *= 2) {
+    if (HW % cl) break;
+    const size_t need = (size_t)(HW / cl) * C * 2 + fixed;
+    if (need <= (size_t)200 * 1024) {
+      CL = cl;
+      break;
+    }
+  }
+  // One wave only: with more clusters than the device holds at once (the 16x16 level needs 8 CTAs x 32 frames at one CTA per
+  // SM) the second wave costs more than the rendezvous kernel's second (L2) read: 27.7 -> 43.6 us; at the 8x8 level the
+  // resident frame wins, 23.7 -> 14.9 us (gpurun_out/r02_c32_gn_timing.txt).
+  if (!CL || (long long)NB * CL > 148) return 2;
+  // more, smaller chunks while the whole grid still is one wave: every SM pulls its chunk at its own (latency-bound) rate
+  while (CL * 2 <= 8 && (long long)NB * CL * 2 <= 148 && HW % (CL * 2) == 0 && HW / (CL * 2) >= R) CL *= 2;
+  GnClusterArgs a{(const __nv_bfloat16*)x1, ld1, C1, (const __nv_bfloat16*)x2, ld2, C2, HW, G, HW / CL, R, gamma, beta, eps, silu,
+                  (__nv_bfloat16*)out, ldo};
+  const size_t smem = (size_t)(HW / CL) * C * 2 + fixed;
+  static bool configured = false;
+  if (!configured) {
+    VX_CHECK_CUDA(cudaFuncSetAttribute(gn_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(CL, NB);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  VX_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gn_cluster_kernel, a));
+  VX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // pe: optional float [pe_frames, C]; row r uses pe[(r / rows_per_frame) % pe_frames]
 extern "C" int vx_layernorm(const void* x, long long ldx, long long rows, int C, const float* gamma,
                             const float* beta, float eps, const float* pe, int rows_per_frame, int pe_frames,
@@ -707,9 +920,11 @@ extern "C" int vx_layernorm(const void* x, long long ldx, long long rows, int C,
   const int V = C / 8;
   auto st = (cudaStream_t)stream;
   if (pe && (rows_per_frame <= 0 || pe_frames <= 0)) return fail("vx_layernorm: bad pe args");
-  // (with a positional-encoding row to fetch per row the one-warp-per-row kernel, with its 8x occupancy, is as fast)
+  // The positional-encoding variant (temporal attention norms) takes the same kernel since its parameters moved to shared
+  // memory: 63.5 -> ~41 us at the 320-wide level (the one-warp-per-row kernel used to be as fast).  VX_LN_PE5=0: old choice.
   static const bool ln_v1 = getenv("VX_LN_V1") != nullptr;   // A/B switch, read once
-  if ((C == 320 || C == 640 || C == 1280) && !pe && ldx % 8 == 0 && ldo % 8 == 0 && !ln_v1) {
+  static const bool ln_pe5 = !(getenv("VX_LN_PE5") && atoi(getenv("VX_LN_PE5")) == 0);
+  if ((C == 320 || C == 640 || C == 1280) && (!pe || ln_pe5) && ldx % 8 == 0 && ldo % 8 == 0 && !ln_v1) {
     const int lpr = C / 40;
     const long long groups = (rows + 32 / lpr - 1) / (32 / lpr);
     long long nb = ((groups + 1) / 2 + 7) / 8;

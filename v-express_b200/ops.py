@@ -363,6 +363,7 @@ def _gn_S(NB, HW, C=0):
 
 
 _GN_FUSED = os.environ.get("VX_GN_FUSED", "1") != "0"
+_GN_CLUSTER = os.environ.get("VX_GN_CLUSTER", "1") != "0"   # cluster-resident GroupNorm for small frames (0: A/B switch)
 _GN_COUNTERS = {}
 
 
@@ -387,13 +388,20 @@ def groupnorm(x1, NB, HW, gamma, beta, eps, silu, x2=None, groups=32, out=None, 
     _chk_bf16(x1, x2, out)
     C1 = x1.shape[1]
     C2 = 0 if x2 is None else x2.shape[1]
-    S = _gn_S(NB, HW, C1 + C2)
-    if ws is None:
-        ws = torch.empty(NB * S * groups * 3, device=x1.device, dtype=torch.float32)
     if out is None:
         out = torch.empty((NB * HW, C1 + C2), device=x1.device, dtype=BF16)
     L = _ffi.lib()
     ld2 = c_ll(0 if x2 is None else x2.stride(0))
+    if _GN_CLUSTER:                     # small frames: resident in a cluster's shared memory, one pass over HBM
+        rc = L.vx_groupnorm_cluster(ptr(x1), c_ll(x1.stride(0)), c_int(C1), ptr(x2), ld2, c_int(C2), c_int(NB), c_int(HW),
+                                    c_int(groups), ptr(gamma), ptr(beta), c_float(eps), c_int(int(silu)), ptr(out),
+                                    c_ll(out.stride(0)), stream_ptr())
+        if rc != 2:                     # 2 = the frame does not fit a cluster
+            check(rc, "vx_groupnorm_cluster")
+            return out
+    S = _gn_S(NB, HW, C1 + C2)
+    if ws is None:
+        ws = torch.empty(NB * S * groups * 3, device=x1.device, dtype=torch.float32)
     if _GN_FUSED:
         rc = L.vx_groupnorm_fused(ptr(x1), c_ll(x1.stride(0)), c_int(C1), ptr(x2), ld2, c_int(C2), c_int(NB), c_int(HW),
                                   c_int(groups), c_int(S), ptr(ws), ptr(_gn_counters(x1.device, NB)), ptr(gamma), ptr(beta),
