@@ -1008,3 +1008,37 @@ def test_boundary_signatures_match_reference(ref_file, cls, fn, spec):
         assert _same_default(d_ref, d_our), (fn, n, d_ref, d_our)
     for n, d in ours[len(ref):]:
         assert n.startswith("**") or d != "<required>", f"{fn}: extra parameter {n} must be optional"
+
+
+def test_downsample_conv_dispatch(monkeypatch):
+    """ops.downsample_conv: stride-2 convs go to the TMA traversal-stride kernel when the channel count allows 64-wide K
+    blocks, otherwise (and under VX_CONV_S2=0) to the gathered im2col + GEMM path, with the padding variant passed on."""
+    from vexpress_b200 import ops
+    calls = []
+    monkeypatch.setattr(ops, "conv3x3_s2", lambda x, w, b, pad_lo=1: calls.append(("s2", tuple(x.shape), pad_lo)) or "s2")
+    monkeypatch.setattr(ops, "im2col_s2", lambda x, NB, H, W: calls.append(("im2col_s2", tuple(x.shape))) or "col")
+    monkeypatch.setattr(ops, "im2col3x3", lambda x, NB, H, W, stride=1, pad_lo=1: calls.append(("im2col3x3", stride, pad_lo)) or "col")
+    monkeypatch.setattr(ops, "gemm", lambda col, w, b: calls.append(("gemm", col)) or "gemm")
+    x = torch.zeros(2 * 8 * 8, 128)
+    monkeypatch.setattr(ops, "CONV_S2_TMA", True)
+    assert ops.downsample_conv(x, 2, 8, 8, "w", "b") == "s2" and calls[-1] == ("s2", (2, 8, 8, 128), 1)
+    assert ops.downsample_conv(x, 2, 8, 8, "w", "b", pad_lo=0) == "s2" and calls[-1] == ("s2", (2, 8, 8, 128), 0)
+    x32 = torch.zeros(2 * 8 * 8, 32)                       # C % 64 != 0: gathered path
+    calls.clear()
+    assert ops.downsample_conv(x32, 2, 8, 8, "w", "b") == "gemm" and [c[0] for c in calls] == ["im2col_s2", "gemm"]
+    calls.clear()
+    assert ops.downsample_conv(x32, 2, 8, 8, "w", "b", pad_lo=0) == "gemm" and calls[0] == ("im2col3x3", 2, 0)
+    monkeypatch.setattr(ops, "CONV_S2_TMA", False)          # A/B switch off
+    calls.clear()
+    assert ops.downsample_conv(x, 2, 8, 8, "w", "b") == "gemm" and calls[0][0] == "im2col_s2"
+
+
+def test_rowsum_slot_capacity():
+    """The producer GEMM of the LayerNorm statistics hand-over writes 2 * ceil(N / block_n) partials per row with
+    block_n >= 32: ops.rowsum_slots must cover the narrowest tile the library may pick."""
+    from vexpress_b200 import ops
+    for N in (64, 320, 640, 1280, 96):
+        assert ops.rowsum_slots(N) == 2 * -(-N // 32)
+        for bn in (32, 64, 96, 128, 160, 192, 256):
+            if N % bn == 0:
+                assert 2 * (N // bn) <= ops.rowsum_slots(N)
