@@ -29,7 +29,7 @@ __device__ __forceinline__ bool elect_one() {
 // completed and flushed.  pdl_trigger: this CTA no longer holds back the LAUNCH of the next grid (whose own pdl_wait still
 // orders the data).  Placement matters: a grid triggered at its first instruction lets the successor's CTAs become
 // resident next to the still-running CTAs wherever registers / shared memory allow, and they sit in pdl_wait for the
-// whole kernel -- measured SLOWER than no PDL at all (UNet 56.5 vs 55.2 ms, VAE 45.3 vs 42.1 ms, gpurun_out/r02_c21).  So
+// whole kernel -- measured SLOWER than no PDL at all (UNet 56.5 vs 55.2 ms, VAE 45.3 vs 42.1 ms, profiles/r02_ab_bench_lines.txt).  So
 // only the long persistent kernels trigger, and late: when their MMA warp has issued the last tile, i.e. one epilogue
 // before the CTA exits; everything else triggers implicitly at exit.  Both are no-ops under ordinary stream serialisation.
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }

@@ -426,14 +426,14 @@ class UNetEngine:
         ops.fold_layernorm), so LayerNorm(x) is never written to HBM.
         The one-kernel variant (ops.gemm_ln: row tile resident in shared memory, statistics computed in the kernel) passes
         its operator tests but measured SLOWER than LayerNorm kernel + GEMM at the 320-wide level (379 vs 44 + 250 us for
-        norm3 -> FF1, gpurun_out/r02_c21) and is not wired into the engine."""
+        norm3 -> FF1, profiles/r02_ab_bench_lines.txt) and is not wired into the engine."""
         self.ln_fold = os.environ.get("VX_LN_FOLD") == "1"
         # VX_LN_FUSE=1 (experiment, measured: parity green, SLOWER -- stays off): statistics hand-over.  Every LayerNorm
         # input is the output of a Linear (+ residual); that GEMM's epilogue emits per-row partial sums (ops.gemm_rowsums),
         # the consumer GEMM normalises in its epilogue (ops.gemm_lnparts): no LayerNorm kernel, no statistics kernel,
         # LayerNorm(x) never written.  The normalising epilogue costs more than the LayerNorm kernel it removes: the K = 320
         # / 640 GEMMs are bound by their epilogues' instruction issue (QKV 117 + 43 us -> 180 us, FF1 267 + 43 -> 383 us;
-        # UNet 54.9 -> 56.6 ms per step, gpurun_out/r02_c25).
+        # UNet 54.9 -> 56.6 ms per step, profiles/r02_ab_bench_lines.txt).
         self.ln_fuse = os.environ.get("VX_LN_FUSE", "0") != "0" and not self.ln_fold
         self.F: Dict[str, tuple] = {}
         self._pe_proj: Dict[str, torch.Tensor] = {}
