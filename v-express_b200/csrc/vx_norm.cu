@@ -879,7 +879,7 @@ extern "C" int vx_groupnorm_cluster(const void* x1, long long ld1, int C1, const
   }
   // One wave only: with more clusters than the device holds at once (the 16x16 level needs 8 CTAs x 32 frames at one CTA per
   // SM) the second wave costs more than the rendezvous kernel's second (L2) read: 27.7 -> 43.6 us; at the 8x8 level the
-  // resident frame wins, 23.7 -> 14.9 us (gpurun_out/r02_c32_gn_timing.txt).
+  // resident frame wins, 23.7 -> 14.9 us (profiles/r02_gn_cluster_timing.txt).
   if (!CL || (long long)NB * CL > 148) return 2;
   // more, smaller chunks while the whole grid still is one wave: every SM pulls its chunk at its own (latency-bound) rate
   while (CL * 2 <= 8 && (long long)NB * CL * 2 <= 148 && HW % (CL * 2) == 0 && HW / (CL * 2) >= R) CL *= 2;
