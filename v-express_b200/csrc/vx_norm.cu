@@ -623,7 +623,6 @@ __global__ void __launch_bounds__(256, MINB) layernorm5_kernel(const __nv_bfloat
       for (int i = 0; i < 5; ++i) {
         const uint32_t w4[4] = {u[r][i].x, u[r][i].y, u[r][i].z, u[r][i].w};
         float y[8];
-#pragma unroll
         int c = (l + i * LPR) * 8;
         asm volatile("" : "+r"(c));     // opaque to the optimiser: or it hoists all 80 parameter loads out of the row loop again
         const float4 g0 = *reinterpret_cast<const float4*>(sg + c), g1 = *reinterpret_cast<const float4*>(sg + c + 4);
